@@ -1,0 +1,141 @@
+/*
+ * mkd_b200.h — C-ABI of the B200-native MakeupDiffuse denoising hot path (libmkd_b200.so).
+ *
+ * The reference (jiean001/MakeupDiffuse) has no native layer and no FFI: its "plugin API" for this path is
+ * Python duck typing:
+ *     sampler  -> model.apply_model(x_noisy, t, cond)                      diffmk/cddim.py:16,39
+ *     apply_model -> control_model(x=, hint=, timesteps=, context=)        diffmk/makeup_diffuse.py:164-165
+ *                 -> diffusion_model(x=, timesteps=, context=, control=..) diffmk/makeup_diffuse.py:167-168
+ * and underneath that everything is a PyTorch library call.  The entry points below are what a binding for
+ * that path binds instead of those library calls: one per kernel family.  Each comment names the reference
+ * operation (file:line, or the upstream lllyasviel/ControlNet op reached from the cited call site) it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers owned by the caller;
+ *   - activations are NHWC ("pixel-major"): element (n,h,w,c) at ((n*H+h)*W+w)*ld + c, ld >= C;
+ *   - `dtype` selects the storage type of activations/weights: MKD_BF16 (production) or MKD_F32
+ *     (the fp32 check mode of BASELINE.json north_star); accumulation/statistics are always fp32;
+ *     biases, norm gammas/betas and DDIM latents are always fp32;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing, retains no pointer,
+ *     never synchronises the device and is CUDA-graph capturable;
+ *   - return value: 0 = ok, negative = error (see MKD_E_*); mkd_last_error() gives a thread-local message.
+ *     There is no CPU fallback and no other backend: a wrong architecture is MKD_E_ARCH.
+ */
+#ifndef MKD_B200_H
+#define MKD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKD_ABI_VERSION 1
+
+typedef void* mkd_stream_t; /* cudaStream_t */
+
+enum { MKD_BF16 = 0, MKD_F32 = 1 };
+enum { MKD_OK = 0, MKD_E_INVALID = -1, MKD_E_ALIGN = -2, MKD_E_ARCH = -3, MKD_E_CUDA = -4, MKD_E_WORKSPACE = -5 };
+enum { MKD_ACT_NONE = 0, MKD_ACT_SILU = 1, MKD_ACT_GEGLU = 2 };
+enum { MKD_PATH_AUTO = 0, MKD_PATH_GENERIC = 1, MKD_PATH_TCGEN05 = 2 };
+
+/* ---- probes ------------------------------------------------------------------------------------------- */
+int mkd_abi_version(void);          /* == MKD_ABI_VERSION */
+int mkd_compiled_arch(void);        /* 100 : built for sm_100a only */
+int mkd_device_ok(int device);      /* 0 if `device` is compute capability 10.0, else MKD_E_ARCH */
+const char* mkd_last_error(void);
+
+/* ---- DDIM x_t -> x_{t-1} update incl. classifier-free-guidance combine -----------------------------------
+ * replaces diffmk/cddim.py:39-40 (CFG combine), :56-63 (coefficients, pred_x0), :74-78 (dir_xt, noise, x_prev).
+ *   e       = cfg ? eps[0:n] + cfg_scale * (eps[n:2n] - eps[0:n]) : eps[0:n]       ([uncond; cond] order)
+ *   pred_x0 = (x - sqrt_one_minus_at * e) / sqrt_at
+ *   x_prev  = sqrt_a_prev * pred_x0 + dir_coef * e + (sigma_t * noise) * temperature   (noise may be NULL)
+ * Every product/sum is rounded separately (no FMA contraction) so the result is bit-identical to the
+ * reference's op-by-op fp32 PyTorch arithmetic.  pred_x0 may be NULL. x_prev may alias x. */
+int mkd_ddim_update(const float* x, const float* eps, int cfg, float cfg_scale, const float* noise,
+                    float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef, float sigma_t,
+                    float temperature, float* x_prev, float* pred_x0, int64_t n, mkd_stream_t stream);
+
+/* ---- layout / small elementwise ---------------------------------------------------------------------------
+ * NCHW fp32 (the reference boundary layout, makeup_diffuse.py:152) <-> NHWC working layout. */
+int mkd_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int C, int H, int W, int ld_dst,
+                     mkd_stream_t stream);
+int mkd_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, int C, int H, int W, int ld_src,
+                     mkd_stream_t stream);
+/* upstream timestep_embedding(): out[b, :] = [cos(t_b f_k), sin(t_b f_k)], optionally followed by nothing. */
+int mkd_timestep_embedding(const int64_t* t, void* out, int dtype, int B, int dim, float max_period,
+                           mkd_stream_t stream);
+/* y = silu(x) on n contiguous elements (ResBlock emb_layers.0, time_embed.1). */
+int mkd_silu(const void* x, void* y, int dtype, int64_t n, mkd_stream_t stream);
+/* GEGLU (upstream ldm.modules.attention.GEGLU): y[m, j] = x[m, j] * gelu_erf(x[m, inner + j]). */
+int mkd_geglu(const void* x, void* y, int dtype, int64_t M, int inner, int ldx, int ldy, mkd_stream_t stream);
+/* y[m, c] = a[m, c] + b[m, c]  (ControlNet: h = input_blocks[0](x) + guided_hint, when not fused). */
+int mkd_add(const void* a, const void* b, void* y, int dtype, int64_t M, int C, int lda, int ldb, int ldy,
+            mkd_stream_t stream);
+
+/* ---- GroupNorm(32 groups) [+ SiLU], NHWC -------------------------------------------------------------------
+ * replaces upstream GroupNorm32/GroupNorm + SiLU at ResBlock.in_layers/out_layers, SpatialTransformer.norm,
+ * UNet.out (reached from makeup_diffuse.py:164-168).  Statistics in fp32 over (C/groups * HW) per sample.
+ * workspace: >= mkd_groupnorm_workspace_bytes(N, groups) bytes, fp32-aligned. */
+size_t mkd_groupnorm_workspace_bytes(int N, int groups);
+int mkd_groupnorm(const void* x, void* y, int dtype, int N, int HW, int C, int groups, int ldx, int ldy,
+                  const float* gamma, const float* beta, float eps, int silu, void* workspace,
+                  size_t workspace_bytes, mkd_stream_t stream);
+
+/* ---- LayerNorm over the last dim (BasicTransformerBlock.norm1/2/3) ---------------------------------------- */
+int mkd_layernorm(const void* x, void* y, int dtype, int64_t M, int C, int ldx, int ldy, const float* gamma,
+                  const float* beta, float eps, mkd_stream_t stream);
+
+/* ---- convolution / GEMM family --------------------------------------------------------------------------
+ * One descriptor covers every contraction of the path: ResBlock 3x3 convs, Down (stride 2) / Up (nearest x2
+ * then 3x3) convs, hint-block convs, 1x1 convs, Linear layers (H=1, W=M, R=S=1) and ControlNet zero-convs:
+ *
+ *   acc[n,p,q,k] = sum_{r,s,c} X[n, p*stride - pad + r, q*stride - pad + s, c] * Wt[k, r, s, c]      (fp32)
+ *   v            = alpha * (acc + bias[k] + emb[n, k]) + residual[n,p,q,k]
+ *   Y[n,p,q,k]   = act(v)
+ *
+ *   bias / emb / residual may be NULL.  `residual == y` (same pointer, ldr == ldy) is the fused ControlNet
+ *   injection  hs[i] += scale_i * zero_conv_i(h)  of makeup_diffuse.py:166 + upstream `hs.pop() + control.pop()`.
+ *   `y` / `x` may point into a wider buffer (ld > channels): that is how skip tensors are produced straight
+ *   into the decoder's concat buffers (upstream torch.cat([h, hs.pop()], 1)).
+ *   act == MKD_ACT_GEGLU: Wt/bias hold K = 2*Ko rows arranged in blocks of 2*geglu_block rows
+ *   (geglu_block value rows, then the geglu_block matching gate rows); Y has Ko channels:
+ *   Y = v_value * gelu_erf(v_gate).  alpha/emb/residual must be unused.
+ *   upsample == 1: X is first nearest-neighbour upsampled x2 (H, W are the *stored* input sizes).
+ *   Weights: [K][R][S][C] ("KRSC"), dtype as activations, row pitch R*S*C elements.
+ *   path: MKD_PATH_AUTO picks the tcgen05/TMA kernel when dtype == bf16 and the shape qualifies
+ *   (mkd_conv2d_path tells which), else the generic kernel; the other two values force a kernel (tests). */
+typedef struct mkd_conv_desc {
+  int dtype;
+  int N, H, W, C; /* input  */
+  int K, R, S;    /* filter */
+  int stride, pad, upsample;
+  int ldx, ldy, ldr, lde; /* element strides: input pixel, output pixel, residual pixel, emb row */
+  int act, geglu_block;
+  int path;
+  float alpha;
+  const void* x;
+  const void* w;
+  void* y;
+  const float* bias;
+  const void* emb; /* [N, lde] activations dtype */
+  const void* residual;
+  void* workspace; /* split-K partials (tcgen05 path); may be NULL -> no split-K */
+  size_t workspace_bytes;
+} mkd_conv_desc;
+
+int mkd_conv2d(const mkd_conv_desc* d, mkd_stream_t stream);
+int mkd_conv2d_path(const mkd_conv_desc* d); /* MKD_PATH_GENERIC or MKD_PATH_TCGEN05, or <0 on invalid desc */
+
+/* ---- attention (SpatialTransformer attn1 self / attn2 cross; upstream CrossAttention.forward) -------------
+ *   O[b, i, h*d:(h+1)*d] = softmax_j( scale * <Q[b,i,h], K[b,j,h]> ) V[b,j,h]      softmax in fp32
+ * Q rows: q + (b*Nq + i)*ldq + h*d ; K/V rows: k + (b*Nkv + j)*ldk + h*d (so q/k/v may be column slices of one
+ * fused projection buffer).  d % 8 == 0, d <= 160. */
+int mkd_attention(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads, int Nq,
+                  int Nkv, int d, int ldq, int ldk, int ldv, int ldo, float scale, mkd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MKD_B200_H */

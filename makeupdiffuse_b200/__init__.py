@@ -1,0 +1,14 @@
+"""makeupdiffuse_b200 — B200-native (sm_100a) implementation of MakeupDiffuse's denoising hot path.
+
+Public surface (mirrors the reference's):
+    B200DDIMSampler      <->  diffmk.cddim.MKDDIMSampler / ldm DDIMSampler
+    B200ControlLDM       <->  the ControlLDM object the sampler calls apply_model(x_t, t, cond) on
+    B200ControlNet       <->  cldm.cldm.ControlNet            (yaml control_stage_config target)
+    B200ControlledUnet   <->  cldm.cldm.ControlledUnetModel   (yaml unet_config target)
+Everything computes through libmkd_b200.so (include/mkd_b200.h); there is no CPU or PyTorch-compute fallback.
+"""
+from .ldm import B200ControlLDM  # noqa: F401
+from .nets import B200ControlNet, B200ControlledUnet  # noqa: F401
+from .sampler import B200DDIMSampler  # noqa: F401
+
+__all__ = ["B200DDIMSampler", "B200ControlLDM", "B200ControlNet", "B200ControlledUnet"]

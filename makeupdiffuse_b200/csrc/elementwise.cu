@@ -1,0 +1,235 @@
+// Probes, the fused DDIM update (+CFG) kernel, layout conversion and the small elementwise kernels.
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mkd {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace mkd
+using namespace mkd;
+
+extern "C" int mkd_abi_version(void) { return MKD_ABI_VERSION; }
+extern "C" int mkd_compiled_arch(void) { return 100; }
+extern "C" const char* mkd_last_error(void) { return mkd::g_err; }
+extern "C" int mkd_device_ok(int device) {
+  cudaDeviceProp p;
+  cudaError_t e = cudaGetDeviceProperties(&p, device);
+  MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+  MKD_REQUIRE(p.major == 10 && p.minor == 0, MKD_E_ARCH,
+              "device %d is sm_%d%d; libmkd_b200 is built for sm_100a (B200) only and has no fallback", device,
+              p.major, p.minor);
+  return MKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DDIM update.  Latents are tiny (4096 floats per 256^2 sample): the point of the kernel is ONE launch
+// instead of ~12 ATen kernels + 4 torch.full + a cat/chunk per step, and exact fp32 op-by-op rounding.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps, int cfg,
+                                   float cfg_scale, const float* __restrict__ noise, float s1m, float sqrt_at,
+                                   float sqrt_ap, float dirc, float sigma, float temp, float* __restrict__ x_prev,
+                                   float* __restrict__ pred_x0, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float e = eps[i];
+    if (cfg) {
+      float ec = eps[n + i];
+      e = __fadd_rn(e, __fmul_rn(cfg_scale, __fsub_rn(ec, e)));  // e_u + s * (e_c - e_u)   cddim.py:40
+    }
+    float xv = x[i];
+    float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(s1m, e)), sqrt_at);  // cddim.py:63
+    float xp = __fadd_rn(__fmul_rn(sqrt_ap, p0), __fmul_rn(dirc, e));  // cddim.py:74,78
+    if (noise) xp = __fadd_rn(xp, __fmul_rn(__fmul_rn(sigma, noise[i]), temp));  // cddim.py:75,78
+    if (pred_x0) pred_x0[i] = p0;
+    x_prev[i] = xp;
+  }
+}
+
+extern "C" int mkd_ddim_update(const float* x, const float* eps, int cfg, float cfg_scale, const float* noise,
+                               float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef,
+                               float sigma_t, float temperature, float* x_prev, float* pred_x0, int64_t n,
+                               mkd_stream_t stream) {
+  MKD_REQUIRE(x && eps && x_prev && n >= 0, MKD_E_INVALID, "ddim_update: null pointer or negative n");
+  if (n == 0) return MKD_OK;
+  int threads = 256;
+  int blocks = (int)((n + threads - 1) / threads);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ddim_update_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(x, eps, cfg, cfg_scale, noise, sqrt_one_minus_at,
+                                                                   sqrt_at, sqrt_a_prev, dir_coef, sigma_t,
+                                                                   temperature, x_prev, pred_x0, n);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC T through a 32x32 smem transpose tile (coalesced on both sides).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int ld) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? src[((int64_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    if (p < HW && c < C) dst[((int64_t)n * HW + p) * ld + c] = from_f<T>(tile[threadIdx.x][j]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW, int ld) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < HW && c < C) ? to_f(src[((int64_t)n * HW + p) * ld + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[((int64_t)n * C + c) * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+extern "C" int mkd_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int C, int H, int W, int ld_dst,
+                                mkd_stream_t stream) {
+  MKD_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && ld_dst >= C, MKD_E_INVALID, "nchw_to_nhwc: bad args");
+  MKD_REQUIRE(N <= 65535, MKD_E_INVALID, "nchw_to_nhwc: N too large");
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  if (dtype == MKD_BF16)
+    nchw_to_nhwc_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, C, H * W, ld_dst);
+  else
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, (float*)dst, C, H * W, ld_dst);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+extern "C" int mkd_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, int C, int H, int W, int ld_src,
+                                mkd_stream_t stream) {
+  MKD_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && ld_src >= C, MKD_E_INVALID, "nhwc_to_nchw: bad args");
+  MKD_REQUIRE(N <= 65535, MKD_E_INVALID, "nhwc_to_nchw: N too large");
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  if (dtype == MKD_BF16)
+    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, C, H * W, ld_src);
+  else
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, dst, C, H * W, ld_src);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, T* __restrict__ out, int B, int dim,
+                                          float neg_log_mp) {
+  int half = dim / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
+    int b = i / half, k = i % half;
+    float f = expf(neg_log_mp * (float)k / (float)half);
+    float a = (float)t[b] * f;
+    out[(int64_t)b * dim + k] = from_f<T>(cosf(a));
+    out[(int64_t)b * dim + half + k] = from_f<T>(sinf(a));
+    if ((dim & 1) && k == 0) out[(int64_t)b * dim + dim - 1] = from_f<T>(0.f);
+  }
+}
+extern "C" int mkd_timestep_embedding(const int64_t* t, void* out, int dtype, int B, int dim, float max_period,
+                                      mkd_stream_t stream) {
+  MKD_REQUIRE(t && out && B > 0 && dim >= 2, MKD_E_INVALID, "timestep_embedding: bad args");
+  int n = B * (dim / 2), threads = 128, blocks = (n + threads - 1) / threads;
+  float nl = -logf(max_period);
+  if (dtype == MKD_BF16)
+    timestep_embedding_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>(t, (bf16*)out, B, dim, nl);
+  else
+    timestep_embedding_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(t, (float*)out, B, dim, nl);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void silu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = from_f<T>(silu_f(to_f(x[i])));
+}
+extern "C" int mkd_silu(const void* x, void* y, int dtype, int64_t n, mkd_stream_t stream) {
+  MKD_REQUIRE(x && y && n >= 0, MKD_E_INVALID, "silu: bad args");
+  if (n == 0) return MKD_OK;
+  int threads = 256, blocks = (int)((n + threads - 1) / threads);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dtype == MKD_BF16)
+    silu_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n);
+  else
+    silu_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, n);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+// GEGLU, 8 channels per thread (16-byte bf16 vectors).
+template <typename T>
+__global__ void geglu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t M, int inner, int ldx, int ldy) {
+  int vpr = inner / 8;
+  int64_t total = M * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = i / vpr;
+    int c = (int)(i % vpr) * 8;
+    float a[8], g[8];
+    load8(x + m * ldx + c, a);
+    load8(x + m * ldx + inner + c, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= gelu_erf_f(g[j]);
+    store8(y + m * ldy + c, a);
+  }
+}
+extern "C" int mkd_geglu(const void* x, void* y, int dtype, int64_t M, int inner, int ldx, int ldy,
+                         mkd_stream_t stream) {
+  MKD_REQUIRE(x && y && M > 0 && inner > 0, MKD_E_INVALID, "geglu: bad args");
+  MKD_REQUIRE(inner % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), MKD_E_ALIGN,
+              "geglu: inner/ld must be multiples of 8 and pointers 16B aligned");
+  int64_t total = M * (inner / 8);
+  int threads = 256, blocks = (int)((total + threads - 1) / threads);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == MKD_BF16)
+    geglu_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, M, inner, ldx, ldy);
+  else
+    geglu_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, M, inner, ldx, ldy);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t M, int C,
+                           int lda, int ldb, int ldy) {
+  int vpr = C / 8;
+  int64_t total = M * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = i / vpr;
+    int c = (int)(i % vpr) * 8;
+    float u[8], v[8];
+    load8(a + m * lda + c, u);
+    load8(b + m * ldb + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] += v[j];
+    store8(y + m * ldy + c, u);
+  }
+}
+extern "C" int mkd_add(const void* a, const void* b, void* y, int dtype, int64_t M, int C, int lda, int ldb, int ldy,
+                       mkd_stream_t stream) {
+  MKD_REQUIRE(a && b && y && M > 0 && C > 0, MKD_E_INVALID, "add: bad args");
+  MKD_REQUIRE(C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldy % 8 == 0 && aligned16(a) && aligned16(b) && aligned16(y),
+              MKD_E_ALIGN, "add: C/ld must be multiples of 8 and pointers 16B aligned");
+  int64_t total = M * (C / 8);
+  int threads = 256, blocks = (int)((total + threads - 1) / threads);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == MKD_BF16)
+    add_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)y, M, C, lda, ldb, ldy);
+  else
+    add_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)a, (const float*)b, (float*)y, M, C, lda, ldb, ldy);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}

@@ -1,0 +1,231 @@
+// GroupNorm(+SiLU) and LayerNorm on NHWC activations: bandwidth kernels.
+//   - every global access is a 16-byte (bf16) / 32-byte (fp32) vector of 8 consecutive channels, so a warp reads
+//     512 contiguous bytes of a pixel row;
+//   - statistics are fp32; the cross-thread reductions are warp shuffles + one small smem pass;
+//   - GroupNorm runs as two launches (per-chunk partial sums -> normalise[+SiLU]); the second read of x is served
+//     by the 126 MB L2 for every tensor of the 256^2 / batch-16 workload (largest: 16*1024*960*2 B = 31 MB).
+#include "common.cuh"
+using namespace mkd;
+
+namespace {
+constexpr int GN_MAX_CHUNKS = 64;  // pixel chunks per sample (partials reduced by the apply kernel)
+
+// One thread owns 8 consecutive channels (vector column vx) and walks rows ry, ry+RY, ...
+// partial[n][chunk][g] = (sum, sumsq) over the chunk's rows and the group's channels.
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partial, int HW, int C, int groups,
+                                int ldx, int rows_per_chunk, int nchunks) {
+  extern __shared__ float sm[];  // [2][RY][C]
+  const int VX = C / 8, RY = blockDim.x / VX;
+  const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (ry < RY) {
+    const T* base = x + (int64_t)n * HW * ldx + vx * 8;
+    for (int r = r0 + ry; r < r1; r += RY) {
+      float v[8];
+      load8(base + (int64_t)r * ldx, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] += v[j] * v[j];
+      }
+    }
+    float* ss = sm + (int64_t)ry * C + vx * 8;
+    float* qq = sm + (int64_t)(RY + ry) * C + vx * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ss[j] = s[j];
+      qq[j] = q[j];
+    }
+  }
+  __syncthreads();
+  // warp w reduces groups w, w+nwarps, ...: lanes stride over the RY*cg values of the group
+  const int cg = C / groups, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < groups; g += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int i = lane; i < RY * cg; i += 32) {
+      int r = i / cg, c = g * cg + i % cg;
+      a += sm[(int64_t)r * C + c];
+      b += sm[(int64_t)(RY + r) * C + c];
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) partial[((int64_t)n * nchunks + chunk) * groups + g] = make_float2(a, b);
+  }
+}
+
+template <typename T, bool SILU>
+__global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float2* __restrict__ partial,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
+                                int groups, int ldx, int ldy, int rows_per_chunk, int nchunks, float eps) {
+  extern __shared__ float sm[];  // scale[C], shift[C]
+  float* scale = sm;
+  float* shift = sm + C;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int cg = C / groups;
+  const float inv_cnt = 1.0f / ((float)cg * (float)HW);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cg;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < nchunks; ++k) {
+      float2 p = partial[((int64_t)n * nchunks + k) * groups + g];
+      a += p.x;
+      b += p.y;
+    }
+    float mean = a * inv_cnt;
+    float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+    float rstd = rsqrtf(var + eps);
+    float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+  }
+  __syncthreads();
+  const int VX = C / 8, RY = blockDim.x / VX;
+  const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
+  if (ry >= RY) return;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[vx * 8 + j];
+    sh[j] = shift[vx * 8 + j];
+  }
+  const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
+  T* yb = y + (int64_t)n * HW * ldy + vx * 8;
+  for (int r = r0 + ry; r < r1; r += RY) {
+    float v[8];
+    load8(xb + (int64_t)r * ldx, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j] * sc[j] + sh[j];
+      v[j] = SILU ? silu_f(t) : t;
+    }
+    store8(yb + (int64_t)r * ldy, v);
+  }
+}
+
+// LayerNorm: one warp per row, the row lives in registers between the mean and the variance pass
+// (exact two-pass variance, like the reference).  C <= 8 * 32 * LN_VPL.
+constexpr int LN_VPL = 8;
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t M, int C, int ldx, int ldy,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nv = C / 8;
+  float v[LN_VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_VPL; ++i) {
+    int vi = lane + i * 32;
+    if (vi < nv) {
+      load8(x + row * ldx + vi * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_VPL; ++i) {
+    int vi = lane + i * 32;
+    if (vi < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < LN_VPL; ++i) {
+    int vi = lane + i * 32;
+    if (vi < nv) {
+      float g[8], b[8], o[8];
+      load8(gamma + vi * 8, g);
+      load8(beta + vi * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      store8(y + row * ldy + vi * 8, o);
+    }
+  }
+}
+}  // namespace
+
+extern "C" size_t mkd_groupnorm_workspace_bytes(int N, int groups) {
+  return (size_t)N * GN_MAX_CHUNKS * groups * sizeof(float2);
+}
+
+template <typename T>
+static int groupnorm_launch(const T* x, T* y, int N, int HW, int C, int groups, int ldx, int ldy, const float* gamma,
+                            const float* beta, float eps, int silu, float2* partial, cudaStream_t st) {
+  const int VX = C / 8;
+  int threads = VX >= 256 ? VX : (256 / VX) * VX;  // whole number of row lanes
+  threads = ((threads + 31) / 32) * 32;
+  const int RY = threads / VX;
+  // enough CTAs to fill the machine (~4 per SM), at least 2*RY rows per chunk
+  int want = (148 * 4 + N - 1) / N;
+  int nchunks = HW / (2 * RY);
+  if (nchunks > want) nchunks = want;
+  if (nchunks > GN_MAX_CHUNKS) nchunks = GN_MAX_CHUNKS;
+  if (nchunks < 1) nchunks = 1;
+  int rows_per_chunk = (HW + nchunks - 1) / nchunks;
+  nchunks = (HW + rows_per_chunk - 1) / rows_per_chunk;
+  dim3 grid(nchunks, N);
+  size_t sm1 = (size_t)2 * RY * C * sizeof(float), sm2 = (size_t)2 * C * sizeof(float);
+  MKD_REQUIRE(sm1 <= 48 * 1024 && sm2 <= 48 * 1024, MKD_E_INVALID, "groupnorm: C=%d too large", C);
+  gn_stats_kernel<T><<<grid, threads, sm1, st>>>(x, partial, HW, C, groups, ldx, rows_per_chunk, nchunks);
+  MKD_CHECK_LAUNCH();
+  if (silu)
+    gn_apply_kernel<T, true><<<grid, threads, sm2, st>>>(x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
+                                                         rows_per_chunk, nchunks, eps);
+  else
+    gn_apply_kernel<T, false><<<grid, threads, sm2, st>>>(x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
+                                                          rows_per_chunk, nchunks, eps);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+extern "C" int mkd_groupnorm(const void* x, void* y, int dtype, int N, int HW, int C, int groups, int ldx, int ldy,
+                             const float* gamma, const float* beta, float eps, int silu, void* workspace,
+                             size_t workspace_bytes, mkd_stream_t stream) {
+  MKD_REQUIRE(x && y && gamma && beta && workspace && N > 0 && HW > 0 && C > 0 && groups > 0, MKD_E_INVALID,
+              "groupnorm: bad args");
+  MKD_REQUIRE(C % groups == 0 && C % 8 == 0 && C <= 8 * 1024, MKD_E_INVALID,
+              "groupnorm: C=%d must be a multiple of groups=%d and of 8", C, groups);
+  MKD_REQUIRE(N <= 65535, MKD_E_INVALID, "groupnorm: N too large");
+  MKD_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && ldx >= C && ldy >= C, MKD_E_ALIGN,
+              "groupnorm: ld must be a multiple of 8 (>= C) and pointers 16B aligned");
+  MKD_REQUIRE(workspace_bytes >= mkd_groupnorm_workspace_bytes(N, groups), MKD_E_WORKSPACE,
+              "groupnorm: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MKD_BF16)
+    return groupnorm_launch<bf16>((const bf16*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu,
+                                  (float2*)workspace, st);
+  return groupnorm_launch<float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu,
+                                 (float2*)workspace, st);
+}
+
+extern "C" int mkd_layernorm(const void* x, void* y, int dtype, int64_t M, int C, int ldx, int ldy,
+                             const float* gamma, const float* beta, float eps, mkd_stream_t stream) {
+  MKD_REQUIRE(x && y && gamma && beta && M > 0 && C > 0, MKD_E_INVALID, "layernorm: bad args");
+  MKD_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_VPL, MKD_E_INVALID, "layernorm: C=%d must be a multiple of 8, <= %d", C,
+              8 * 32 * LN_VPL);
+  MKD_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta),
+              MKD_E_ALIGN, "layernorm: ld must be a multiple of 8 and pointers 16B aligned");
+  const int warps = 8;
+  int64_t blocks = (M + warps - 1) / warps;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MKD_BF16)
+    layernorm_kernel<bf16><<<(unsigned)blocks, warps * 32, 0, st>>>((const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps);
+  else
+    layernorm_kernel<float><<<(unsigned)blocks, warps * 32, 0, st>>>((const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}

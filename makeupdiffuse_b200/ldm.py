@@ -1,0 +1,123 @@
+"""``B200ControlLDM``: the object the sampler holds as ``self.model`` (SURVEY.md §8(b) levels B1/B2).
+
+It exposes exactly what ``diffmk/cddim.py`` reads off the model — ``apply_model``, ``parameterization``,
+``alphas_cumprod``, ``alphas_cumprod_prev``, ``sqrt_one_minus_alphas_cumprod``, ``num_timesteps``, ``betas``,
+``device`` — plus ``control_model`` / ``model.diffusion_model`` / ``control_scales`` / ``only_mid_control`` with the
+reference's names, so ``apply_model(x_noisy, t, cond)`` keeps the signature and semantics of
+``diffmk/makeup_diffuse.py:152-170``.
+
+What differs is the execution order inside ``apply_model`` (results are identical): UNet encoder first, then the
+ControlNet whose zero-conv epilogues add ``scale_i * residual_i`` into the encoder skip slots, then the UNet decoder.
+Step-invariant work is hoisted and cached per ``cond``: the hint block (independent of x and t, identical for both CFG
+halves because ``uc_cat = c_cat``, diffusion_makeup.py:401) and every cross-attention K/V projection.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .nets import B200ControlNet, B200ControlledUnet
+
+
+class _Wrapper:
+    def __init__(self, unet):
+        self.diffusion_model = unet
+
+
+class B200ControlLDM:
+    def __init__(self, control_params=None, unet_params=None, timesteps=1000, linear_start=0.00085,
+                 linear_end=0.0120, parameterization="eps", only_mid_control=False, scale_factor=0.18215,
+                 dtype=torch.bfloat16, device="cuda"):
+        self.dtype = dtype
+        self._device = torch.device(device)
+        self.control_model = B200ControlNet(dtype=dtype, **(control_params or {}))
+        self.model = _Wrapper(B200ControlledUnet(dtype=dtype, **(unet_params or {})))
+        self.control_scales = [1.0] * 13
+        self.only_mid_control = only_mid_control
+        self.parameterization = parameterization
+        self.scale_factor = scale_factor
+        self.num_timesteps = int(timesteps)
+        # yaml:4-8 `linear` schedule (upstream register_schedule): computed in float64, stored fp32
+        betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=np.float64) ** 2
+        ac = np.cumprod(1.0 - betas, axis=0)
+        f32 = lambda a: torch.tensor(a, dtype=torch.float32, device=self._device)  # noqa: E731
+        self.betas = f32(betas)
+        self.alphas_cumprod = f32(ac)
+        self.alphas_cumprod_prev = f32(np.append(1.0, ac[:-1]))
+        self.sqrt_alphas_cumprod = f32(np.sqrt(ac))
+        self.sqrt_one_minus_alphas_cumprod = f32(np.sqrt(1.0 - ac))
+        self.sqrt_recip_alphas_cumprod = f32(np.sqrt(1.0 / ac))
+        self.sqrt_recipm1_alphas_cumprod = f32(np.sqrt(1.0 / ac - 1))
+        self._cond_cache = {}
+
+    @property
+    def device(self):
+        return self._device
+
+    def load_state_dict(self, sd, strict=True):
+        """upstream prefixes: ``control_model.*`` and ``model.diffusion_model.*`` (runs/train.py:61)"""
+        if self._device.type == "cuda":
+            ops.device_ok(self._device.index or 0)
+        cn = {k: v for k, v in sd.items() if k.startswith("control_model.")}
+        un = {k: v for k, v in sd.items() if k.startswith("model.diffusion_model.")}
+        self.control_model.load_state_dict(cn, strict=strict, prefix="control_model.", device=self._device)
+        self.model.diffusion_model.load_state_dict(un, strict=strict, prefix="model.diffusion_model.", device=self._device)
+        self._cond_cache.clear()
+        return self
+
+    # ---- step-invariant conditioning ------------------------------------------------------------------------
+    @staticmethod
+    def _tkey(t):
+        return None if t is None else (t.data_ptr(), tuple(t.shape), t._version)
+
+    def _prepare(self, cond):
+        ctx_list, cat_list = cond["c_crossattn"], cond["c_concat"]
+        key = (tuple(self._tkey(t) for t in ctx_list), None if cat_list is None else tuple(self._tkey(t) for t in cat_list))
+        hit = self._cond_cache.get("k")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        ctx = ctx_list[0] if len(ctx_list) == 1 else torch.cat(ctx_list, 1)
+        un, cn = self.model.diffusion_model, self.control_model
+        prep = {"kv_unet": un.context_kv(ctx)}
+        if cat_list is not None:
+            hint = cat_list[0] if len(cat_list) == 1 else torch.cat(cat_list, 1)
+            prep["kv_cn"] = cn.context_kv(ctx)
+            prep["hint"] = cn.hint_features(hint)
+        # keep the source tensors alive so data_ptr-based keys cannot be recycled
+        self._cond_cache["k"] = (key, prep, ctx_list, cat_list)
+        return prep
+
+    # ---- diffmk/makeup_diffuse.py:152-170 ---------------------------------------------------------------------
+    def apply_model(self, x_noisy, t, cond, return_all=False, *args, **kwargs):
+        assert isinstance(cond, dict)
+        un, cn = self.model.diffusion_model, self.control_model
+        N, _, H, W = x_noisy.shape
+        prep = self._prepare(cond)
+        t = t.to(torch.int64).contiguous()
+        xin = un._to_nhwc(x_noisy, "x_in")
+        slots = un.encode(xin, t, prep["kv_unet"], N, H, W)
+        if cond["c_concat"] is not None:
+            inject = [None] * 12 + [slots[12]] if self.only_mid_control else slots
+            cn.run(cn._to_nhwc(x_noisy, "x_in"), prep["hint"], t, prep["kv_cn"], N, H, W, inject=inject,
+                   scales=self.control_scales)
+        e = un.decode(prep["kv_unet"], N, H, W)
+        eps = torch.empty(N, un.out_channels, H, W, dtype=torch.float32, device=x_noisy.device)
+        ops.nhwc_to_nchw(e, eps)
+        if not return_all:
+            return eps
+        return eps, self.predict_start_from_noise(x_noisy, t, eps)
+
+    # ---- x_p entry helpers (diffusion_makeup.py:384-389); latent-sized, outside the 50-step loop ---------------
+    @staticmethod
+    def _extract(a, t, x):
+        return a.gather(-1, t).reshape(t.shape[0], *((1,) * (x.dim() - 1)))
+
+    def q_sample(self, x_start, t, noise=None):
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return (self._extract(self.sqrt_alphas_cumprod, t, x_start) * x_start +
+                self._extract(self.sqrt_one_minus_alphas_cumprod, t, x_start) * noise)
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        return (self._extract(self.sqrt_recip_alphas_cumprod, t, x_t) * x_t -
+                self._extract(self.sqrt_recipm1_alphas_cumprod, t, x_t) * noise)

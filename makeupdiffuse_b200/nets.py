@@ -1,0 +1,474 @@
+"""B200 replacements for the two networks ``apply_model`` drives (SURVEY.md §8(b) level B2).
+
+``B200ControlNet`` / ``B200ControlledUnet`` take the same ``params:`` kwargs as ``cldm.cldm.ControlNet`` /
+``cldm.cldm.ControlledUnetModel`` in ``diffmodels/base_diffusion_makeup.yaml:52-84`` and the same keyword call forms as
+``diffmk/makeup_diffuse.py:164-168``:
+
+    control_model(x=, hint=, timesteps=, context=)                         -> list of 13 residuals (NCHW fp32)
+    diffusion_model(x=, timesteps=, context=, control=, only_mid_control=) -> eps (NCHW fp32)
+
+so they are installed by pointing the yaml's two ``target:`` strings at them.  ``load_state_dict`` accepts upstream
+checkpoint keys (``input_blocks.1.0.in_layers.2.weight`` ...) and repacks once: OIHW fp32 -> KRSC bf16, fused q/k/v
+and cross k/v projection matrices, GEGLU rows interleaved for the fused epilogue.
+
+Everything below the Python orchestration is a hand-written sm_100a kernel behind the C-ABI (ops.py): activations
+are NHWC bf16 (fp32 in check mode), skip tensors are produced directly into the decoder's concat buffers, and the
+fused path (``inject=`` / ``B200ControlLDM.apply_model``) lets the ControlNet zero-conv GEMM epilogues accumulate
+into those skip slots, so ``hs.pop() + control.pop()`` and ``torch.cat`` never run as separate passes.
+There is no PyTorch compute fallback: without the CUDA library these classes cannot run.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+_SPLITK_WS_BYTES = 96 << 20
+
+
+def _geglu_block(inner: int) -> int:
+    for gb in (80, 64, 32, 16, 8):
+        if inner % gb == 0:
+            return gb
+    raise ValueError(f"FF inner dim {inner} not supported")
+
+
+class _Net(nn.Module):
+    """time_embed + input_blocks + middle_block; subclasses add the ControlNet or decoder specific parts."""
+
+    def __init__(self, in_channels=4, model_channels=320, attention_resolutions=(4, 2, 1), num_res_blocks=2,
+                 channel_mult=(1, 2, 4, 4), num_heads=8, transformer_depth=1, context_dim=768,
+                 dtype=torch.bfloat16, **unused):
+        super().__init__()
+        if transformer_depth != 1:
+            raise NotImplementedError("only transformer_depth=1 (the yaml's value) is implemented")
+        self.dtype = dtype
+        self.in_channels, self.mc, self.heads, self.context_dim = in_channels, model_channels, num_heads, context_dim
+        self.ted = 4 * model_channels
+        mc = model_channels
+        self.input_blocks = [[("conv_in", "input_blocks.0.0", in_channels, mc)]]
+        self.block_chans = [mc]
+        self.block_ds = [1]
+        ch, ds = mc, 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                i = len(self.input_blocks)
+                layers = [("res", f"input_blocks.{i}.0", ch, mult * mc)]
+                ch = mult * mc
+                if ds in attention_resolutions:
+                    layers.append(("st", f"input_blocks.{i}.1", ch))
+                self.input_blocks.append(layers)
+                self.block_chans.append(ch)
+                self.block_ds.append(ds)
+            if level != len(channel_mult) - 1:
+                i = len(self.input_blocks)
+                self.input_blocks.append([("down", f"input_blocks.{i}.0.op", ch)])
+                ds *= 2
+                self.block_chans.append(ch)
+                self.block_ds.append(ds)
+        self.middle = [("res", "middle_block.0", ch, ch), ("st", "middle_block.1", ch), ("res", "middle_block.2", ch, ch)]
+        self._ch, self._ds = ch, ds
+        self._attn_res = tuple(attention_resolutions)
+        self._channel_mult, self._nrb = tuple(channel_mult), num_res_blocks
+        self.w: dict[str, torch.Tensor] = {}
+        self._bufs: dict = {}
+        self._loaded = False
+
+    # ---- parameters ------------------------------------------------------------------------------------------
+    def _all_layers(self):
+        for blk in self.input_blocks:
+            yield from blk
+        yield from self.middle
+
+    def _res_layers(self):
+        return [l for l in self._all_layers() if l[0] == "res"]
+
+    def _put(self, name, t, act_dtype=False):
+        t = t.detach().to(device=self._device, dtype=self.dtype if act_dtype else torch.float32).contiguous()
+        self.w[name] = t
+
+    @staticmethod
+    def _krsc(w):  # OIHW -> [O][R][S][I]
+        return w.permute(0, 2, 3, 1).contiguous()
+
+    def load_state_dict(self, sd, strict=True, prefix="", device="cuda"):  # noqa: D401 (upstream-keyed checkpoints)
+        """Repack an upstream-keyed state dict (fp32 OIHW / [out,in]) into the layouts the kernels read."""
+        self._device = torch.device(device)
+        used = set()
+
+        def g(k):
+            used.add(prefix + k)
+            return sd[prefix + k]
+
+        self._put("te0.w", g("time_embed.0.weight"), True); self._put("te0.b", g("time_embed.0.bias"))
+        self._put("te2.w", g("time_embed.2.weight"), True); self._put("te2.b", g("time_embed.2.bias"))
+        emb_w, emb_b = [], []
+        for layer in self._all_layers():
+            kind, key = layer[0], layer[1]
+            if kind in ("conv_in", "down", "up"):
+                self._put(key + ".w", self._krsc(g(key + ".weight")), True); self._put(key + ".b", g(key + ".bias"))
+            elif kind == "res":
+                self._put(key + ".gn1.g", g(key + ".in_layers.0.weight")); self._put(key + ".gn1.b", g(key + ".in_layers.0.bias"))
+                self._put(key + ".c1.w", self._krsc(g(key + ".in_layers.2.weight")), True); self._put(key + ".c1.b", g(key + ".in_layers.2.bias"))
+                emb_w.append(g(key + ".emb_layers.1.weight")); emb_b.append(g(key + ".emb_layers.1.bias"))
+                self._put(key + ".gn2.g", g(key + ".out_layers.0.weight")); self._put(key + ".gn2.b", g(key + ".out_layers.0.bias"))
+                self._put(key + ".c2.w", self._krsc(g(key + ".out_layers.3.weight")), True); self._put(key + ".c2.b", g(key + ".out_layers.3.bias"))
+                if layer[2] != layer[3]:
+                    self._put(key + ".sk.w", self._krsc(g(key + ".skip_connection.weight")), True)
+                    self._put(key + ".sk.b", g(key + ".skip_connection.bias"))
+            elif kind == "st":
+                tb = key + ".transformer_blocks.0."
+                self._put(key + ".gn.g", g(key + ".norm.weight")); self._put(key + ".gn.b", g(key + ".norm.bias"))
+                self._put(key + ".pi.w", self._krsc(g(key + ".proj_in.weight")), True); self._put(key + ".pi.b", g(key + ".proj_in.bias"))
+                self._put(key + ".po.w", self._krsc(g(key + ".proj_out.weight")), True); self._put(key + ".po.b", g(key + ".proj_out.bias"))
+                for n in ("norm1", "norm2", "norm3"):
+                    self._put(key + f".{n}.g", g(tb + n + ".weight")); self._put(key + f".{n}.b", g(tb + n + ".bias"))
+                self._put(key + ".qkv.w", torch.cat([g(tb + "attn1.to_q.weight"), g(tb + "attn1.to_k.weight"),
+                                                     g(tb + "attn1.to_v.weight")], 0), True)
+                self._put(key + ".o1.w", g(tb + "attn1.to_out.0.weight"), True); self._put(key + ".o1.b", g(tb + "attn1.to_out.0.bias"))
+                self._put(key + ".q2.w", g(tb + "attn2.to_q.weight"), True)
+                self._put(key + ".kv2.w", torch.cat([g(tb + "attn2.to_k.weight"), g(tb + "attn2.to_v.weight")], 0), True)
+                self._put(key + ".o2.w", g(tb + "attn2.to_out.0.weight"), True); self._put(key + ".o2.b", g(tb + "attn2.to_out.0.bias"))
+                wff, bff = g(tb + "ff.net.0.proj.weight"), g(tb + "ff.net.0.proj.bias")
+                inner = wff.shape[0] // 2
+                gb = _geglu_block(inner)
+                # rows: blocks of [gb value rows | gb gate rows]  (mkd_conv_desc GEGLU layout)
+                wv, wg = wff[:inner].reshape(inner // gb, gb, -1), wff[inner:].reshape(inner // gb, gb, -1)
+                bv, bg = bff[:inner].reshape(inner // gb, gb), bff[inner:].reshape(inner // gb, gb)
+                self._put(key + ".ff1.w", torch.stack([wv, wg], 1).reshape(2 * inner, -1), True)
+                self._put(key + ".ff1.b", torch.stack([bv, bg], 1).reshape(2 * inner))
+                self._put(key + ".ff2.w", g(tb + "ff.net.2.weight"), True); self._put(key + ".ff2.b", g(tb + "ff.net.2.bias"))
+        # all ResBlock emb_layers as ONE [sum(Cout), 4*mc] matrix: one skinny GEMM per step instead of 22 / 10
+        self._put("emb_all.w", torch.cat(emb_w, 0), True); self._put("emb_all.b", torch.cat(emb_b, 0))
+        off = 0
+        self._emb_off = {}
+        for layer in self._res_layers():
+            self._emb_off[layer[1]] = off
+            off += layer[3]
+        self._emb_total = off
+        self._load_extra(g)
+        if strict:
+            missing = [k for k in sd if k.startswith(prefix) and k not in used]
+            if missing:
+                raise KeyError(f"unexpected keys in state dict: {missing[:5]} ...")
+        self._ws = torch.empty(_SPLITK_WS_BYTES // 4, dtype=torch.float32, device=self._device)
+        self._loaded = True
+        return self
+
+    def _load_extra(self, g):
+        pass
+
+    # ---- buffers ---------------------------------------------------------------------------------------------
+    def _buf(self, name, rows, cols, dtype=None):
+        key = (name, rows, cols, dtype)
+        b = self._bufs.get(key)
+        if b is None:
+            b = torch.empty(rows, cols, dtype=dtype or self.dtype, device=self._device)
+            self._bufs[key] = b
+        return b
+
+    def _gn_ws(self, N):
+        return self._buf("gn_ws", 1, ops.groupnorm_workspace_bytes(N) // 4, torch.float32)
+
+    # ---- building blocks ---------------------------------------------------------------------------------------
+    def _conv(self, x, wkey, y, N, H, W, R=1, **kw):
+        ops.conv2d(x, self.w[wkey + ".w"], y, N=N, H=H, W=W, R=R, S=R, pad=R // 2 if "pad" not in kw else kw.pop("pad"),
+                   bias=self.w.get(wkey + ".b"), workspace=self._ws, **kw)
+
+    def _linear(self, x, wkey, y, **kw):
+        ops.conv2d(x, self.w[wkey + ".w"], y, N=1, H=1, W=x.shape[0], bias=self.w.get(wkey + ".b"), workspace=self._ws, **kw)
+
+    def _time_embedding(self, t, B):
+        """emb = time_embed(timestep_embedding(t)); returns silu(emb) @ W_all + b_all for every ResBlock at once."""
+        te = self._buf("t_emb", B, self.mc)
+        ops.timestep_embedding(t, te)
+        e1 = self._buf("te1", B, self.ted)
+        self._linear(te, "te0", e1, act=L.ACT_SILU)
+        e2 = self._buf("te2", B, self.ted)
+        self._linear(e1, "te2", e2)
+        ops.silu(e2, e2)  # every consumer (ResBlock.emb_layers) starts with SiLU
+        ea = self._buf("emb_all", B, self._emb_total)
+        self._linear(e2, "emb_all", ea)
+        return ea
+
+    def _res(self, layer, x, y, emb_all, N, H, W):
+        _, key, cin, cout = layer
+        M = N * H * W
+        t1 = self._buf("gn_a", M, cin)
+        ops.groupnorm(x, t1, N, self.w[key + ".gn1.g"], self.w[key + ".gn1.b"], 1e-5, True, self._gn_ws(N))
+        h = self._buf("res_h", M, cout)
+        e = emb_all[:, self._emb_off[key]:self._emb_off[key] + cout]
+        self._conv(t1, key + ".c1", h, N, H, W, R=3, emb=e)
+        t2 = self._buf("gn_b", M, cout)
+        ops.groupnorm(h, t2, N, self.w[key + ".gn2.g"], self.w[key + ".gn2.b"], 1e-5, True, self._gn_ws(N))
+        if cin != cout:
+            sk = self._buf("res_sk", M, cout)
+            self._conv(x, key + ".sk", sk, N, H, W, R=1)
+        else:
+            sk = x
+        self._conv(t2, key + ".c2", y, N, H, W, R=3, residual=sk)
+
+    def _st(self, layer, x, y, ctx_kv, N, H, W):
+        _, key, ch = layer
+        M, hd = N * H * W, ch // self.heads
+        scale = hd ** -0.5
+        n = self._buf("st_n", M, ch)
+        ops.groupnorm(x, n, N, self.w[key + ".gn.g"], self.w[key + ".gn.b"], 1e-6, False, self._gn_ws(N))
+        xs = self._buf("st_x", M, ch)
+        self._conv(n, key + ".pi", xs, N, H, W, R=1)
+        ln = self._buf("st_ln", M, ch)
+        # self-attention
+        ops.layernorm(xs, ln, self.w[key + ".norm1.g"], self.w[key + ".norm1.b"])
+        qkv = self._buf("st_qkv", M, 3 * ch)
+        self._linear(ln, key + ".qkv", qkv)
+        att = self._buf("st_att", M, ch)
+        ops.attention(qkv[:, :ch], qkv[:, ch:2 * ch], qkv[:, 2 * ch:], att, B=N, heads=self.heads, Nq=H * W, Nkv=H * W,
+                      d=hd, scale=scale)
+        self._linear(att, key + ".o1", xs, residual=xs)
+        # cross-attention (K/V of the step-invariant context are precomputed: ctx_kv[key] = [N*L, 2*ch])
+        ops.layernorm(xs, ln, self.w[key + ".norm2.g"], self.w[key + ".norm2.b"])
+        q2 = self._buf("st_q2", M, ch)
+        self._linear(ln, key + ".q2", q2)
+        kv = ctx_kv[key]
+        Lc = kv.shape[0] // N
+        ops.attention(q2, kv[:, :ch], kv[:, ch:], att, B=N, heads=self.heads, Nq=H * W, Nkv=Lc, d=hd, scale=scale)
+        self._linear(att, key + ".o2", xs, residual=xs)
+        # GEGLU feed-forward (gate fused into the first GEMM's epilogue)
+        ops.layernorm(xs, ln, self.w[key + ".norm3.g"], self.w[key + ".norm3.b"])
+        inner = 4 * ch
+        ff = self._buf("st_ff", M, inner)
+        self._linear(ln, key + ".ff1", ff, act=L.ACT_GEGLU, geglu_block=_geglu_block(inner))
+        self._linear(ff, key + ".ff2", xs, residual=xs)
+        self._conv(xs, key + ".po", y, N, H, W, R=1, residual=x)
+
+    def context_kv(self, context):
+        """attn2 K/V projections of the (step-invariant) text context for every SpatialTransformer: hoisted out of
+        the 50-step loop (SURVEY.md §7 hard part 7).  context: [B, L, context_dim] fp32/bf16."""
+        B, Lc, D = context.shape
+        ctx = self._buf("ctx", B * Lc, D)
+        ctx.copy_(context.reshape(B * Lc, D))
+        out = {}
+        for layer in self._all_layers():
+            if layer[0] == "st":
+                kv = self._buf("kv_" + layer[1], B * Lc, 2 * layer[2])
+                self._linear(ctx, layer[1] + ".kv2", kv)
+                out[layer[1]] = kv
+        return out
+
+    def _to_nhwc(self, x, name):
+        B, Cc, H, W = x.shape
+        buf = self._buf(name, B * H * W, (Cc + 7) // 8 * 8)
+        v = buf[:, :Cc]
+        ops.nchw_to_nhwc(x.float().contiguous(), v)
+        return v
+
+    def _run_block(self, layers, x, y, emb_all, ctx_kv, N, H, W):
+        """runs a block's layers x -> y through ping-pong temporaries; returns output spatial size"""
+        cur = x
+        for li, layer in enumerate(layers):
+            last = li == len(layers) - 1
+            kind = layer[0]
+            if kind == "conv_in":
+                self._conv(cur, layer[1], y, N, H, W, R=3)
+            elif kind == "res":
+                out = y if last else self._buf(f"pp{li % 2}", N * H * W, layer[3])
+                self._res(layer, cur, out, emb_all, N, H, W)
+                cur = out
+            elif kind == "st":
+                out = y if last else self._buf(f"pp{li % 2}", N * H * W, layer[2])
+                self._st(layer, cur, out, ctx_kv, N, H, W)
+                cur = out
+            elif kind == "down":
+                self._conv(cur, layer[1], y, N, H, W, R=3, stride=2)
+                H, W = H // 2, W // 2
+            elif kind == "up":
+                assert last
+                self._conv(cur, layer[1], y, N, H, W, R=3, upsample=True)
+                H, W = 2 * H, 2 * W
+        return H, W
+
+
+class B200ControlNet(_Net):
+    """Drop-in for ``cldm.cldm.ControlNet`` (yaml:52-67)."""
+
+    HINT = ((16, 1), (16, 1), (32, 2), (32, 1), (96, 2), (96, 1), (256, 2))
+
+    def __init__(self, image_size=32, in_channels=4, hint_channels=6, model_channels=320, attention_resolutions=(4, 2, 1),
+                 num_res_blocks=2, channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True,
+                 transformer_depth=1, context_dim=768, use_checkpoint=False, legacy=False, dtype=torch.bfloat16, **kw):
+        super().__init__(in_channels, model_channels, attention_resolutions, num_res_blocks, channel_mult, num_heads,
+                         transformer_depth, context_dim, dtype)
+        self.hint_channels = hint_channels
+
+    def _load_extra(self, g):
+        for i in range(8):
+            k = f"input_hint_block.{2 * i}"
+            self._put(k + ".w", self._krsc(g(k + ".weight")), True); self._put(k + ".b", g(k + ".bias"))
+        for j in range(len(self.input_blocks)):
+            k = f"zero_convs.{j}.0"
+            self._put(k + ".w", self._krsc(g(k + ".weight")), True); self._put(k + ".b", g(k + ".bias"))
+        k = "middle_block_out.0"
+        self._put(k + ".w", self._krsc(g(k + ".weight")), True); self._put(k + ".b", g(k + ".bias"))
+
+    def hint_features(self, hint):
+        """input_hint_block(hint): independent of x and t, so computed once per batch of images, not once per step.
+        hint: [B, 6, 8h, 8w] fp32 in [0,1] = cat(source, reference) (makeup_diffuse.py:56).  Returns [B*h*w, mc]."""
+        B, Cc, H, W = hint.shape
+        cur = self._to_nhwc(hint, "hint_in")
+        chans = [c for c, _ in self.HINT] + [self.mc]
+        strides = [s for _, s in self.HINT] + [1]
+        for i, (co, s) in enumerate(zip(chans, strides)):
+            Ho, Wo = (H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1
+            out = self._buf(f"hint_{i}", B * Ho * Wo, co)
+            self._conv(cur, f"input_hint_block.{2 * i}", out, B, H, W, R=3, stride=s,
+                       act=L.ACT_SILU if i < 7 else L.ACT_NONE)
+            cur, H, W = out, Ho, Wo
+        return cur
+
+    def run(self, x_nhwc, guided_hint, t, ctx_kv, N, H, W, inject=None, scales=None):
+        """x_nhwc: [N*H*W, in_ch] view.  Writes the 13 residuals to own buffers, or — when ``inject`` (13 views into
+        the UNet's skip slots) is given — accumulates ``scale_i * zero_conv_i(h)`` straight into them."""
+        emb_all = self._time_embedding(t, N)
+        outs = []
+        cur, h, w = x_nhwc, H, W
+        for j, blk in enumerate(self.input_blocks):
+            ch = self.block_chans[j]
+            ho, wo = (h // 2, w // 2) if blk[0][0] == "down" else (h, w)
+            y = self._buf(f"cn_h{j}", N * ho * wo, ch)
+            self._run_block(blk, cur, y, emb_all, ctx_kv, N, h, w)
+            if j == 0:
+                ops.add(y, guided_hint, y)
+            cur, h, w = y, ho, wo
+            outs.append(self._zero_conv(f"zero_convs.{j}.0", cur, j, N, h, w, inject, scales))
+        y = self._buf("cn_mid", N * h * w, self._ch)
+        self._run_block(self.middle, cur, y, emb_all, ctx_kv, N, h, w)
+        outs.append(self._zero_conv("middle_block_out.0", y, len(self.input_blocks), N, h, w, inject, scales))
+        return outs
+
+    def _zero_conv(self, key, x, j, N, h, w, inject, scales):
+        ch = x.shape[1]
+        if inject is None:
+            out = self._buf(f"cn_out{j}", N * h * w, ch)
+            self._conv(x, key, out, N, h, w, R=1)
+            return (out, h, w)
+        if inject[j] is not None:
+            self._conv(x, key, inject[j], N, h, w, R=1, residual=inject[j], alpha=1.0 if scales is None else scales[j])
+        return None
+
+    def forward(self, x, hint, timesteps, context, **kwargs):
+        """Reference call form (makeup_diffuse.py:164): returns the 13 control residuals as NCHW fp32 tensors."""
+        assert self._loaded, "load_state_dict() first"
+        N, _, H, W = x.shape
+        xin = self._to_nhwc(x, "x_in")
+        outs = self.run(xin, self.hint_features(hint), timesteps.to(torch.int64).contiguous(),
+                        self.context_kv(context), N, H, W)
+        res = []
+        for o, h, w in outs:
+            t = torch.empty(N, o.shape[1], h, w, dtype=torch.float32, device=o.device)
+            ops.nhwc_to_nchw(o, t)
+            res.append(t)
+        return res
+
+
+class B200ControlledUnet(_Net):
+    """Drop-in for ``cldm.cldm.ControlledUnetModel`` (yaml:69-84)."""
+
+    def __init__(self, image_size=32, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=(4, 2, 1),
+                 num_res_blocks=2, channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True,
+                 transformer_depth=1, context_dim=768, use_checkpoint=False, legacy=False, dtype=torch.bfloat16, **kw):
+        super().__init__(in_channels, model_channels, attention_resolutions, num_res_blocks, channel_mult, num_heads,
+                         transformer_depth, context_dim, dtype)
+        self.out_channels = out_channels
+        mc, ch, ds = model_channels, self._ch, self._ds
+        chans = list(self.block_chans)
+        self.output_blocks, self.cat_split = [], []
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = chans.pop()
+                k = len(self.output_blocks)
+                layers = [("res", f"output_blocks.{k}.0", ch + ich, mc * mult)]
+                self.cat_split.append((ch, ich))
+                ch = mc * mult
+                if ds in self._attn_res:
+                    layers.append(("st", f"output_blocks.{k}.1", ch))
+                if level and i == num_res_blocks:
+                    layers.append(("up", f"output_blocks.{k}.{len(layers)}.conv", ch))
+                    ds //= 2
+                self.output_blocks.append(layers)
+        self._out_ch = ch
+
+    def _all_layers(self):
+        yield from super()._all_layers()
+        for blk in self.output_blocks:
+            yield from blk
+
+    def _load_extra(self, g):
+        self._put("out.gn.g", g("out.0.weight")); self._put("out.gn.b", g("out.0.bias"))
+        self._put("out.2.w", self._krsc(g("out.2.weight")), True); self._put("out.2.b", g("out.2.bias"))
+
+    # the decoder's concat buffers: cat_i = [ h (C_h) | hs[11-i] (C_skip) ]
+    def _cat(self, i, N, H, W):
+        nb = len(self.input_blocks)
+        ds = self.block_ds[nb - 1 - i]
+        ch, ich = self.cat_split[i]
+        return self._buf(f"cat{i}", N * (H // ds) * (W // ds), ch + ich), ch, ds
+
+    def skip_slots(self, N, H, W):
+        """views the 12 encoder outputs live in + the view of the middle-block output (13 injection targets,
+        ordered like ControlNet's outputs)"""
+        nb = len(self.input_blocks)
+        slots = []
+        for j in range(nb):
+            cat, ch, _ = self._cat(nb - 1 - j, N, H, W)
+            slots.append(cat[:, ch:])
+        cat0, ch0, _ = self._cat(0, N, H, W)
+        slots.append(cat0[:, :ch0])
+        return slots
+
+    def encode(self, x_nhwc, t, ctx_kv, N, H, W):
+        self._emb_cur = self._time_embedding(t, N)
+        slots = self.skip_slots(N, H, W)
+        cur, h, w = x_nhwc, H, W
+        for j, blk in enumerate(self.input_blocks):
+            h, w = self._run_block(blk, cur, slots[j], self._emb_cur, ctx_kv, N, h, w)
+            cur = slots[j]
+        self._run_block(self.middle, cur, slots[-1], self._emb_cur, ctx_kv, N, h, w)
+        return slots
+
+    def decode(self, ctx_kv, N, H, W):
+        nb = len(self.output_blocks)
+        for i, blk in enumerate(self.output_blocks):
+            cat, _, ds = self._cat(i, N, H, W)
+            if i + 1 < nb:
+                nxt, nch, _ = self._cat(i + 1, N, H, W)
+                y = nxt[:, :nch]
+            else:
+                y = self._buf("dec_out", N * H * W, self._out_ch)
+            self._run_block(blk, cat, y, self._emb_cur, ctx_kv, N, H // ds, W // ds)
+        M = N * H * W
+        g = self._buf("gn_a", M, self._out_ch)
+        ops.groupnorm(y, g, N, self.w["out.gn.g"], self.w["out.gn.b"], 1e-5, True, self._gn_ws(N))
+        eo = self._buf("eps_nhwc", M, 8)
+        self._conv(g, "out.2", eo[:, :self.out_channels], N, H, W, R=3)
+        return eo[:, :self.out_channels]
+
+    def forward(self, x, timesteps=None, context=None, control=None, only_mid_control=False, **kwargs):
+        """Reference call form (makeup_diffuse.py:161-168). ``control``: list of 13 NCHW tensors or None."""
+        assert self._loaded, "load_state_dict() first"
+        N, _, H, W = x.shape
+        ctx_kv = self.context_kv(context)
+        xin = self._to_nhwc(x, "x_in")
+        slots = self.encode(xin, timesteps.to(torch.int64).contiguous(), ctx_kv, N, H, W)
+        if control is not None:
+            idx = [len(slots) - 1] if only_mid_control else range(len(slots))
+            for j in idx:
+                c = self._to_nhwc(control[j], f"ctl_in{j}")
+                ops.add(slots[j], c, slots[j])
+        e = self.decode(ctx_kv, N, H, W)
+        out = torch.empty(N, self.out_channels, H, W, dtype=torch.float32, device=e.device)
+        ops.nhwc_to_nchw(e, out)
+        return out

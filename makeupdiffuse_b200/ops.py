@@ -1,0 +1,184 @@
+"""Tensor-level wrappers over the C-ABI: torch is used for device memory and streams only.
+
+Activations are 2-D strided views ``[pixels, channels]`` (NHWC with an explicit row pitch), so a tensor may be a
+column slice of a wider concat buffer; spatial sizes travel as plain ints.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.bfloat16: L.MKD_BF16, torch.float32: L.MKD_F32}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; the B200 path stores bf16 (or fp32 in check mode)") from None
+
+
+def _rows(t: torch.Tensor):
+    """(data_ptr, row pitch) of a 2-D view whose last dim is contiguous"""
+    if t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
+        raise ValueError(f"expected a CUDA 2-D view with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.data_ptr(), t.stride(0)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def device_ok(device: int = 0):
+    L.check(L.load().mkd_device_ok(device), "device check")
+
+
+def ddim_update(x, eps, x_prev, *, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_t=0.0, temperature=1.0,
+                noise=None, pred_x0=None, cfg_scale=None):
+    """eps holds n values, or 2n ([uncond; cond]) when cfg_scale is given  (diffmk/cddim.py:39-40,56-78)."""
+    n = x.numel()
+    for t in (x, eps, x_prev, noise, pred_x0):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda):
+            raise ValueError("ddim_update works on contiguous fp32 CUDA latents")
+    cfg = cfg_scale is not None
+    if eps.numel() != (2 * n if cfg else n):
+        raise ValueError("eps has the wrong number of elements")
+    L.check(L.load().mkd_ddim_update(x.data_ptr(), eps.data_ptr(), int(cfg), float(cfg_scale or 0.0), _p(noise),
+                                     float(sqrt_one_minus_at), float(sqrt_at), float(sqrt_a_prev), float(dir_coef),
+                                     float(sigma_t), float(temperature), x_prev.data_ptr(), _p(pred_x0), n, _stream()),
+            "ddim_update")
+
+
+def nchw_to_nhwc(src, dst2d):
+    N, Cc, H, W = src.shape
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        raise ValueError("nchw_to_nhwc expects a contiguous fp32 NCHW tensor")
+    p, ld = _rows(dst2d)
+    assert dst2d.shape == (N * H * W, Cc)
+    L.check(L.load().mkd_nchw_to_nhwc(src.data_ptr(), p, _dt(dst2d), N, Cc, H, W, ld, _stream()), "nchw_to_nhwc")
+
+
+def nhwc_to_nchw(src2d, dst):
+    N, Cc, H, W = dst.shape
+    if dst.dtype != torch.float32 or not dst.is_contiguous():
+        raise ValueError("nhwc_to_nchw expects a contiguous fp32 NCHW destination")
+    p, ld = _rows(src2d)
+    assert src2d.shape == (N * H * W, Cc)
+    L.check(L.load().mkd_nhwc_to_nchw(p, dst.data_ptr(), _dt(src2d), N, Cc, H, W, ld, _stream()), "nhwc_to_nchw")
+
+
+def timestep_embedding(t, out, max_period=10000.0):
+    assert t.dtype == torch.int64 and t.is_contiguous() and out.is_contiguous()
+    B, dim = out.shape
+    L.check(L.load().mkd_timestep_embedding(t.data_ptr(), out.data_ptr(), _dt(out), B, dim, float(max_period), _stream()),
+            "timestep_embedding")
+
+
+def silu(x, y):
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype
+    L.check(L.load().mkd_silu(x.data_ptr(), y.data_ptr(), _dt(x), x.numel(), _stream()), "silu")
+
+
+def geglu(x2d, y2d):
+    px, ldx = _rows(x2d)
+    py, ldy = _rows(y2d)
+    M, inner = y2d.shape
+    assert x2d.shape == (M, 2 * inner)
+    L.check(L.load().mkd_geglu(px, py, _dt(x2d), M, inner, ldx, ldy, _stream()), "geglu")
+
+
+def add(a2d, b2d, y2d):
+    pa, lda = _rows(a2d)
+    pb, ldb = _rows(b2d)
+    py, ldy = _rows(y2d)
+    M, Cc = y2d.shape
+    L.check(L.load().mkd_add(pa, pb, py, _dt(y2d), M, Cc, lda, ldb, ldy, _stream()), "add")
+
+
+def groupnorm_workspace_bytes(N, groups=32) -> int:
+    return int(L.load().mkd_groupnorm_workspace_bytes(N, groups))
+
+
+def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
+    px, ldx = _rows(x2d)
+    py, ldy = _rows(y2d)
+    M, Cc = x2d.shape
+    assert M % N == 0 and y2d.shape == x2d.shape and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    L.check(L.load().mkd_groupnorm(px, py, _dt(x2d), N, M // N, Cc, groups, ldx, ldy, gamma.data_ptr(), beta.data_ptr(),
+                                   float(eps), int(bool(silu)), workspace.data_ptr(),
+                                   workspace.numel() * workspace.element_size(), _stream()), "groupnorm")
+
+
+def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
+    px, ldx = _rows(x2d)
+    py, ldy = _rows(y2d)
+    M, Cc = x2d.shape
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    L.check(L.load().mkd_layernorm(px, py, _dt(x2d), M, Cc, ldx, ldy, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                   _stream()), "layernorm")
+
+
+def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None,
+                   residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None) -> L.ConvDesc:
+    px, ldx = _rows(x2d)
+    py, ldy = _rows(y2d)
+    Cc = x2d.shape[1]
+    K = w.shape[0]
+    assert x2d.shape[0] == N * H * W, (x2d.shape, N, H, W)
+    assert w.is_contiguous() and w.numel() == K * R * S * Cc and w.dtype == x2d.dtype == y2d.dtype
+    if y2d.shape[1] != (K // 2 if act == L.ACT_GEGLU else K):
+        raise ValueError(f"output view has {y2d.shape[1]} channels, the filter bank produces {K}")
+    d = L.ConvDesc()
+    d.dtype = _dt(x2d)
+    d.N, d.H, d.W, d.C, d.K, d.R, d.S = N, H, W, Cc, K, R, S
+    d.stride, d.pad, d.upsample = stride, pad, int(bool(upsample))
+    d.ldx, d.ldy = ldx, ldy
+    d.act, d.geglu_block, d.path, d.alpha = act, geglu_block, path, float(alpha)
+    d.x, d.w, d.y = px, w.data_ptr(), py
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+        d.bias = bias.data_ptr()
+    if emb is not None:
+        pe, lde = _rows(emb)
+        assert emb.dtype == x2d.dtype
+        d.emb, d.lde = pe, lde
+    if residual is not None:
+        pr, ldr = _rows(residual)
+        assert residual.dtype == x2d.dtype
+        d.residual, d.ldr = pr, ldr
+    if workspace is not None:
+        d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    return d
+
+
+def conv2d(x2d, w, y2d, **kw):
+    d = make_conv_desc(x2d, w, y2d, **kw)
+    L.check(L.load().mkd_conv2d(C.byref(d), _stream()), "conv2d")
+
+
+def conv2d_path(x2d, w, y2d, **kw) -> int:
+    d = make_conv_desc(x2d, w, y2d, **kw)
+    rc = L.load().mkd_conv2d_path(C.byref(d))
+    if rc < 0:
+        L.check(rc, "conv2d_path")
+    return rc
+
+
+def run_conv_desc(d: L.ConvDesc):
+    L.check(L.load().mkd_conv2d(C.byref(d), _stream()), "conv2d")
+
+
+def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
+    pq, ldq = _rows(q2d)
+    pk, ldk = _rows(k2d)
+    pv, ldv = _rows(v2d)
+    po, ldo = _rows(o2d)
+    L.check(L.load().mkd_attention(pq, pk, pv, po, _dt(q2d), B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, float(scale),
+                                   _stream()), "attention")

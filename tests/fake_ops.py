@@ -1,0 +1,115 @@
+"""TEST-ONLY stand-ins for makeupdiffuse_b200.ops: each function restates the C-ABI contract of include/mkd_b200.h in
+plain torch on the CPU so that the HOST logic (buffer/slot plumbing, weight repacking, call order) can be tested
+without a GPU.  Never imported by the product."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from makeupdiffuse_b200 import _lib as L
+
+
+def device_ok(device=0):
+    pass
+
+
+def groupnorm_workspace_bytes(N, groups=32):
+    return N * 64 * groups * 8
+
+
+def ddim_update(x, eps, x_prev, *, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_t=0.0, temperature=1.0,
+                noise=None, pred_x0=None, cfg_scale=None):
+    f = lambda v: torch.tensor(v, dtype=torch.float32)  # noqa: E731
+    e = eps
+    if cfg_scale is not None:
+        eu, ec = eps.chunk(2)
+        e = eu + f(cfg_scale) * (ec - eu)
+    p0 = (x - f(sqrt_one_minus_at) * e) / f(sqrt_at)
+    xp = f(sqrt_a_prev) * p0 + f(dir_coef) * e
+    if noise is not None:
+        xp = xp + f(sigma_t) * noise * f(temperature)
+    x_prev.copy_(xp)
+    if pred_x0 is not None:
+        pred_x0.copy_(p0)
+
+
+def nchw_to_nhwc(src, dst2d):
+    N, C, H, W = src.shape
+    dst2d.copy_(src.permute(0, 2, 3, 1).reshape(N * H * W, C))
+
+
+def nhwc_to_nchw(src2d, dst):
+    N, C, H, W = dst.shape
+    dst.copy_(src2d.float().reshape(N, H, W, C).permute(0, 3, 1, 2))
+
+
+def timestep_embedding(t, out, max_period=10000.0):
+    B, dim = out.shape
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    out.copy_(torch.cat([torch.cos(args), torch.sin(args)], -1))
+
+
+def silu(x, y):
+    y.copy_(F.silu(x.float()))
+
+
+def geglu(x2d, y2d):
+    inner = y2d.shape[1]
+    y2d.copy_(x2d[:, :inner].float() * F.gelu(x2d[:, inner:].float()))
+
+
+def add(a2d, b2d, y2d):
+    y2d.copy_(a2d.float() + b2d.float())
+
+
+def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
+    M, C = x2d.shape
+    xr = x2d.float().reshape(N, M // N, C).permute(0, 2, 1)
+    r = F.group_norm(xr, groups, gamma, beta, eps)
+    if silu:
+        r = F.silu(r)
+    y2d.copy_(r.permute(0, 2, 1).reshape(M, C))
+
+
+def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
+    y2d.copy_(F.layer_norm(x2d.float(), (x2d.shape[1],), gamma, beta, eps))
+
+
+def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None, residual=None,
+           alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None):
+    C = x2d.shape[1]
+    K = w.shape[0]
+    assert x2d.shape[0] == N * H * W and w.numel() == K * R * S * C
+    xr = x2d.float().reshape(N, H, W, C).permute(0, 3, 1, 2)
+    if upsample:
+        xr = F.interpolate(xr, scale_factor=2, mode="nearest")
+    acc = F.conv2d(xr, w.float().reshape(K, R, S, C).permute(0, 3, 1, 2), None if bias is None else bias.float(),
+                   stride=stride, padding=pad)
+    Mo = acc.shape[0] * acc.shape[2] * acc.shape[3]
+    if emb is not None:
+        acc = acc + emb.float()[:, :, None, None]
+    acc = (acc * alpha).permute(0, 2, 3, 1).reshape(Mo, K)
+    if act == L.ACT_GEGLU:
+        gb = geglu_block
+        Ko = K // 2
+        assert emb is None and residual is None and alpha == 1.0 and Ko % gb == 0
+        a = acc.reshape(Mo, Ko // gb, 2, gb)
+        acc = (a[:, :, 0] * F.gelu(a[:, :, 1])).reshape(Mo, Ko)
+    if residual is not None:
+        acc = acc + residual.float()
+    if act == L.ACT_SILU:
+        acc = F.silu(acc)
+    assert y2d.shape == acc.shape, (y2d.shape, acc.shape)
+    y2d.copy_(acc)
+
+
+def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
+    sp = lambda t, n: t.float().reshape(B, n, heads, d).permute(0, 2, 1, 3)  # noqa: E731
+    o = F.scaled_dot_product_attention(sp(q2d, Nq), sp(k2d, Nkv), sp(v2d, Nkv), scale=scale)
+    o2d.copy_(o.permute(0, 2, 1, 3).reshape(B * Nq, heads * d))
+
+
+ALL = ["device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
+       "silu", "geglu", "add", "groupnorm", "layernorm", "conv2d", "attention"]

@@ -1,0 +1,279 @@
+"""Per-kernel parity on a real B200: every C-ABI entry point against a plain PyTorch fp32 statement of the same op
+(the reference executes these as PyTorch library calls).  All calls go through the C-ABI (ops.py -> ctypes)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from makeupdiffuse_b200 import _lib as L  # noqa: E402
+from makeupdiffuse_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+BF, F32 = torch.bfloat16, torch.float32
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def tol(dt):
+    return 6e-3 if dt == BF else 2e-5
+
+
+def rnd(*shape, dt=F32, seed=0, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randn(*shape, device=DEV, generator=g) * scale).to(dt)
+
+
+def test_device_is_b200():
+    ops.device_ok(0)
+    assert torch.cuda.get_device_capability(0) == (10, 0)
+
+
+# ---- DDIM update: bit-exact against the reference's op-by-op fp32 arithmetic (cddim.py:39-40,56-78) --------------
+@pytest.mark.parametrize("cfg", [False, True])
+@pytest.mark.parametrize("sigma", [0.0, 0.37])
+@pytest.mark.parametrize("n", [1, 4096 * 16 + 3])
+def test_ddim_update_bit_exact(cfg, sigma, n):
+    x, e_c, e_u, nz = rnd(n, seed=1), rnd(n, seed=2), rnd(n, seed=3), rnd(n, seed=4)
+    a_t, a_prev, scale, temp = 0.2314, 0.3127, 9.0, 0.9
+    full = lambda v: torch.full((1,), v, device=DEV)  # noqa: E731
+    ta, tp, ts, t1 = full(a_t), full(a_prev), full(sigma), full(math.sqrt(1 - a_t))
+    e = e_u + scale * (e_c - e_u) if cfg else e_c
+    pred = (x - t1 * e) / ta.sqrt()
+    ref = tp.sqrt() * pred + (1.0 - tp - ts ** 2).sqrt() * e + ts * nz * temp
+    out, p0 = torch.empty_like(x), torch.empty_like(x)
+    ops.ddim_update(x, torch.cat([e_u, e_c]) if cfg else e_c, out, sqrt_one_minus_at=float(t1), sqrt_at=float(ta.sqrt()),
+                    sqrt_a_prev=float(tp.sqrt()), dir_coef=float((1.0 - tp - ts ** 2).sqrt()), sigma_t=sigma,
+                    temperature=temp, noise=nz if sigma else None, pred_x0=p0, cfg_scale=scale if cfg else None)
+    if not sigma:
+        ref = tp.sqrt() * pred + (1.0 - tp - ts ** 2).sqrt() * e
+    assert torch.equal(p0, pred)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dt", [BF, F32])
+def test_layout_roundtrip(dt):
+    x = rnd(3, 6, 20, 12)
+    buf = torch.zeros(3 * 20 * 12, 8, device=DEV, dtype=dt)
+    ops.nchw_to_nhwc(x, buf[:, :6])
+    ref = x.permute(0, 2, 3, 1).reshape(-1, 6).to(dt)
+    assert torch.equal(buf[:, :6], ref) and float(buf[:, 6:].abs().max()) == 0
+    back = torch.empty_like(x)
+    ops.nhwc_to_nchw(buf[:, :6], back)
+    assert torch.equal(back, x.to(dt).float())
+
+
+@pytest.mark.parametrize("dt", [BF, F32])
+def test_timestep_embedding(dt):
+    t = torch.tensor([0, 1, 21, 501, 981, 999], device=DEV)
+    out = torch.empty(6, 320, device=DEV, dtype=dt)
+    ops.timestep_embedding(t, out)
+    half = 160
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=F32, device=DEV) / half)
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert float((out.float() - ref).abs().max()) < (1e-2 if dt == BF else 2e-4)
+
+
+@pytest.mark.parametrize("dt", [BF, F32])
+def test_silu_geglu_add(dt):
+    x = rnd(37, 256, dt=dt)
+    y = torch.empty_like(x)
+    ops.silu(x, y)
+    assert rel(y, F.silu(x.float())) < tol(dt)
+    wide = rnd(50, 2 * 128 + 16, dt=dt, seed=3)
+    out = torch.zeros(50, 136, device=DEV, dtype=dt)
+    ops.geglu(wide[:, :256], out[:, :128])
+    ref = wide[:, :128].float() * F.gelu(wide[:, 128:256].float())
+    assert rel(out[:, :128], ref) < tol(dt) and float(out[:, 128:].abs().max()) == 0
+    a, b = rnd(50, 64, dt=dt, seed=5), rnd(50, 64, dt=dt, seed=6)
+    ops.add(a, b, a)
+    # a was overwritten in place: recompute the reference from fresh copies
+    a0 = rnd(50, 64, dt=dt, seed=5)
+    assert rel(a, a0.float() + b.float()) < tol(dt)
+
+
+@pytest.mark.parametrize("dt", [BF, F32])
+@pytest.mark.parametrize("N,HW,C,ld,silu,eps", [(2, 1024, 320, 320, True, 1e-5), (3, 256, 960, 960, True, 1e-5),
+                                                 (2, 64, 1920, 1920, False, 1e-6), (16, 16, 2560, 2560, True, 1e-5),
+                                                 (2, 1024, 320, 640, True, 1e-5), (1, 64, 64, 64, True, 1e-5),
+                                                 (5, 4096, 320, 320, False, 1e-6), (2, 100, 128, 136, True, 1e-5)])
+def test_groupnorm(dt, N, HW, C, ld, silu, eps):
+    buf = rnd(N * HW, ld, dt=dt, seed=1) * 1.7 + 0.4
+    x = buf[:, ld - C:]  # channel slice of a wider (concat) buffer
+    gamma, beta = 1 + 0.2 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
+    y = torch.empty(N * HW, C, device=DEV, dtype=dt)
+    ws = torch.empty(ops.groupnorm_workspace_bytes(N) // 4, device=DEV)
+    ops.groupnorm(x, y, N, gamma, beta, eps, silu, ws)
+    xr = x.float().reshape(N, HW, C).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma, beta, eps)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 1).reshape(N * HW, C)
+    assert rel(y, ref) < tol(dt)
+
+
+@pytest.mark.parametrize("dt", [BF, F32])
+@pytest.mark.parametrize("M,C", [(1024, 320), (77, 640), (300, 1280), (5, 64)])
+def test_layernorm(dt, M, C):
+    x = rnd(M, C, dt=dt, seed=1) * 2 + 0.3
+    g, b = 1 + 0.2 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
+    y = torch.empty_like(x)
+    ops.layernorm(x, y, g, b)
+    assert rel(y, F.layer_norm(x.float(), (C,), g, b)) < tol(dt)
+
+
+# ---- convolution / GEMM family -----------------------------------------------------------------------------------
+def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True, emb=False, residual=False,
+              inplace=False, alpha=1.0, act=L.ACT_NONE, ldx_extra=0, ldy_extra=0, workspace=False, seed=0):
+    M = N * H * W
+    xb = rnd(M, C + ldx_extra, dt=dt, seed=seed + 1)
+    x = xb[:, ldx_extra:]
+    w_oihw = rnd(K, C, R, R, seed=seed + 2, scale=1.0 / math.sqrt(C * R * R)).to(dt)
+    w = w_oihw.permute(0, 2, 3, 1).contiguous()
+    b = 0.5 * rnd(K, seed=seed + 3) if bias else None
+    e = rnd(N, K + 8, dt=dt, seed=seed + 4)[:, 8:] if emb else None
+    Hi, Wi = (2 * H, 2 * W) if upsample else (H, W)
+    P, Q = (Hi + 2 * (R // 2) - R) // stride + 1, (Wi + 2 * (R // 2) - R) // stride + 1
+    Mo = N * P * Q
+    Ko = K // 2 if act == L.ACT_GEGLU else K
+    yb = rnd(Mo, Ko + ldy_extra, dt=dt, seed=seed + 5)
+    y = yb[:, ldy_extra:]
+    res = y if inplace else (rnd(Mo, Ko, dt=dt, seed=seed + 6) if residual else None)
+    res_ref = None if res is None else res.float().clone()
+    gb = 80 if act == L.ACT_GEGLU and Ko % 80 == 0 else 16
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV) if workspace else None
+    kw = dict(N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=upsample, bias=b, emb=e, residual=res,
+              alpha=alpha, act=act, geglu_block=gb, path=path, workspace=ws)
+    assert ops.conv2d_path(x, w, y, **kw) == (path if path else ops.conv2d_path(x, w, y, **kw))
+    ops.conv2d(x, w, y, **kw)
+    # fp32 reference on the same (rounded) inputs
+    xr = x.float().reshape(N, H, W, C).permute(0, 3, 1, 2)
+    if upsample:
+        xr = F.interpolate(xr, scale_factor=2, mode="nearest")
+    wr = w_oihw.float()
+    if act == L.ACT_GEGLU:  # undo the [gb value | gb gate] row blocking
+        wv = wr.reshape(Ko // gb, 2, gb, C, R, R)
+        wr = torch.cat([wv[:, 0].reshape(Ko, C, R, R), wv[:, 1].reshape(Ko, C, R, R)], 0)
+        bv = b.reshape(Ko // gb, 2, gb)
+        br = torch.cat([bv[:, 0].reshape(Ko), bv[:, 1].reshape(Ko)], 0)
+    else:
+        br = b
+    acc = F.conv2d(xr.double(), wr.double(), None if br is None else br.double(), stride=stride, padding=R // 2)
+    if emb:
+        acc = acc + e.double()[:, :, None, None]
+    acc = acc * alpha
+    acc = acc.permute(0, 2, 3, 1).reshape(Mo, K)
+    if res_ref is not None:
+        acc = acc + res_ref.double()
+    if act == L.ACT_SILU:
+        acc = F.silu(acc)
+    if act == L.ACT_GEGLU:
+        acc = acc[:, :Ko] * F.gelu(acc[:, Ko:])
+    err = rel(y, acc.float())
+    assert err < tol(dt), f"rel err {err}"
+    if ldy_extra:  # the kernel must not touch the columns outside its slice
+        assert torch.equal(yb[:, :ldy_extra], rnd(Mo, Ko + ldy_extra, dt=dt, seed=seed + 5)[:, :ldy_extra])
+    return err
+
+
+GENERIC_CASES = [
+    dict(N=2, H=8, W=8, C=4, K=64, R=3),                                   # conv_in
+    dict(N=2, H=8, W=8, C=64, K=4, R=3),                                   # out conv
+    dict(N=1, H=16, W=16, C=6, K=16, R=3, act=L.ACT_SILU),                 # hint conv 0
+    dict(N=2, H=16, W=16, C=32, K=96, R=3, stride=2, act=L.ACT_SILU),      # hint stride-2
+    dict(N=2, H=8, W=8, C=64, K=64, R=3, stride=2),                        # Downsample
+    dict(N=2, H=4, W=4, C=64, K=64, R=3, upsample=True),                   # Upsample
+    dict(N=3, H=8, W=8, C=64, K=128, R=3, emb=True),                       # ResBlock conv1 (+emb)
+    dict(N=2, H=8, W=8, C=128, K=128, R=3, residual=True, ldx_extra=64, ldy_extra=64),  # ResBlock conv2 (+skip), slices
+    dict(N=2, H=8, W=8, C=64, K=64, R=1, inplace=True, alpha=0.7),         # zero-conv injection
+    dict(N=1, H=1, W=77, C=64, K=128, R=1, bias=False),                    # linear, no bias
+    dict(N=1, H=1, W=100, C=64, K=512, R=1, act=L.ACT_GEGLU),              # GEGLU
+    dict(N=1, H=1, W=3, C=1280, K=320, R=1, act=L.ACT_SILU),               # tiny-M linear (time embed)
+]
+
+
+@pytest.mark.parametrize("dt", [BF, F32])
+@pytest.mark.parametrize("case", GENERIC_CASES)
+def test_conv_generic(dt, case):
+    conv_case(dt, L.PATH_GENERIC, **case)
+
+
+TC_CASES = [
+    dict(N=1, H=1, W=128, C=64, K=32, R=1, bias=False),                    # one MMA group
+    dict(N=1, H=1, W=128, C=128, K=160, R=1),                              # 2 k-blocks, BN=160
+    dict(N=1, H=1, W=1024, C=320, K=320, R=1),                             # attention projection
+    dict(N=1, H=1, W=1000, C=320, K=960, R=1, bias=False),                 # ragged M (qkv)
+    dict(N=1, H=1, W=77 * 3, C=768, K=640, R=1, bias=False),               # cross k/v projection
+    dict(N=1, H=1, W=16, C=1280, K=1280, R=1, act=L.ACT_SILU),             # time-embed linear, tiny M
+    dict(N=1, H=1, W=300, C=320, K=2560, R=1, act=L.ACT_GEGLU),            # fused GEGLU
+    dict(N=1, H=1, W=256, C=1280, K=320, R=1, residual=True),              # FF out + residual
+    dict(N=1, H=1, W=200, C=640, K=640, R=1, inplace=True, alpha=0.5),     # in-place residual (injection)
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, emb=True),                    # ResBlock conv1 @32x32
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, residual=True),               # ResBlock conv2 @32x32
+    dict(N=3, H=16, W=16, C=640, K=640, R=3, emb=True),                    # @16x16
+    dict(N=3, H=8, W=8, C=1280, K=1280, R=3, residual=True),               # @8x8, box spans 2 images, ragged N
+    dict(N=5, H=4, W=4, C=1280, K=1280, R=3, emb=True),                    # @4x4, box spans 8 images
+    dict(N=1, H=64, W=64, C=320, K=320, R=3, emb=True),                    # 512^2 level: box = 2 rows of 64
+    dict(N=2, H=16, W=16, C=960, K=640, R=3, ldx_extra=320, ldy_extra=640, residual=True),  # concat slices in/out
+    dict(N=2, H=32, W=32, C=320, K=4, R=3),                                # `out` conv: 4 channels
+    dict(N=16, H=4, W=4, C=2560, K=1280, R=3, emb=True, workspace=True),   # split-K (deep level)
+    dict(N=4, H=8, W=8, C=1280, K=1280, R=1, workspace=True),              # split-K plain
+    dict(N=1, H=1, W=64, C=1280, K=10240, R=1, act=L.ACT_GEGLU, workspace=True),  # split-K + GEGLU
+    dict(N=2, H=32, W=32, C=320, K=320, R=1, residual=True),               # proj_out 1x1 conv
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05(case):
+    conv_case(BF, L.PATH_TCGEN05, **case)
+
+
+def test_conv_auto_dispatch():
+    """hot shapes go to the tcgen05 kernel, odd ones to the generic kernel"""
+    def path(**c):
+        M = c["N"] * c["H"] * c["W"]
+        x = torch.empty(M, c["C"], device=DEV, dtype=BF)
+        R = c.get("R", 1)
+        w = torch.empty(c["K"], R, R, c["C"], device=DEV, dtype=BF)
+        s = c.get("stride", 1)
+        y = torch.empty(M // (s * s), c["K"], device=DEV, dtype=BF)
+        return ops.conv2d_path(x, w, y, N=c["N"], H=c["H"], W=c["W"], R=R, S=R, stride=s, pad=R // 2)
+    assert path(N=16, H=32, W=32, C=320, K=320, R=3) == L.PATH_TCGEN05
+    assert path(N=16, H=1, W=1024, C=320, K=960) == L.PATH_TCGEN05
+    assert path(N=16, H=32, W=32, C=4, K=320, R=3) == L.PATH_GENERIC
+    assert path(N=16, H=32, W=32, C=320, K=320, R=3, stride=2) == L.PATH_GENERIC
+
+
+def test_conv_rejects_bad_descriptors():
+    x = torch.empty(64, 64, device=DEV, dtype=BF)
+    w = torch.empty(64, 64, device=DEV, dtype=BF)
+    with pytest.raises(RuntimeError, match="tcgen05|generic|stride"):
+        ops.conv2d(x, w, x, N=1, H=8, W=8, stride=2, path=L.PATH_TCGEN05)
+    with pytest.raises(ValueError):
+        ops.conv2d(x, w, x[:, :32], N=1, H=8, W=8)  # 32-column view cannot hold K=64 output channels
+
+
+# ---- attention -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [BF, F32])
+@pytest.mark.parametrize("B,heads,Nq,Nkv,d", [(2, 8, 1024, 1024, 40), (2, 8, 256, 256, 80), (3, 8, 64, 64, 160),
+                                               (2, 8, 16, 16, 160), (2, 8, 1024, 77, 40), (2, 8, 64, 77, 160),
+                                               (1, 4, 100, 77, 16), (1, 4, 64, 64, 32), (2, 2, 200, 130, 64)])
+def test_attention(dt, B, heads, Nq, Nkv, d):
+    C = heads * d
+    self_attn = Nq == Nkv
+    if self_attn:
+        qkv = rnd(B * Nq, 3 * C, dt=dt, seed=1)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    else:
+        q = rnd(B * Nq, C, dt=dt, seed=1)
+        kv = rnd(B * Nkv, 2 * C, dt=dt, seed=2)
+        k, v = kv[:, :C], kv[:, C:]
+    o = torch.empty(B * Nq, C, device=DEV, dtype=dt)
+    ops.attention(q, k, v, o, B=B, heads=heads, Nq=Nq, Nkv=Nkv, d=d, scale=d ** -0.5)
+    sp = lambda t, n: t.float().reshape(B, n, heads, d).permute(0, 2, 1, 3)  # noqa: E731
+    ref = F.scaled_dot_product_attention(sp(q, Nq), sp(k, Nkv), sp(v, Nkv)).permute(0, 2, 1, 3).reshape(B * Nq, C)
+    assert rel(o, ref) < (1e-2 if dt == BF else 2e-5)

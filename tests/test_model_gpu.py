@@ -1,0 +1,221 @@
+"""Whole-path parity on a real B200: B200ControlLDM / B200DDIMSampler against the oracle on identical inputs,
+weights and noise.  Tolerances are BASELINE.json's: per-step eps relative L2 <= 1e-2 in bf16, <= 1e-4 in the fp32
+check mode (teacher-forced); final latents within a PSNR bound (free-running)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from makeupdiffuse_b200 import B200ControlLDM, B200DDIMSampler  # noqa: E402
+from oracle import MKDDIMSampler, OracleControlLDM, seeded_state_dict  # noqa: E402
+
+DEV = "cuda"
+TOL_BF16, TOL_F32 = 1e-2, 1e-4
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+
+
+def make_cond(B, h, cdim, seed=0, hint=True):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    ctx = torch.randn(B, 77, cdim, device=DEV, generator=g)
+    cat = torch.rand(B, 6, 8 * h, 8 * h, device=DEV, generator=g) if hint else None
+    x = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    return {"c_crossattn": [ctx], "c_concat": [cat] if hint else None}, x
+
+
+class Bundle:
+    def __init__(self, params):
+        with torch.device(DEV):
+            self.oracle = OracleControlLDM(control_params=params, unet_params=params).eval()
+        sd = seeded_state_dict(self.oracle, 0)
+        for p in self.oracle.parameters():
+            p.requires_grad_(False)
+        self.bf16 = B200ControlLDM(params, params, dtype=torch.bfloat16).load_state_dict(sd)
+        self.f32 = B200ControlLDM(params, params, dtype=torch.float32).load_state_dict(sd)
+
+
+@pytest.fixture(scope="module")
+def tiny(tiny_params):
+    return Bundle(tiny_params)
+
+
+@pytest.mark.parametrize("B,h", [(2, 16), (1, 8), (3, 32)])
+def test_apply_model_parity(tiny, B, h):
+    cond, x = make_cond(B, h, 64, seed=B)
+    t = torch.tensor([981, 501, 21][:B], device=DEV)
+    with torch.no_grad():
+        ref = tiny.oracle.apply_model(x, t, cond)
+    e32 = tiny.f32.apply_model(x, t, cond)
+    e16 = tiny.bf16.apply_model(x, t, cond)
+    assert e32.shape == ref.shape and e32.dtype == torch.float32
+    assert rel(e32, ref) < TOL_F32, rel(e32, ref)
+    assert rel(e16, ref) < TOL_BF16, rel(e16, ref)
+    # no hint -> UNet only (makeup_diffuse.py:160-162)
+    nc = {"c_crossattn": cond["c_crossattn"], "c_concat": None}
+    with torch.no_grad():
+        ref0 = tiny.oracle.apply_model(x, t, nc)
+    assert rel(tiny.f32.apply_model(x, t, nc), ref0) < TOL_F32
+    assert rel(ref, ref0) > 0.1  # the ControlNet really contributes with the seeded non-zero init
+
+
+def test_control_scales_and_only_mid(tiny):
+    cond, x = make_cond(2, 16, 64, seed=7)
+    t = torch.tensor([301, 301], device=DEV)
+    scales = [0.5 + 0.1 * i for i in range(13)]
+    try:
+        tiny.oracle.control_scales = tiny.f32.control_scales = scales
+        with torch.no_grad():
+            ref = tiny.oracle.apply_model(x, t, cond)
+        assert rel(tiny.f32.apply_model(x, t, cond), ref) < TOL_F32
+        tiny.oracle.only_mid_control = tiny.f32.only_mid_control = True
+        with torch.no_grad():
+            ref = tiny.oracle.apply_model(x, t, cond)
+        assert rel(tiny.f32.apply_model(x, t, cond), ref) < TOL_F32
+    finally:
+        tiny.oracle.control_scales = tiny.f32.control_scales = [1.0] * 13
+        tiny.oracle.only_mid_control = tiny.f32.only_mid_control = False
+
+
+def test_module_level_call_forms(tiny):
+    """the two yaml `target:` replacements called exactly like makeup_diffuse.py:164-168"""
+    cond, x = make_cond(2, 16, 64, seed=3)
+    t = torch.tensor([701, 41], device=DEV)
+    ctx, hint = cond["c_crossattn"][0], cond["c_concat"][0]
+    with torch.no_grad():
+        ref_ctrl = tiny.oracle.control_model(x=x, hint=hint, timesteps=t, context=ctx)
+        ref_eps = tiny.oracle.model.diffusion_model(x=x, timesteps=t, context=ctx, control=ref_ctrl, only_mid_control=False)
+        ref_mid = tiny.oracle.model.diffusion_model(x=x, timesteps=t, context=ctx, control=ref_ctrl, only_mid_control=True)
+    for m, tolr in ((tiny.f32, TOL_F32), (tiny.bf16, TOL_BF16)):
+        ctrl = m.control_model(x=x, hint=hint, timesteps=t, context=ctx)
+        assert len(ctrl) == 13
+        for a, b in zip(ctrl, ref_ctrl):
+            assert a.shape == b.shape and rel(a, b) < tolr
+        eps = m.model.diffusion_model(x=x, timesteps=t, context=ctx, control=[c.clone() for c in ref_ctrl], only_mid_control=False)
+        assert rel(eps, ref_eps) < tolr
+    assert rel(tiny.f32.model.diffusion_model(x=x, timesteps=t, context=ctx, control=ref_ctrl, only_mid_control=True), ref_mid) < TOL_F32
+
+
+def _teacher_forced(bundle, B, h, cdim, S, cfg_scale=1.0):
+    cond, x = make_cond(B, h, cdim, seed=11)
+    uc = None
+    if cfg_scale != 1.0:
+        uc, _ = make_cond(B, h, cdim, seed=12)
+        uc["c_concat"] = cond["c_concat"]  # uc_cat = c_cat (diffusion_makeup.py:401)
+    so = MKDDIMSampler(bundle.oracle)
+    so.make_schedule(S, ddim_eta=0.0, verbose=False)
+    steps = np.flip(so.ddim_timesteps)
+    out = {"bf16": [], "f32": []}
+    samplers = {k: B200DDIMSampler(getattr(bundle, k), use_cuda_graph=False) for k in out}
+    for s in samplers.values():
+        s.make_schedule(S, ddim_eta=0.0, verbose=False)
+    xt = x
+    for i, step in enumerate(steps):
+        index = S - i - 1
+        ts = torch.full((B,), int(step), device=DEV, dtype=torch.long)
+        with torch.no_grad():
+            x_next, p0 = so.denoising_step(xt, cond, ts, index, unconditional_guidance_scale=cfg_scale,
+                                           unconditional_conditioning=uc)
+        for k, s in samplers.items():
+            xn, pp = s.denoising_step(xt, cond, ts, index, unconditional_guidance_scale=cfg_scale,
+                                      unconditional_conditioning=uc)
+            # x_prev / pred_x0 are affine in eps: compare the eps they imply
+            out[k].append(max(rel(xn, x_next), rel(pp, p0)))
+        xt = x_next
+    return out
+
+
+def test_sampler_teacher_forced_tiny(tiny):
+    r = _teacher_forced(tiny, 2, 16, 64, S=10)
+    assert max(r["f32"]) < TOL_F32, r["f32"]
+    assert max(r["bf16"]) < TOL_BF16, r["bf16"]
+
+
+def test_sampler_teacher_forced_cfg_tiny(tiny):
+    r = _teacher_forced(tiny, 2, 16, 64, S=5, cfg_scale=9.0)
+    assert max(r["f32"]) < 5 * TOL_F32, r["f32"]   # CFG scale 9 amplifies eps differences ~9x
+    assert max(r["bf16"]) < 5 * TOL_BF16, r["bf16"]
+
+
+def psnr(a, b):
+    peak = float(b.abs().max())
+    return 10 * math.log10(peak * peak / float(((a - b) ** 2).mean()))
+
+
+def test_free_running_psnr_and_graph(tiny):
+    """50 free-running steps: final latents within a PSNR bound of the oracle's; CUDA-graph replay == eager."""
+    B, h, S = 2, 16, 50
+    cond, x = make_cond(B, h, 64, seed=21)
+    with torch.no_grad():
+        ref, _ = MKDDIMSampler(tiny.oracle).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    a, inter = B200DDIMSampler(tiny.f32, use_cuda_graph=False).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    g, _ = B200DDIMSampler(tiny.f32, use_cuda_graph=True).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    b, _ = B200DDIMSampler(tiny.bf16, use_cuda_graph=True).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    assert torch.equal(a, g)
+    assert len(inter["x_inter"]) == 2 and len(inter["pred_x0"]) == 2  # log_every_t=100: start + last
+    p32, p16 = psnr(a, ref), psnr(b, ref)
+    print(f"free-running PSNR vs oracle: fp32-check {p32:.1f} dB, bf16 {p16:.1f} dB")
+    assert p32 > 60 and p16 > 25, (p32, p16)
+
+
+def test_sampler_kats_on_b200(tiny, monkeypatch):
+    B, h = 2, 16
+    cond, x = make_cond(B, h, 64, seed=5)
+    s = B200DDIMSampler(tiny.f32, use_cuda_graph=False)
+    # K6: reconstruct(t_start=S) == sample(x_T)
+    a, _ = s.sample(10, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    b = s.reconstruct(x, cond, t_start=10)
+    assert torch.equal(a, b)
+    # K5: eta=0 -> independent of RNG, but one randn(x.shape) per step is consumed (cddim.py:75)
+    torch.manual_seed(1)
+    s.sample(4, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    after = torch.rand(1, device=DEV)
+    torch.manual_seed(1)
+    for _ in range(4):
+        torch.randn(B, 4, h, h, device=DEV)
+    assert torch.equal(after, torch.rand(1, device=DEV))
+    # K3: scale == 1 or uc None -> single un-doubled call
+    calls = []
+    orig = tiny.f32.apply_model
+    monkeypatch.setattr(tiny.f32, "apply_model", lambda x, t, c: (calls.append(x.shape[0]), orig(x, t, c))[1])
+    ts = torch.full((B,), 981, device=DEV, dtype=torch.long)
+    s.denoising_step(x, cond, ts, 9, unconditional_guidance_scale=1.0, unconditional_conditioning=cond)
+    s.denoising_step(x, cond, ts, 9, unconditional_guidance_scale=9.0, unconditional_conditioning=None)
+    s.denoising_step(x, cond, ts, 9, unconditional_guidance_scale=9.0, unconditional_conditioning=cond)
+    assert calls == [B, B, 2 * B]
+    # K2: eps == 0 closed form
+    monkeypatch.setattr(tiny.f32, "apply_model", lambda x, t, c: torch.zeros_like(x))
+    z, _ = s.sample(50, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    torch.testing.assert_close(z, x * 13.152870, rtol=2e-5, atol=0)
+
+
+def test_eta_nonzero_uses_reference_noise_stream(tiny):
+    """eta > 0: with the same torch RNG seed the B200 sampler adds the same sigma*randn as the oracle"""
+    B, h = 1, 16
+    cond, x = make_cond(B, h, 64, seed=9)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        ref, _ = MKDDIMSampler(tiny.oracle).sample(5, B, (4, h, h), cond, eta=0.8, x_T=x, verbose=False)
+    torch.manual_seed(3)
+    out, _ = B200DDIMSampler(tiny.f32, use_cuda_graph=False).sample(5, B, (4, h, h), cond, eta=0.8, x_T=x, verbose=False)
+    assert rel(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("h,B", [(32, 2)])
+def test_full_size_parity(h, B):
+    """yaml-sized networks (859.5 M + 361.3 M parameters), 256^2 images: teacher-forced eps parity"""
+    full = Bundle({})
+    cond, x = make_cond(B, h, 768, seed=1)
+    for step in (981, 501, 1):
+        t = torch.full((B,), step, device=DEV, dtype=torch.long)
+        with torch.no_grad():
+            ref = full.oracle.apply_model(x, t, cond)
+        r32, r16 = rel(full.f32.apply_model(x, t, cond), ref), rel(full.bf16.apply_model(x, t, cond), ref)
+        print(f"full-size t={step}: rel-L2 fp32-check {r32:.2e}  bf16 {r16:.2e}")
+        assert r32 < TOL_F32 and r16 < TOL_BF16
+    del full
+    torch.cuda.empty_cache()
