@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 1
+#define MKD_ABI_VERSION 2
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 
@@ -77,15 +77,17 @@ int mkd_add(const void* a, const void* b, void* y, int dtype, int64_t M, int C, 
 /* ---- GroupNorm(32 groups) [+ SiLU], NHWC -------------------------------------------------------------------
  * replaces upstream GroupNorm32/GroupNorm + SiLU at ResBlock.in_layers/out_layers, SpatialTransformer.norm,
  * UNet.out (reached from makeup_diffuse.py:164-168).  Statistics in fp32 over (C/groups * HW) per sample.
+ * x_dtype / y_dtype may differ: tensors that are not tensor-core operands (the residual trunk, ResBlock `h`) are
+ * kept in fp32 by the bf16 path so that their rounding does not accumulate; norm outputs (GEMM operands) are bf16.
  * workspace: >= mkd_groupnorm_workspace_bytes(N, groups) bytes, fp32-aligned. */
 size_t mkd_groupnorm_workspace_bytes(int N, int groups);
-int mkd_groupnorm(const void* x, void* y, int dtype, int N, int HW, int C, int groups, int ldx, int ldy,
-                  const float* gamma, const float* beta, float eps, int silu, void* workspace,
+int mkd_groupnorm(const void* x, void* y, int x_dtype, int y_dtype, int N, int HW, int C, int groups, int ldx,
+                  int ldy, const float* gamma, const float* beta, float eps, int silu, void* workspace,
                   size_t workspace_bytes, mkd_stream_t stream);
 
 /* ---- LayerNorm over the last dim (BasicTransformerBlock.norm1/2/3) ---------------------------------------- */
-int mkd_layernorm(const void* x, void* y, int dtype, int64_t M, int C, int ldx, int ldy, const float* gamma,
-                  const float* beta, float eps, mkd_stream_t stream);
+int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,
+                  const float* gamma, const float* beta, float eps, mkd_stream_t stream);
 
 /* ---- convolution / GEMM family --------------------------------------------------------------------------
  * One descriptor covers every contraction of the path: ResBlock 3x3 convs, Down (stride 2) / Up (nearest x2
@@ -95,6 +97,7 @@ int mkd_layernorm(const void* x, void* y, int dtype, int64_t M, int C, int ldx, 
  *   v            = alpha * (acc + bias[k] + emb[n, k]) + residual[n,p,q,k]
  *   Y[n,p,q,k]   = act(v)
  *
+ *   The result goes to `y` (activation dtype) and/or `y32` (fp32, pixel stride ldy32); at least one is non-NULL.
  *   bias / emb / residual may be NULL.  `residual == y` (same pointer, ldr == ldy) is the fused ControlNet
  *   injection  hs[i] += scale_i * zero_conv_i(h)  of makeup_diffuse.py:166 + upstream `hs.pop() + control.pop()`.
  *   `y` / `x` may point into a wider buffer (ld > channels): that is how skip tensors are produced straight
@@ -121,6 +124,9 @@ typedef struct mkd_conv_desc {
   const float* bias;
   const void* emb; /* [N, lde] activations dtype */
   const void* residual;
+  int residual_dtype; /* MKD_BF16 / MKD_F32: storage type of `residual` (fp32 for trunk tensors kept unrounded) */
+  int ldy32;
+  float* y32;         /* optional fp32 copy of the output (same values before rounding); `y` may then be NULL */
   void* workspace; /* split-K partials (tcgen05 path); may be NULL -> no split-K */
   size_t workspace_bytes;
 } mkd_conv_desc;

@@ -22,12 +22,14 @@ struct ConvP {
   int gb;        // geglu block
   int act;
   float alpha;
+  int res_f32, ldy32;
+  float* y32;
 };
 
 template <typename T, bool GEGLU>
 __global__ void __launch_bounds__(256) conv_generic_kernel(ConvP p, const T* __restrict__ x, const T* __restrict__ w,
                                                            T* __restrict__ y, const float* __restrict__ bias,
-                                                           const T* __restrict__ emb, const T* __restrict__ res) {
+                                                           const T* __restrict__ emb, const void* __restrict__ res) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[GEGLU ? 2 : 1][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -132,10 +134,13 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvP p, const T* __r
         if (bias) v += bias[o];
         if (emb) v += to_f(emb[(int64_t)nimg * p.lde + o]);
         v *= p.alpha;
-        if (res) v += to_f(res[(int64_t)mm * p.ldr + o]);
+        if (res)
+          v += p.res_f32 ? static_cast<const float*>(res)[(int64_t)mm * p.ldr + o]
+                         : to_f(static_cast<const T*>(res)[(int64_t)mm * p.ldr + o]);
         if (p.act == MKD_ACT_SILU) v = silu_f(v);
       }
-      y[(int64_t)mm * p.ldy + o] = from_f<T>(v);
+      if (p.y32) p.y32[(int64_t)mm * p.ldy32 + o] = v;
+      if (y) y[(int64_t)mm * p.ldy + o] = from_f<T>(v);
     }
   }
 }
@@ -157,25 +162,28 @@ int conv2d_generic(const mkd_conv_desc* d, cudaStream_t stream) {
   p.gb = d->geglu_block > 0 ? d->geglu_block : 1;
   p.Kout = d->act == MKD_ACT_GEGLU ? d->K / 2 : d->K;
   p.alpha = d->alpha;
+  p.res_f32 = (d->residual_dtype == MKD_F32 || d->dtype == MKD_F32) ? 1 : 0;
+  p.y32 = d->y32;
+  p.ldy32 = d->ldy32;
   dim3 grid((p.M + BM - 1) / BM, (p.Kout + BN - 1) / BN);
   MKD_REQUIRE(grid.y <= 65535, MKD_E_INVALID, "conv2d: K too large");
   const bool geglu = d->act == MKD_ACT_GEGLU;
   if (d->dtype == MKD_BF16) {
     if (geglu)
       conv_generic_kernel<bf16, true><<<grid, 256, 0, stream>>>(p, (const bf16*)d->x, (const bf16*)d->w, (bf16*)d->y,
-                                                                d->bias, (const bf16*)d->emb, (const bf16*)d->residual);
+                                                                d->bias, (const bf16*)d->emb, d->residual);
     else
       conv_generic_kernel<bf16, false><<<grid, 256, 0, stream>>>(p, (const bf16*)d->x, (const bf16*)d->w, (bf16*)d->y,
-                                                                 d->bias, (const bf16*)d->emb, (const bf16*)d->residual);
+                                                                 d->bias, (const bf16*)d->emb, d->residual);
   } else {
     if (geglu)
       conv_generic_kernel<float, true><<<grid, 256, 0, stream>>>(p, (const float*)d->x, (const float*)d->w,
                                                                  (float*)d->y, d->bias, (const float*)d->emb,
-                                                                 (const float*)d->residual);
+                                                                 d->residual);
     else
       conv_generic_kernel<float, false><<<grid, 256, 0, stream>>>(p, (const float*)d->x, (const float*)d->w,
                                                                   (float*)d->y, d->bias, (const float*)d->emb,
-                                                                  (const float*)d->residual);
+                                                                  d->residual);
   }
   MKD_CHECK_LAUNCH();
   return MKD_OK;
@@ -185,13 +193,15 @@ int conv2d_generic(const mkd_conv_desc* d, cudaStream_t stream) {
 static int validate(const mkd_conv_desc* d) {
   MKD_REQUIRE(d != nullptr, MKD_E_INVALID, "conv2d: null descriptor");
   MKD_REQUIRE(d->dtype == MKD_BF16 || d->dtype == MKD_F32, MKD_E_INVALID, "conv2d: bad dtype %d", d->dtype);
-  MKD_REQUIRE(d->x && d->w && d->y, MKD_E_INVALID, "conv2d: null x/w/y");
+  MKD_REQUIRE(d->x && d->w && (d->y || d->y32), MKD_E_INVALID, "conv2d: null x/w/y");
+  MKD_REQUIRE(d->residual_dtype == MKD_BF16 || d->residual_dtype == MKD_F32, MKD_E_INVALID, "conv2d: bad residual_dtype");
   MKD_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0 && d->stride > 0 &&
                   d->pad >= 0,
               MKD_E_INVALID, "conv2d: non-positive dimension");
   MKD_REQUIRE(d->ldx >= d->C, MKD_E_INVALID, "conv2d: ldx %d < C %d", d->ldx, d->C);
   const int kout = d->act == MKD_ACT_GEGLU ? d->K / 2 : d->K;
-  MKD_REQUIRE(d->ldy >= kout, MKD_E_INVALID, "conv2d: ldy %d < output channels %d", d->ldy, kout);
+  MKD_REQUIRE(!d->y || d->ldy >= kout, MKD_E_INVALID, "conv2d: ldy %d < output channels %d", d->ldy, kout);
+  MKD_REQUIRE(!d->y32 || d->ldy32 >= kout, MKD_E_INVALID, "conv2d: ldy32 %d < output channels %d", d->ldy32, kout);
   MKD_REQUIRE(!d->residual || d->ldr >= kout, MKD_E_INVALID, "conv2d: ldr too small");
   MKD_REQUIRE(!d->emb || d->lde >= kout, MKD_E_INVALID, "conv2d: lde too small");
   MKD_REQUIRE(d->act >= MKD_ACT_NONE && d->act <= MKD_ACT_GEGLU, MKD_E_INVALID, "conv2d: bad act");

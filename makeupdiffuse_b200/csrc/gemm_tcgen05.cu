@@ -30,10 +30,12 @@ struct EpiP {
   int pix_per_img;   // P*Q  (emb row = m / pix_per_img)
   int act;
   float alpha;
-  bf16* y;
+  bf16* y;           // bf16 output (may be null when y32 is set)
+  float* y32;        // optional fp32 copy of the output
+  int ldy32, res_f32;
   const float* bias;
   const bf16* emb;
-  const bf16* res;
+  const void* res;   // bf16 or fp32 (res_f32)
   float* partial;    // split-K workspace or nullptr
 };
 
@@ -144,7 +146,8 @@ __device__ __forceinline__ void epilogue_store16(const EpiP& e, int m, int n, fl
       for (int i = 0; i < 8; ++i) r[i] *= e.alpha;
       if (e.res) {
         float t[8];
-        load8(e.res + (int64_t)m * e.ldr + o, t);
+        if (e.res_f32) load8(static_cast<const float*>(e.res) + (int64_t)m * e.ldr + o, t);
+        else load8(static_cast<const bf16*>(e.res) + (int64_t)m * e.ldr + o, t);
 #pragma unroll
         for (int i = 0; i < 8; ++i) r[i] += t[i];
       }
@@ -152,15 +155,19 @@ __device__ __forceinline__ void epilogue_store16(const EpiP& e, int m, int n, fl
 #pragma unroll
         for (int i = 0; i < 8; ++i) r[i] = silu_f(r[i]);
       }
-      store8(e.y + (int64_t)m * e.ldy + o, r);
+      if (e.y32) store8(e.y32 + (int64_t)m * e.ldy32 + o, r);
+      if (e.y) store8(e.y + (int64_t)m * e.ldy + o, r);
     } else {  // ragged channel tail (e.g. the 4-channel `out` conv): scalar
       for (int i = 0; i < 8 && o + i < e.N_out; ++i) {
         float t = v[j + i] + (e.bias ? e.bias[o + i] : 0.f);
         if (e.emb) t += to_f(e.emb[(int64_t)nimg * e.lde + o + i]);
         t *= e.alpha;
-        if (e.res) t += to_f(e.res[(int64_t)m * e.ldr + o + i]);
+        if (e.res)
+          t += e.res_f32 ? static_cast<const float*>(e.res)[(int64_t)m * e.ldr + o + i]
+                         : to_f(static_cast<const bf16*>(e.res)[(int64_t)m * e.ldr + o + i]);
         if (e.act == MKD_ACT_SILU) t = silu_f(t);
-        e.y[(int64_t)m * e.ldy + o + i] = from_f<bf16>(t);
+        if (e.y32) e.y32[(int64_t)m * e.ldy32 + o + i] = t;
+        if (e.y) e.y[(int64_t)m * e.ldy + o + i] = from_f<bf16>(t);
       }
     }
   }
@@ -383,7 +390,10 @@ bool geometry(const mkd_conv_desc* d, Geometry& g) {
   if (d->C % BK != 0) { set_error("C=%d is not a multiple of 64", d->C); return false; }
   if (d->stride != 1 || d->upsample) { set_error("stride/upsample convs use the generic kernel"); return false; }
   if (d->R != d->S || (d->R != 1 && d->R != 3) || d->pad != d->R / 2) { set_error("filter is not 1x1/p0 or 3x3/p1"); return false; }
-  if (d->ldx % 8 || d->ldy % 8 || !aligned16(d->x) || !aligned16(d->w) || !aligned16(d->y)) { set_error("x/w/y alignment"); return false; }
+  if (d->ldx % 8 || !aligned16(d->x) || !aligned16(d->w)) { set_error("x/w alignment"); return false; }
+  if (d->y && (d->ldy % 8 || !aligned16(d->y))) { set_error("y alignment"); return false; }
+  if (d->y32 && (d->ldy32 % 8 || !aligned16(d->y32))) { set_error("y32 alignment"); return false; }
+  if (d->act == MKD_ACT_GEGLU && !d->y) { set_error("GEGLU writes the bf16 output only"); return false; }
   if (d->residual && (d->ldr % 8 || !aligned16(d->residual))) { set_error("residual alignment"); return false; }
   if (d->emb && (d->lde % 8 || !aligned16(d->emb))) { set_error("emb alignment"); return false; }
   g.conv = d->R == 3;
@@ -476,7 +486,8 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   ep.ldy = d->ldy; ep.ldr = d->ldr; ep.lde = d->lde;
   ep.pix_per_img = g.P * g.Q;
   ep.act = d->act; ep.alpha = d->alpha;
-  ep.y = (bf16*)d->y; ep.bias = d->bias; ep.emb = (const bf16*)d->emb; ep.res = (const bf16*)d->residual;
+  ep.y = (bf16*)d->y; ep.bias = d->bias; ep.emb = (const bf16*)d->emb; ep.res = d->residual;
+  ep.y32 = d->y32; ep.ldy32 = d->ldy32; ep.res_f32 = d->residual_dtype == MKD_F32;
   ep.partial = splits > 1 ? (float*)d->workspace : nullptr;
 
   dim3 grid(g.m_tiles, n_tiles, splits);

@@ -58,8 +58,8 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ pa
   }
 }
 
-template <typename T, bool SILU>
-__global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float2* __restrict__ partial,
+template <typename T, typename TO, bool SILU>
+__global__ void gn_apply_kernel(const T* __restrict__ x, TO* __restrict__ y, const float2* __restrict__ partial,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
                                 int groups, int ldx, int ldy, int rows_per_chunk, int nchunks, float eps) {
   extern __shared__ float sm[];  // scale[C], shift[C]
@@ -95,7 +95,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
     sh[j] = shift[vx * 8 + j];
   }
   const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
-  T* yb = y + (int64_t)n * HW * ldy + vx * 8;
+  TO* yb = y + (int64_t)n * HW * ldy + vx * 8;
   for (int r = r0 + ry; r < r1; r += RY) {
     float v[8];
     load8(xb + (int64_t)r * ldx, v);
@@ -111,8 +111,8 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
 // LayerNorm: one warp per row, the row lives in registers between the mean and the variance pass
 // (exact two-pass variance, like the reference).  C <= 8 * 32 * LN_VPL.
 constexpr int LN_VPL = 8;
-template <typename T>
-__global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t M, int C, int ldx, int ldy,
+template <typename T, typename TO>
+__global__ void layernorm_kernel(const T* __restrict__ x, TO* __restrict__ y, int64_t M, int C, int ldx, int ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -162,8 +162,8 @@ extern "C" size_t mkd_groupnorm_workspace_bytes(int N, int groups) {
   return (size_t)N * GN_MAX_CHUNKS * groups * sizeof(float2);
 }
 
-template <typename T>
-static int groupnorm_launch(const T* x, T* y, int N, int HW, int C, int groups, int ldx, int ldy, const float* gamma,
+template <typename T, typename TO>
+static int groupnorm_launch(const T* x, TO* y, int N, int HW, int C, int groups, int ldx, int ldy, const float* gamma,
                             const float* beta, float eps, int silu, float2* partial, cudaStream_t st) {
   const int VX = C / 8;
   int threads = VX >= 256 ? VX : (256 / VX) * VX;  // whole number of row lanes
@@ -183,17 +183,17 @@ static int groupnorm_launch(const T* x, T* y, int N, int HW, int C, int groups, 
   gn_stats_kernel<T><<<grid, threads, sm1, st>>>(x, partial, HW, C, groups, ldx, rows_per_chunk, nchunks);
   MKD_CHECK_LAUNCH();
   if (silu)
-    gn_apply_kernel<T, true><<<grid, threads, sm2, st>>>(x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
+    gn_apply_kernel<T, TO, true><<<grid, threads, sm2, st>>>(x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
                                                          rows_per_chunk, nchunks, eps);
   else
-    gn_apply_kernel<T, false><<<grid, threads, sm2, st>>>(x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
+    gn_apply_kernel<T, TO, false><<<grid, threads, sm2, st>>>(x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
                                                           rows_per_chunk, nchunks, eps);
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
 
-extern "C" int mkd_groupnorm(const void* x, void* y, int dtype, int N, int HW, int C, int groups, int ldx, int ldy,
-                             const float* gamma, const float* beta, float eps, int silu, void* workspace,
+extern "C" int mkd_groupnorm(const void* x, void* y, int x_dtype, int y_dtype, int N, int HW, int C, int groups, int ldx,
+                             int ldy, const float* gamma, const float* beta, float eps, int silu, void* workspace,
                              size_t workspace_bytes, mkd_stream_t stream) {
   MKD_REQUIRE(x && y && gamma && beta && workspace && N > 0 && HW > 0 && C > 0 && groups > 0, MKD_E_INVALID,
               "groupnorm: bad args");
@@ -205,14 +205,17 @@ extern "C" int mkd_groupnorm(const void* x, void* y, int dtype, int N, int HW, i
   MKD_REQUIRE(workspace_bytes >= mkd_groupnorm_workspace_bytes(N, groups), MKD_E_WORKSPACE,
               "groupnorm: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MKD_BF16)
-    return groupnorm_launch<bf16>((const bf16*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu,
-                                  (float2*)workspace, st);
-  return groupnorm_launch<float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu,
-                                 (float2*)workspace, st);
+  float2* ws = (float2*)workspace;
+  if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
+    return groupnorm_launch<bf16, bf16>((const bf16*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, st);
+  if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
+    return groupnorm_launch<float, bf16>((const float*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, st);
+  if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
+    return groupnorm_launch<float, float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, st);
+  MKD_REQUIRE(false, MKD_E_INVALID, "groupnorm: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
 }
 
-extern "C" int mkd_layernorm(const void* x, void* y, int dtype, int64_t M, int C, int ldx, int ldy,
+extern "C" int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,
                              const float* gamma, const float* beta, float eps, mkd_stream_t stream) {
   MKD_REQUIRE(x && y && gamma && beta && M > 0 && C > 0, MKD_E_INVALID, "layernorm: bad args");
   MKD_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_VPL, MKD_E_INVALID, "layernorm: C=%d must be a multiple of 8, <= %d", C,
@@ -222,10 +225,14 @@ extern "C" int mkd_layernorm(const void* x, void* y, int dtype, int64_t M, int C
   const int warps = 8;
   int64_t blocks = (M + warps - 1) / warps;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MKD_BF16)
-    layernorm_kernel<bf16><<<(unsigned)blocks, warps * 32, 0, st>>>((const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps);
+  if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
+    layernorm_kernel<bf16, bf16><<<(unsigned)blocks, warps * 32, 0, st>>>((const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps);
+  else if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
+    layernorm_kernel<float, bf16><<<(unsigned)blocks, warps * 32, 0, st>>>((const float*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps);
+  else if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
+    layernorm_kernel<float, float><<<(unsigned)blocks, warps * 32, 0, st>>>((const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps);
   else
-    layernorm_kernel<float><<<(unsigned)blocks, warps * 32, 0, st>>>((const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps);
+    MKD_REQUIRE(false, MKD_E_INVALID, "layernorm: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }

@@ -30,6 +30,21 @@ from . import ops
 _SPLITK_WS_BYTES = 96 << 20
 
 
+class Act:
+    """A trunk tensor of the bf16 path, stored up to twice:
+    ``lo`` — activation dtype (bf16), what tensor-core A operands and the decoder's concat slots read;
+    ``hi`` — fp32 copy written by the same epilogue, what norms and residual adds read, so that the residual
+             stream is not re-rounded at every block (that rounding, not the bf16 MMAs, dominated the eps error).
+    In the fp32 check mode only ``lo`` (fp32) exists."""
+    __slots__ = ("lo", "hi")
+
+    def __init__(self, lo=None, hi=None):
+        self.lo, self.hi = lo, hi
+
+    def src(self):
+        return self.hi if self.hi is not None else self.lo
+
+
 def _geglu_block(inner: int) -> int:
     for gb in (80, 64, 32, 16, 8):
         if inner % gb == 0:
@@ -176,6 +191,7 @@ class _Net(nn.Module):
 
     # ---- building blocks ---------------------------------------------------------------------------------------
     def _conv(self, x, wkey, y, N, H, W, R=1, **kw):
+        """y: activation-dtype output view or None; kw may carry y32= (fp32 copy), residual=, emb=, act= ..."""
         ops.conv2d(x, self.w[wkey + ".w"], y, N=N, H=H, W=W, R=R, S=R, pad=R // 2 if "pad" not in kw else kw.pop("pad"),
                    bias=self.w.get(wkey + ".b"), workspace=self._ws, **kw)
 
@@ -195,31 +211,55 @@ class _Net(nn.Module):
         self._linear(e2, "emb_all", ea)
         return ea
 
+    @property
+    def _hi(self):
+        return self.dtype != torch.float32
+
+    def _side(self, name, rows, cols):
+        """a non-operand intermediate: fp32 in the bf16 path (returned as (None, buf32)), plain buffer in check mode"""
+        if self._hi:
+            return None, self._buf(name + "32", rows, cols, torch.float32)
+        return self._buf(name, rows, cols), None
+
+    def _act(self, name, rows, cols, lo=True, hi=True):
+        """allocate an Act with the requested forms (check mode: always just lo)"""
+        if not self._hi:
+            return Act(self._buf(name, rows, cols))
+        return Act(self._buf(name, rows, cols) if lo else None,
+                   self._buf(name + "32", rows, cols, torch.float32) if hi else None)
+
     def _res(self, layer, x, y, emb_all, N, H, W):
+        """x, y: Act.  h and the skip projection never feed a tensor core directly -> fp32 side buffers."""
         _, key, cin, cout = layer
         M = N * H * W
         t1 = self._buf("gn_a", M, cin)
-        ops.groupnorm(x, t1, N, self.w[key + ".gn1.g"], self.w[key + ".gn1.b"], 1e-5, True, self._gn_ws(N))
-        h = self._buf("res_h", M, cout)
+        ops.groupnorm(x.src(), t1, N, self.w[key + ".gn1.g"], self.w[key + ".gn1.b"], 1e-5, True, self._gn_ws(N))
+        h_lo, h_hi = self._side("res_h", M, cout)
         e = emb_all[:, self._emb_off[key]:self._emb_off[key] + cout]
-        self._conv(t1, key + ".c1", h, N, H, W, R=3, emb=e)
+        self._conv(t1, key + ".c1", h_lo, N, H, W, R=3, emb=e, y32=h_hi)
         t2 = self._buf("gn_b", M, cout)
-        ops.groupnorm(h, t2, N, self.w[key + ".gn2.g"], self.w[key + ".gn2.b"], 1e-5, True, self._gn_ws(N))
+        ops.groupnorm(h_hi if h_hi is not None else h_lo, t2, N, self.w[key + ".gn2.g"], self.w[key + ".gn2.b"], 1e-5,
+                      True, self._gn_ws(N))
         if cin != cout:
-            sk = self._buf("res_sk", M, cout)
-            self._conv(x, key + ".sk", sk, N, H, W, R=1)
+            s_lo, s_hi = self._side("res_sk", M, cout)
+            self._conv(x.lo, key + ".sk", s_lo, N, H, W, R=1, y32=s_hi)
+            sk = s_hi if s_hi is not None else s_lo
         else:
-            sk = x
-        self._conv(t2, key + ".c2", y, N, H, W, R=3, residual=sk)
+            sk = x.src()
+        self._conv(t2, key + ".c2", y.lo, N, H, W, R=3, residual=sk, y32=y.hi)
 
     def _st(self, layer, x, y, ctx_kv, N, H, W):
+        """x, y: Act.  The token stream xs (x += attn1, += attn2, += ff) lives in fp32 until its last update, which
+        writes the bf16 operand of proj_out directly."""
         _, key, ch = layer
         M, hd = N * H * W, ch // self.heads
         scale = hd ** -0.5
         n = self._buf("st_n", M, ch)
-        ops.groupnorm(x, n, N, self.w[key + ".gn.g"], self.w[key + ".gn.b"], 1e-6, False, self._gn_ws(N))
-        xs = self._buf("st_x", M, ch)
-        self._conv(n, key + ".pi", xs, N, H, W, R=1)
+        ops.groupnorm(x.src(), n, N, self.w[key + ".gn.g"], self.w[key + ".gn.b"], 1e-6, False, self._gn_ws(N))
+        x_lo, x_hi = self._side("st_x", M, ch)
+        xs = x_hi if x_hi is not None else x_lo           # the stream every LN / residual reads
+        o_lo, o_hi = (None, xs) if self._hi else (xs, None)  # how an in-place update of xs is written
+        self._conv(n, key + ".pi", o_lo, N, H, W, R=1, y32=o_hi)
         ln = self._buf("st_ln", M, ch)
         # self-attention
         ops.layernorm(xs, ln, self.w[key + ".norm1.g"], self.w[key + ".norm1.b"])
@@ -228,7 +268,7 @@ class _Net(nn.Module):
         att = self._buf("st_att", M, ch)
         ops.attention(qkv[:, :ch], qkv[:, ch:2 * ch], qkv[:, 2 * ch:], att, B=N, heads=self.heads, Nq=H * W, Nkv=H * W,
                       d=hd, scale=scale)
-        self._linear(att, key + ".o1", xs, residual=xs)
+        self._linear(att, key + ".o1", o_lo, residual=xs, y32=o_hi)
         # cross-attention (K/V of the step-invariant context are precomputed: ctx_kv[key] = [N*L, 2*ch])
         ops.layernorm(xs, ln, self.w[key + ".norm2.g"], self.w[key + ".norm2.b"])
         q2 = self._buf("st_q2", M, ch)
@@ -236,14 +276,15 @@ class _Net(nn.Module):
         kv = ctx_kv[key]
         Lc = kv.shape[0] // N
         ops.attention(q2, kv[:, :ch], kv[:, ch:], att, B=N, heads=self.heads, Nq=H * W, Nkv=Lc, d=hd, scale=scale)
-        self._linear(att, key + ".o2", xs, residual=xs)
+        self._linear(att, key + ".o2", o_lo, residual=xs, y32=o_hi)
         # GEGLU feed-forward (gate fused into the first GEMM's epilogue)
         ops.layernorm(xs, ln, self.w[key + ".norm3.g"], self.w[key + ".norm3.b"])
         inner = 4 * ch
         ff = self._buf("st_ff", M, inner)
         self._linear(ln, key + ".ff1", ff, act=L.ACT_GEGLU, geglu_block=_geglu_block(inner))
-        self._linear(ff, key + ".ff2", xs, residual=xs)
-        self._conv(xs, key + ".po", y, N, H, W, R=1, residual=x)
+        xa = self._buf("st_xa", M, ch) if self._hi else xs  # proj_out's A operand (activation dtype)
+        self._linear(ff, key + ".ff2", xa, residual=xs)
+        self._conv(xa, key + ".po", y.lo, N, H, W, R=1, residual=x.src(), y32=y.hi)
 
     def context_kv(self, context):
         """attn2 K/V projections of the (step-invariant) text context for every SpatialTransformer: hoisted out of
@@ -266,30 +307,47 @@ class _Net(nn.Module):
         ops.nchw_to_nhwc(x.float().contiguous(), v)
         return v
 
-    def _run_block(self, layers, x, y, emb_all, ctx_kv, N, H, W):
-        """runs a block's layers x -> y through ping-pong temporaries; returns output spatial size"""
+    @staticmethod
+    def _needs(layer):
+        """(lo, hi) forms a layer reads of its input: A operands want lo, norms / identity residuals want hi"""
+        kind = layer[0]
+        if kind == "res":
+            return layer[2] != layer[3], True
+        if kind == "st":
+            return False, True
+        return True, False  # down / up / conv: tensor-core operand only
+
+    def _run_block(self, layers, x, y, emb_all, ctx_kv, N, H, W, conv_in_residual=None):
+        """runs a block's layers x -> y (Acts) through ping-pong temporaries; returns the output spatial size"""
         cur = x
         for li, layer in enumerate(layers):
             last = li == len(layers) - 1
             kind = layer[0]
+            if not last:
+                lo, hi = self._needs(layers[li + 1])
+                out = self._act(f"pp{li % 2}", N * H * W, layer[3] if kind == "res" else layer[2], lo=lo, hi=hi)
+            else:
+                out = y
             if kind == "conv_in":
-                self._conv(cur, layer[1], y, N, H, W, R=3)
+                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, residual=conv_in_residual, y32=out.hi)
             elif kind == "res":
-                out = y if last else self._buf(f"pp{li % 2}", N * H * W, layer[3])
                 self._res(layer, cur, out, emb_all, N, H, W)
-                cur = out
             elif kind == "st":
-                out = y if last else self._buf(f"pp{li % 2}", N * H * W, layer[2])
                 self._st(layer, cur, out, ctx_kv, N, H, W)
-                cur = out
             elif kind == "down":
-                self._conv(cur, layer[1], y, N, H, W, R=3, stride=2)
+                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, stride=2, y32=out.hi)
                 H, W = H // 2, W // 2
             elif kind == "up":
                 assert last
-                self._conv(cur, layer[1], y, N, H, W, R=3, upsample=True)
+                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, upsample=True, y32=out.hi)
                 H, W = 2 * H, 2 * W
+            cur = out
         return H, W
+
+    def _next_needs_hi(self, j):
+        """does the consumer of input block j's output (block j+1, or the middle block) read the fp32 form?"""
+        nxt = self.input_blocks[j + 1][0] if j + 1 < len(self.input_blocks) else self.middle[0]
+        return self._needs(nxt)[1]
 
 
 class B200ControlNet(_Net):
@@ -334,19 +392,18 @@ class B200ControlNet(_Net):
         the UNet's skip slots) is given — accumulates ``scale_i * zero_conv_i(h)`` straight into them."""
         emb_all = self._time_embedding(t, N)
         outs = []
-        cur, h, w = x_nhwc, H, W
+        cur, h, w = Act(x_nhwc), H, W
         for j, blk in enumerate(self.input_blocks):
             ch = self.block_chans[j]
             ho, wo = (h // 2, w // 2) if blk[0][0] == "down" else (h, w)
-            y = self._buf(f"cn_h{j}", N * ho * wo, ch)
-            self._run_block(blk, cur, y, emb_all, ctx_kv, N, h, w)
-            if j == 0:
-                ops.add(y, guided_hint, y)
+            y = self._act(f"cn_h{j}", N * ho * wo, ch, lo=True, hi=self._next_needs_hi(j))
+            # h = input_blocks[0](x) + guided_hint: the add rides in conv_in's epilogue
+            self._run_block(blk, cur, y, emb_all, ctx_kv, N, h, w, conv_in_residual=guided_hint if j == 0 else None)
             cur, h, w = y, ho, wo
-            outs.append(self._zero_conv(f"zero_convs.{j}.0", cur, j, N, h, w, inject, scales))
-        y = self._buf("cn_mid", N * h * w, self._ch)
+            outs.append(self._zero_conv(f"zero_convs.{j}.0", cur.lo, j, N, h, w, inject, scales))
+        y = self._act("cn_mid", N * h * w, self._ch, lo=True, hi=False)
         self._run_block(self.middle, cur, y, emb_all, ctx_kv, N, h, w)
-        outs.append(self._zero_conv("middle_block_out.0", y, len(self.input_blocks), N, h, w, inject, scales))
+        outs.append(self._zero_conv("middle_block_out.0", y.lo, len(self.input_blocks), N, h, w, inject, scales))
         return outs
 
     def _zero_conv(self, key, x, j, N, h, w, inject, scales):
@@ -432,11 +489,14 @@ class B200ControlledUnet(_Net):
     def encode(self, x_nhwc, t, ctx_kv, N, H, W):
         self._emb_cur = self._time_embedding(t, N)
         slots = self.skip_slots(N, H, W)
-        cur, h, w = x_nhwc, H, W
+        cur, h, w = Act(x_nhwc), H, W
         for j, blk in enumerate(self.input_blocks):
-            h, w = self._run_block(blk, cur, slots[j], self._emb_cur, ctx_kv, N, h, w)
-            cur = slots[j]
-        self._run_block(self.middle, cur, slots[-1], self._emb_cur, ctx_kv, N, h, w)
+            # bf16 copy straight into the decoder's concat slot; fp32 copy for the next block's norm / identity skip
+            y = Act(slots[j], self._buf(f"enc{j}_32", slots[j].shape[0], slots[j].shape[1], torch.float32)
+                    if self._hi and self._next_needs_hi(j) else None)
+            h, w = self._run_block(blk, cur, y, self._emb_cur, ctx_kv, N, h, w)
+            cur = y
+        self._run_block(self.middle, cur, Act(slots[-1]), self._emb_cur, ctx_kv, N, h, w)
         return slots
 
     def decode(self, ctx_kv, N, H, W):
@@ -445,13 +505,13 @@ class B200ControlledUnet(_Net):
             cat, _, ds = self._cat(i, N, H, W)
             if i + 1 < nb:
                 nxt, nch, _ = self._cat(i + 1, N, H, W)
-                y = nxt[:, :nch]
+                y = Act(nxt[:, :nch])
             else:
-                y = self._buf("dec_out", N * H * W, self._out_ch)
-            self._run_block(blk, cat, y, self._emb_cur, ctx_kv, N, H // ds, W // ds)
+                y = self._act("dec_out", N * H * W, self._out_ch, lo=False, hi=True)  # only the out GroupNorm reads it
+            self._run_block(blk, Act(cat), y, self._emb_cur, ctx_kv, N, H // ds, W // ds)
         M = N * H * W
         g = self._buf("gn_a", M, self._out_ch)
-        ops.groupnorm(y, g, N, self.w["out.gn.g"], self.w["out.gn.b"], 1e-5, True, self._gn_ws(N))
+        ops.groupnorm(y.src(), g, N, self.w["out.gn.g"], self.w["out.gn.b"], 1e-5, True, self._gn_ws(N))
         eo = self._buf("eps_nhwc", M, 8)
         self._conv(g, "out.2", eo[:, :self.out_channels], N, H, W, R=3)
         return eo[:, :self.out_channels]

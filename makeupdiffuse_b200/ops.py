@@ -111,7 +111,7 @@ def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
     py, ldy = _rows(y2d)
     M, Cc = x2d.shape
     assert M % N == 0 and y2d.shape == x2d.shape and gamma.dtype == torch.float32 and beta.dtype == torch.float32
-    L.check(L.load().mkd_groupnorm(px, py, _dt(x2d), N, M // N, Cc, groups, ldx, ldy, gamma.data_ptr(), beta.data_ptr(),
+    L.check(L.load().mkd_groupnorm(px, py, _dt(x2d), _dt(y2d), N, M // N, Cc, groups, ldx, ldy, gamma.data_ptr(), beta.data_ptr(),
                                    float(eps), int(bool(silu)), workspace.data_ptr(),
                                    workspace.numel() * workspace.element_size(), _stream()), "groupnorm")
 
@@ -121,27 +121,38 @@ def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
     py, ldy = _rows(y2d)
     M, Cc = x2d.shape
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
-    L.check(L.load().mkd_layernorm(px, py, _dt(x2d), M, Cc, ldx, ldy, gamma.data_ptr(), beta.data_ptr(), float(eps),
+    L.check(L.load().mkd_layernorm(px, py, _dt(x2d), _dt(y2d), M, Cc, ldx, ldy, gamma.data_ptr(), beta.data_ptr(), float(eps),
                                    _stream()), "layernorm")
 
 
 def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None,
-                   residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None) -> L.ConvDesc:
+                   residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None,
+                   y32=None) -> L.ConvDesc:
+    """y2d: output in the activation dtype (or None); y32: optional fp32 copy of the same result."""
     px, ldx = _rows(x2d)
-    py, ldy = _rows(y2d)
     Cc = x2d.shape[1]
     K = w.shape[0]
     assert x2d.shape[0] == N * H * W, (x2d.shape, N, H, W)
-    assert w.is_contiguous() and w.numel() == K * R * S * Cc and w.dtype == x2d.dtype == y2d.dtype
-    if y2d.shape[1] != (K // 2 if act == L.ACT_GEGLU else K):
-        raise ValueError(f"output view has {y2d.shape[1]} channels, the filter bank produces {K}")
+    assert w.is_contiguous() and w.numel() == K * R * S * Cc and w.dtype == x2d.dtype
     d = L.ConvDesc()
     d.dtype = _dt(x2d)
+    d.residual_dtype = d.dtype
+    for out in (y2d, y32):
+        if out is not None and out.shape[1] != (K // 2 if act == L.ACT_GEGLU else K):
+            raise ValueError(f"output view has {out.shape[1]} channels, the filter bank produces {K}")
+    if y2d is None and y32 is None:
+        raise ValueError("conv2d needs an output")
+    if y2d is not None:
+        assert y2d.dtype == x2d.dtype
+        d.y, d.ldy = _rows(y2d)
+    if y32 is not None:
+        assert y32.dtype == torch.float32
+        d.y32, d.ldy32 = _rows(y32)
     d.N, d.H, d.W, d.C, d.K, d.R, d.S = N, H, W, Cc, K, R, S
     d.stride, d.pad, d.upsample = stride, pad, int(bool(upsample))
-    d.ldx, d.ldy = ldx, ldy
+    d.ldx = ldx
     d.act, d.geglu_block, d.path, d.alpha = act, geglu_block, path, float(alpha)
-    d.x, d.w, d.y = px, w.data_ptr(), py
+    d.x, d.w = px, w.data_ptr()
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
         d.bias = bias.data_ptr()
@@ -151,8 +162,7 @@ def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=
         d.emb, d.lde = pe, lde
     if residual is not None:
         pr, ldr = _rows(residual)
-        assert residual.dtype == x2d.dtype
-        d.residual, d.ldr = pr, ldr
+        d.residual, d.ldr, d.residual_dtype = pr, ldr, _dt(residual)
     if workspace is not None:
         d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     return d

@@ -78,7 +78,7 @@ def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
 
 
 def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None, residual=None,
-           alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None):
+           alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None, y32=None):
     C = x2d.shape[1]
     K = w.shape[0]
     assert x2d.shape[0] == N * H * W and w.numel() == K * R * S * C
@@ -101,8 +101,11 @@ def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, b
         acc = acc + residual.float()
     if act == L.ACT_SILU:
         acc = F.silu(acc)
-    assert y2d.shape == acc.shape, (y2d.shape, acc.shape)
-    y2d.copy_(acc)
+    assert y2d is not None or y32 is not None
+    for out in (y2d, y32):
+        if out is not None:
+            assert out.shape == acc.shape, (out.shape, acc.shape)
+            out.copy_(acc)
 
 
 def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):

@@ -67,6 +67,25 @@ def test_fused_apply_model_plumbing(faked, pair, B, h):
     assert rel(x0, r0) < 2e-5
 
 
+def test_bf16_path_plumbing_with_fp32_side_buffers(faked, tiny_params):
+    """dtype=bf16 takes the lo/hi (bf16 operand + fp32 trunk copy) code paths; the fakes round on store like the kernels"""
+    o = OracleControlLDM(control_params=tiny_params, unet_params=tiny_params).eval()
+    sd = seeded_state_dict(o, 0)
+    m = B200ControlLDM(tiny_params, tiny_params, dtype=torch.bfloat16, device="cpu").load_state_dict(sd)
+    cond, x = cond_x(2, 8, seed=3)
+    t = torch.tensor([981, 41])
+    with torch.no_grad():
+        ref = o.apply_model(x, t, cond)
+        r = rel(m.apply_model(x, t, cond), ref)
+        assert 1e-4 < r < 1.5e-2, r
+        ctx, hint = cond["c_crossattn"][0], cond["c_concat"][0]
+        rc = o.control_model(x=x, hint=hint, timesteps=t, context=ctx)
+        mc = m.control_model(x=x, hint=hint, timesteps=t, context=ctx)
+        assert all(rel(a, b) < 1.5e-2 for a, b in zip(mc, rc))
+        me = m.model.diffusion_model(x=x, timesteps=t, context=ctx, control=rc, only_mid_control=False)
+        assert rel(me, ref) < 1.5e-2
+
+
 def test_control_scales_only_mid_and_module_call_forms(faked, pair):
     o, m = pair
     cond, x = cond_x(2, 8, seed=5)

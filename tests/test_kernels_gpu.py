@@ -98,37 +98,41 @@ def test_silu_geglu_add(dt):
     assert rel(a, a0.float() + b.float()) < tol(dt)
 
 
-@pytest.mark.parametrize("dt", [BF, F32])
+@pytest.mark.parametrize("dt", [BF, F32, (F32, BF)])
 @pytest.mark.parametrize("N,HW,C,ld,silu,eps", [(2, 1024, 320, 320, True, 1e-5), (3, 256, 960, 960, True, 1e-5),
                                                  (2, 64, 1920, 1920, False, 1e-6), (16, 16, 2560, 2560, True, 1e-5),
                                                  (2, 1024, 320, 640, True, 1e-5), (1, 64, 64, 64, True, 1e-5),
                                                  (5, 4096, 320, 320, False, 1e-6), (2, 100, 128, 136, True, 1e-5)])
 def test_groupnorm(dt, N, HW, C, ld, silu, eps):
+    dt, dto = dt if isinstance(dt, tuple) else (dt, dt)  # (fp32 trunk in, bf16 operand out) is the bf16 path's common case
     buf = rnd(N * HW, ld, dt=dt, seed=1) * 1.7 + 0.4
     x = buf[:, ld - C:]  # channel slice of a wider (concat) buffer
     gamma, beta = 1 + 0.2 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
-    y = torch.empty(N * HW, C, device=DEV, dtype=dt)
+    y = torch.empty(N * HW, C, device=DEV, dtype=dto)
     ws = torch.empty(ops.groupnorm_workspace_bytes(N) // 4, device=DEV)
     ops.groupnorm(x, y, N, gamma, beta, eps, silu, ws)
     xr = x.float().reshape(N, HW, C).permute(0, 2, 1)
     ref = F.group_norm(xr, 32, gamma, beta, eps)
     ref = (F.silu(ref) if silu else ref).permute(0, 2, 1).reshape(N * HW, C)
-    assert rel(y, ref) < tol(dt)
+    assert rel(y, ref) < tol(dto)
 
 
-@pytest.mark.parametrize("dt", [BF, F32])
+@pytest.mark.parametrize("dt", [BF, F32, (F32, BF)])
 @pytest.mark.parametrize("M,C", [(1024, 320), (77, 640), (300, 1280), (5, 64)])
 def test_layernorm(dt, M, C):
+    dt, dto = dt if isinstance(dt, tuple) else (dt, dt)
     x = rnd(M, C, dt=dt, seed=1) * 2 + 0.3
     g, b = 1 + 0.2 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
-    y = torch.empty_like(x)
+    y = torch.empty(M, C, device=DEV, dtype=dto)
     ops.layernorm(x, y, g, b)
-    assert rel(y, F.layer_norm(x.float(), (C,), g, b)) < tol(dt)
+    assert rel(y, F.layer_norm(x.float(), (C,), g, b)) < tol(dto)
 
 
 # ---- convolution / GEMM family -----------------------------------------------------------------------------------
 def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True, emb=False, residual=False,
-              inplace=False, alpha=1.0, act=L.ACT_NONE, ldx_extra=0, ldy_extra=0, workspace=False, seed=0):
+              inplace=False, alpha=1.0, act=L.ACT_NONE, ldx_extra=0, ldy_extra=0, ldy_pad=0, workspace=False, seed=0,
+              y32="", res32=False):
+    """y32: "" (activation-dtype output only), "both" (+ fp32 copy) or "only" (fp32 copy only); res32: fp32 residual"""
     M = N * H * W
     xb = rnd(M, C + ldx_extra, dt=dt, seed=seed + 1)
     x = xb[:, ldx_extra:]
@@ -140,14 +144,18 @@ def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True,
     P, Q = (Hi + 2 * (R // 2) - R) // stride + 1, (Wi + 2 * (R // 2) - R) // stride + 1
     Mo = N * P * Q
     Ko = K // 2 if act == L.ACT_GEGLU else K
-    yb = rnd(Mo, Ko + ldy_extra, dt=dt, seed=seed + 5)
-    y = yb[:, ldy_extra:]
-    res = y if inplace else (rnd(Mo, Ko, dt=dt, seed=seed + 6) if residual else None)
+    yb = rnd(Mo, Ko + ldy_extra + ldy_pad, dt=dt, seed=seed + 5)
+    y = yb[:, ldy_extra:ldy_extra + Ko]
+    res = y if inplace else (rnd(Mo, Ko, dt=F32 if res32 else dt, seed=seed + 6) if residual else None)
+    out32 = torch.full((Mo, Ko + 8), 3.0, device=DEV)[:, :Ko] if y32 else None
+    if y32 == "only":
+        assert not inplace
+        y = None
     res_ref = None if res is None else res.float().clone()
     gb = 80 if act == L.ACT_GEGLU and Ko % 80 == 0 else 16
     ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV) if workspace else None
     kw = dict(N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=upsample, bias=b, emb=e, residual=res,
-              alpha=alpha, act=act, geglu_block=gb, path=path, workspace=ws)
+              alpha=alpha, act=act, geglu_block=gb, path=path, workspace=ws, y32=out32)
     assert ops.conv2d_path(x, w, y, **kw) == (path if path else ops.conv2d_path(x, w, y, **kw))
     ops.conv2d(x, w, y, **kw)
     # fp32 reference on the same (rounded) inputs
@@ -173,10 +181,18 @@ def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True,
         acc = F.silu(acc)
     if act == L.ACT_GEGLU:
         acc = acc[:, :Ko] * F.gelu(acc[:, Ko:])
+    if out32 is not None:
+        e32 = rel(out32, acc.float())
+        assert e32 < (2e-5 if dt == F32 else 3e-3 if res32 else 6e-3), f"fp32 copy rel err {e32}"  # operands are still bf16
+        if y is None:
+            return e32
+        assert torch.equal(y, out32.to(dt))  # the bf16 output is the rounding of the fp32 copy
     err = rel(y, acc.float())
     assert err < tol(dt), f"rel err {err}"
     if ldy_extra:  # the kernel must not touch the columns outside its slice
-        assert torch.equal(yb[:, :ldy_extra], rnd(Mo, Ko + ldy_extra, dt=dt, seed=seed + 5)[:, :ldy_extra])
+        assert torch.equal(yb[:, :ldy_extra], rnd(Mo, Ko + ldy_extra + ldy_pad, dt=dt, seed=seed + 5)[:, :ldy_extra])
+    if ldy_pad:
+        assert torch.equal(yb[:, ldy_extra + Ko:], rnd(Mo, Ko + ldy_extra + ldy_pad, dt=dt, seed=seed + 5)[:, ldy_extra + Ko:])
     return err
 
 
@@ -193,6 +209,9 @@ GENERIC_CASES = [
     dict(N=1, H=1, W=77, C=64, K=128, R=1, bias=False),                    # linear, no bias
     dict(N=1, H=1, W=100, C=64, K=512, R=1, act=L.ACT_GEGLU),              # GEGLU
     dict(N=1, H=1, W=3, C=1280, K=320, R=1, act=L.ACT_SILU),               # tiny-M linear (time embed)
+    dict(N=2, H=8, W=8, C=64, K=64, R=3, stride=2, y32="both"),            # Downsample, bf16 + fp32 outputs
+    dict(N=2, H=8, W=8, C=64, K=128, R=3, emb=True, y32="only"),           # ResBlock h kept in fp32
+    dict(N=2, H=8, W=8, C=128, K=128, R=3, residual=True, res32=True, y32="both"),  # fp32 trunk residual
 ]
 
 
@@ -219,11 +238,15 @@ TC_CASES = [
     dict(N=5, H=4, W=4, C=1280, K=1280, R=3, emb=True),                    # @4x4, box spans 8 images
     dict(N=1, H=64, W=64, C=320, K=320, R=3, emb=True),                    # 512^2 level: box = 2 rows of 64
     dict(N=2, H=16, W=16, C=960, K=640, R=3, ldx_extra=320, ldy_extra=640, residual=True),  # concat slices in/out
-    dict(N=2, H=32, W=32, C=320, K=4, R=3),                                # `out` conv: 4 channels
+    dict(N=2, H=32, W=32, C=320, K=4, R=3, ldy_pad=4),                     # `out` conv: 4 channels in an 8-wide buffer
     dict(N=16, H=4, W=4, C=2560, K=1280, R=3, emb=True, workspace=True),   # split-K (deep level)
     dict(N=4, H=8, W=8, C=1280, K=1280, R=1, workspace=True),              # split-K plain
     dict(N=1, H=1, W=64, C=1280, K=10240, R=1, act=L.ACT_GEGLU, workspace=True),  # split-K + GEGLU
     dict(N=2, H=32, W=32, C=320, K=320, R=1, residual=True),               # proj_out 1x1 conv
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, emb=True, y32="only"),        # ResBlock h -> fp32 only
+    dict(N=2, H=16, W=16, C=640, K=640, R=3, residual=True, res32=True, y32="both", ldy_extra=640),  # trunk: slot + fp32
+    dict(N=1, H=1, W=300, C=1280, K=320, R=1, residual=True, res32=True),  # ff2: fp32 stream in, bf16 operand out
+    dict(N=8, H=4, W=4, C=1280, K=1280, R=3, residual=True, res32=True, y32="both", workspace=True),  # split-K + fp32
 ]
 
 
