@@ -45,6 +45,7 @@ int mkd_abi_version(void);          /* == MKD_ABI_VERSION */
 int mkd_compiled_arch(void);        /* 100 : built for sm_100a only */
 int mkd_device_ok(int device);      /* 0 if `device` is compute capability 10.0, else MKD_E_ARCH */
 const char* mkd_last_error(void);
+long long mkd_launch_count(void);   /* kernels launched by this library in this process so far (bench accounting) */
 
 /* ---- DDIM x_t -> x_{t-1} update incl. classifier-free-guidance combine -----------------------------------
  * replaces diffmk/cddim.py:39-40 (CFG combine), :56-63 (coefficients, pred_x0), :74-78 (dir_xt, noise, x_prev).

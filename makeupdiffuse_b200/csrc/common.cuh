@@ -10,6 +10,7 @@
 namespace mkd {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define MKD_REQUIRE(cond, code, ...)      \
   do {                                    \
@@ -26,6 +27,7 @@ void set_error(const char* fmt, ...);
       ::mkd::set_error("%s:%d launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
       return MKD_E_CUDA;                                                        \
     }                                                                           \
+    ::mkd::count_launch();                                                      \
   } while (0)
 
 typedef __nv_bfloat16 bf16;

@@ -2,6 +2,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace mkd {
@@ -12,9 +14,12 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace mkd
 using namespace mkd;
 
+extern "C" long long mkd_launch_count(void) { return mkd::g_launches.load(std::memory_order_relaxed); }
 extern "C" int mkd_abi_version(void) { return MKD_ABI_VERSION; }
 extern "C" int mkd_compiled_arch(void) { return 100; }
 extern "C" const char* mkd_last_error(void) { return mkd::g_err; }

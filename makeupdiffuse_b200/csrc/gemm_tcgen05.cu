@@ -6,13 +6,15 @@
 //     tap (r, s) is the same box shifted by (s - pad, r - pad) — out-of-bounds rows/columns (the padding halo, and
 //     the M tail) are zero-filled by the TMA unit, so no im2col buffer and no halo code exist anywhere.
 //   * B (weights, [K_out][R*S*C] "KRSC") arrives by a 2-D TMA map, box (64, BN).
-//   * warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane; owns the TMEM allocation),
-//     warps 2-5 = epilogue (tcgen05.ld -> registers -> fused bias / timestep-embedding / alpha / residual (incl. the
-//     in-place ControlNet injection) / SiLU / GEGLU -> bf16 -> global, possibly into a channel slice of a concat buffer).
+//   * persistent: one CTA per SM walks the (n_tile, m_tile, k-split) work units; warp 0 = TMA producer (one lane),
+//     warp 1 = MMA issuer (one lane; owns the TMEM allocation), warps 2-9 = epilogue (tcgen05.ld -> registers ->
+//     smem staging -> coalesced fused bias / timestep-embedding / alpha / residual (incl. the in-place ControlNet
+//     injection) / SiLU / GEGLU -> bf16 and/or fp32 -> global, possibly into a channel slice of a concat buffer).
 //   * STAGES-deep smem ring with full/empty mbarriers; tcgen05.commit releases a stage when its MMAs retire.
-//   * split-K (gridDim.z > 1): each split writes fp32 partials to the workspace; splitk_epilogue_kernel reduces them
-//     and applies the same epilogue.  Used where M*N tiles alone cannot fill 148 SMs (the 8x8 and 4x4 levels).
-//   * 2 CTAs per SM (<= 113 KB smem, <= 256 TMEM columns each): one CTA's epilogue overlaps the other's main loop.
+//   * two TMEM accumulator buffers (tmem_full / tmem_empty mbarriers): the epilogue of unit j overlaps the main loop
+//     of unit j+1, and the producer prefetches across unit borders.
+//   * split-K (extra work units): each split writes fp32 partials to the workspace; splitk_epilogue_kernel reduces them
+//     and applies the same epilogue.  Only where the tiles cannot fill half the SMs and K is deep (the 4x4 / 8x8 levels).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -47,6 +49,7 @@ struct MainP {
   int S, pad;
   int Wb, Hb, Nb;      // box
   int tiles_w, tiles_h;
+  int m_tiles, n_tiles, num_units;  // persistent scheduler: unit -> (n_tile, m_tile, split)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -125,41 +128,43 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 __host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
 // ---- shared epilogue math (used by the main kernel and by the split-K reducer) ------------------------------
-// v[16] = accumulators of columns [n, n+16) of row m (n is a *weight-row* index).
-__device__ __forceinline__ void epilogue_store16(const EpiP& e, int m, int n, float (&v)[16]) {
-  const int nimg = e.emb ? m / e.pix_per_img : 0;
+// r[8] = accumulators of output channels [o, o+8) of row m.
+__device__ __forceinline__ void epilogue_vec8(const EpiP& e, int m, int o, float (&r)[8]) {
+  if (o >= e.N_out) return;
+  if (o + 8 <= e.N_out) {
+    if (e.bias) {
+      float t[8];
+      load8(e.bias + o, t);
 #pragma unroll
-  for (int j = 0; j < 16; j += 8) {
-    const int o = n + j;
-    if (o >= e.N_out) return;
-    float r[8];
-    if (o + 8 <= e.N_out) {
+      for (int i = 0; i < 8; ++i) r[i] += t[i];
+    }
+    if (e.emb) {
+      float t[8];
+      load8(e.emb + (int64_t)(m / e.pix_per_img) * e.lde + o, t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = v[j + i] + (e.bias ? e.bias[o + i] : 0.f);
-      if (e.emb) {
-        float t[8];
-        load8(e.emb + (int64_t)nimg * e.lde + o, t);
+      for (int i = 0; i < 8; ++i) r[i] += t[i];
+    }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] += t[i];
-      }
+    for (int i = 0; i < 8; ++i) r[i] *= e.alpha;
+    if (e.res) {
+      float t[8];
+      if (e.res_f32) load8(static_cast<const float*>(e.res) + (int64_t)m * e.ldr + o, t);
+      else load8(static_cast<const bf16*>(e.res) + (int64_t)m * e.ldr + o, t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] *= e.alpha;
-      if (e.res) {
-        float t[8];
-        if (e.res_f32) load8(static_cast<const float*>(e.res) + (int64_t)m * e.ldr + o, t);
-        else load8(static_cast<const bf16*>(e.res) + (int64_t)m * e.ldr + o, t);
+      for (int i = 0; i < 8; ++i) r[i] += t[i];
+    }
+    if (e.act == MKD_ACT_SILU) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] += t[i];
-      }
-      if (e.act == MKD_ACT_SILU) {
+      for (int i = 0; i < 8; ++i) r[i] = silu_f(r[i]);
+    }
+    if (e.y32) store8(e.y32 + (int64_t)m * e.ldy32 + o, r);
+    if (e.y) store8(e.y + (int64_t)m * e.ldy + o, r);
+  } else {  // ragged channel tail (e.g. the 4-channel `out` conv): scalar
+    const int nimg = e.emb ? m / e.pix_per_img : 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = silu_f(r[i]);
-      }
-      if (e.y32) store8(e.y32 + (int64_t)m * e.ldy32 + o, r);
-      if (e.y) store8(e.y + (int64_t)m * e.ldy + o, r);
-    } else {  // ragged channel tail (e.g. the 4-channel `out` conv): scalar
-      for (int i = 0; i < 8 && o + i < e.N_out; ++i) {
-        float t = v[j + i] + (e.bias ? e.bias[o + i] : 0.f);
+    for (int i = 0; i < 8; ++i) {
+      if (o + i < e.N_out) {
+        float t = r[i] + (e.bias ? e.bias[o + i] : 0.f);
         if (e.emb) t += to_f(e.emb[(int64_t)nimg * e.lde + o + i]);
         t *= e.alpha;
         if (e.res)
@@ -172,41 +177,72 @@ __device__ __forceinline__ void epilogue_store16(const EpiP& e, int m, int n, fl
     }
   }
 }
-// GEGLU: a tile of BN weight rows = BN/2 value rows then BN/2 gate rows; val/gate are 16 matching columns.
-__device__ __forceinline__ void epilogue_geglu16(const EpiP& e, int m, int row_val, int row_gate, int o, float (&a)[16],
-                                                 float (&g)[16]) {
+__device__ __forceinline__ void epilogue_store16(const EpiP& e, int m, int n, float (&v)[16]) {
+  float a[8], b[8];
 #pragma unroll
-  for (int j = 0; j < 16; j += 8) {
-    float r[8];
+  for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
+  epilogue_vec8(e, m, n, a);
+  epilogue_vec8(e, m, n + 8, b);
+}
+__device__ __forceinline__ void epilogue_geglu8(const EpiP& e, int m, int row_val, int row_gate, int o, float (&a)[8],
+                                                float (&g)[8]) {
+  float r[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float av = a[j + i] + (e.bias ? e.bias[row_val + j + i] : 0.f);
-      float gv = g[j + i] + (e.bias ? e.bias[row_gate + j + i] : 0.f);
-      r[i] = av * gelu_erf_f(gv);
-    }
-    store8(e.y + (int64_t)m * e.ldy + o + j, r);
+  for (int i = 0; i < 8; ++i) {
+    float av = a[i] + (e.bias ? e.bias[row_val + i] : 0.f);
+    float gv = g[i] + (e.bias ? e.bias[row_gate + i] : 0.f);
+    r[i] = av * gelu_erf_f(gv);
   }
+  store8(e.y + (int64_t)m * e.ldy + o, r);
+}
+// ---- main kernel: persistent, warp-specialised -------------------------------------------------------------
+//   grid = min(#work units, #SMs) CTAs of 320 threads, 1 CTA / SM; every role walks the same unit sequence
+//   unit -> (n_tile fastest, m_tile, k-split).
+//   warp 0      TMA producer (one lane): STAGES-deep smem ring, full/empty mbarriers, runs ahead across tile borders
+//   warp 1      MMA issuer (one lane; owns the TMEM allocation): accumulates tile j into TMEM buffer j & 1
+//   warps 2-9   epilogue: drain buffer j & 1 while the MMA warp is already filling the other one
+//               (tmem_full / tmem_empty mbarriers), in column panels of PW:
+//                 phase 1  TMEM -> registers -> fp32 staging panel in smem (thread = accumulator row)
+//                 phase 2  256 threads walk the panel row-major, 8 channels each: coalesced bias / emb / residual
+//                          loads and bf16 / fp32 stores (consecutive threads -> consecutive 16 / 32 bytes)
+template <int BN> struct Cfg {
+  static constexpr int PW = (BN % 80 == 0) ? 80 : (BN >= 64 ? 64 : 32);  // staging panel width (columns)
+  static constexpr int NP = BN / PW;
+  static constexpr int LDT = PW + 4;                                      // +4 floats: conflict-free phase-1 writes
+  static constexpr int STAGE_BYTES = A_BYTES + BN * BK * 2;
+  static constexpr int STAGES = (BN > 128) ? 4 : 5;
+  static constexpr int STAGING_BYTES = BM * LDT * 4;
+  static constexpr int TCOLS = tmem_cols(2 * BN);                         // two accumulator buffers
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+__host__ __device__ constexpr int tmem_cols2(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
 }
 
-// ---- main kernel -----------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
-                                                           const __grid_constant__ CUtensorMap bmap, MainP mp, EpiP ep) {
-  constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TCOLS = tmem_cols(BN);
+template <int BN>
+__global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
+                                                              const __grid_constant__ CUtensorMap bmap, MainP mp, EpiP ep) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, PW = C::PW, NP = C::NP, LDT = C::LDT;
+  constexpr int TCOLS = tmem_cols2(2 * BN);
+  constexpr int NG = PW / 8;  // 8-column groups per panel
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + C::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y, split = blockIdx.z;
-  const int kb0 = split * mp.kb_per_split;
-  const int kb1 = min(mp.kblocks, kb0 + mp.kb_per_split);
-  const int nkb = kb1 - kb0;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
@@ -215,7 +251,10 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
       mbar_init(full_bar + i, 1);
       mbar_init(empty_bar + i, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full_bar + i, 1);
+      mbar_init(tmem_empty_bar + i, 8);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation (this warp also frees it)
@@ -230,81 +269,149 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int w0 = 0, h0 = 0, n0 = 0;
-      if (mp.conv) {
-        int tw = m_tile % mp.tiles_w, th = (m_tile / mp.tiles_w) % mp.tiles_h, tn = m_tile / (mp.tiles_w * mp.tiles_h);
-        w0 = tw * mp.Wb;
-        h0 = th * mp.Hb;
-        n0 = tn * mp.Nb;
-      }
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        mbar_expect_tx(full_bar + s, STAGE_BYTES);
-        unsigned char* sa = smem + s * STAGE_BYTES;
-        const int kb = kb0 + i;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < mp.num_units; unit += gridDim.x) {
+        const int n_tile = unit % mp.n_tiles, rest = unit / mp.n_tiles;
+        const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
+        const int kb0 = split * mp.kb_per_split, kb1 = min(mp.kblocks, kb0 + mp.kb_per_split);
+        int w0 = 0, h0 = 0, n0 = 0;
         if (mp.conv) {
-          const int tap = kb / mp.cblocks, cb = kb - tap * mp.cblocks;
-          const int r = tap / mp.S, sx = tap - r * mp.S;
-          tma_load_4d(&amap, full_bar + s, sa, cb * BK, w0 + sx - mp.pad, h0 + r - mp.pad, n0);
-        } else {
-          tma_load_2d(&amap, full_bar + s, sa, kb * BK, m_tile * BM);
+          const int tw = m_tile % mp.tiles_w, th = (m_tile / mp.tiles_w) % mp.tiles_h, tn = m_tile / (mp.tiles_w * mp.tiles_h);
+          w0 = tw * mp.Wb;
+          h0 = th * mp.Hb;
+          n0 = tn * mp.Nb;
         }
-        tma_load_2d(&bmap, full_bar + s, sa + A_BYTES, kb * BK, n_tile * BN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          unsigned char* sa = smem + s * STAGE_BYTES;
+          if (mp.conv) {
+            const int tap = kb / mp.cblocks, cb = kb - tap * mp.cblocks;
+            const int r = tap / mp.S, sx = tap - r * mp.S;
+            tma_load_4d(&amap, full_bar + s, sa, cb * BK, w0 + sx - mp.pad, h0 + r - mp.pad, n0);
+          } else {
+            tma_load_2d(&amap, full_bar + s, sa, kb * BK, m_tile * BM);
+          }
+          tma_load_2d(&bmap, full_bar + s, sa + A_BYTES, kb * BK, n_tile * BN);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(full_bar + s, ph);
+      int it = 0, j = 0;
+      for (int unit = blockIdx.x; unit < mp.num_units; unit += gridDim.x, ++j) {
+        const int split = (unit / mp.n_tiles) / mp.m_tiles;
+        const int kb0 = split * mp.kb_per_split, kb1 = min(mp.kblocks, kb0 + mp.kb_per_split);
+        const int ab = j & 1, use = j >> 1;
+        mbar_wait(tmem_empty_bar + ab, (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+        const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(full_bar + s, ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance K inside the 128-byte swizzle atom: +32 bytes per UMMA_K (encoded >> 4)
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance K inside the 128-byte swizzle atom: +32 bytes per UMMA_K (encoded >> 4)
+            umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > kb0 || k) ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar + s);  // frees this smem stage once the MMAs above retire
         }
-        tcgen05_commit(empty_bar + s);  // frees this smem stage once the MMAs above retire
+        tcgen05_commit(tmem_full_bar + ab);  // accumulator of this unit complete
       }
-      tcgen05_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
-    const int quad = warp & 3;
-    const int m = m_tile * BM + quad * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const bool mvalid = m < ep.M;
-    if (ep.partial) {
-      float* prow = ep.partial + ((int64_t)split * ep.M + m) * ep.n_rows + n_tile * BN;
+    // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4 =====
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    const int et = threadIdx.x - 64;  // 0..255
+    const int trow_idx = quad * 32 + lane;
+    int j = 0;
+    for (int unit = blockIdx.x; unit < mp.num_units; unit += gridDim.x, ++j) {
+      const int n_tile = unit % mp.n_tiles, rest = unit / mp.n_tiles;
+      const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
+      const int ab = j & 1, use = j >> 1;
+      const int m_base = m_tile * BM;
+      mbar_wait(tmem_full_bar + ab, use & 1);
+      tcgen05_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
+      const bool geglu = ep.act == MKD_ACT_GEGLU && !ep.partial;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        float v[16];
-        tmem_ld16(trow + c, v);
-        if (mvalid && n_tile * BN + c < ep.n_rows) {
+      for (int p = 0; p < NP; ++p) {
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // previous panel fully consumed (WAR on the staging panel)
+        // ---- phase 1: this thread's row, column groups g = half, half + 2, ... of the panel ----
+        {
+          uint32_t r[(NG + 1) / 2][8];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(prow + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int gi = 0; gi < (NG + 1) / 2; ++gi) {
+            const int g = half + 2 * gi;
+            if (g < NG) {
+              // GEGLU panels interleave NG/2 value groups with their NG/2 gate groups (gate columns start at BN/2)
+              const int col = geglu ? (g < NG / 2 ? p * (PW / 2) + g * 8 : BN / 2 + p * (PW / 2) + (g - NG / 2) * 8)
+                                    : p * PW + g * 8;
+              tmem_ld8_nowait(trow + col, r[gi]);
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int gi = 0; gi < (NG + 1) / 2; ++gi) {
+            const int g = half + 2 * gi;
+            if (g < NG) {
+              float* dst = staging + trow_idx * LDT + g * 8;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(r[gi][0], r[gi][1], r[gi][2], r[gi][3]);
+              *reinterpret_cast<uint4*>(dst + 4) = make_uint4(r[gi][4], r[gi][5], r[gi][6], r[gi][7]);
+            }
+          }
         }
-      }
-    } else if (ep.act == MKD_ACT_GEGLU) {
-#pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 16) {
-        float a[16], g[16];
-        tmem_ld16(trow + c, a);
-        tmem_ld16(trow + BN / 2 + c, g);
-        if (mvalid) epilogue_geglu16(ep, m, n_tile * BN + c, n_tile * BN + BN / 2 + c, n_tile * (BN / 2) + c, a, g);
-      }
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        float v[16];
-        tmem_ld16(trow + c, v);
-        if (mvalid) epilogue_store16(ep, m, n_tile * BN + c, v);
+        if (p == NP - 1) {  // every TMEM read of this unit is done: hand the accumulator buffer back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar + ab);
+        }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // panel staged (RAW)
+        // ---- phase 2: coalesced walk over the panel ----
+        if (ep.partial) {
+#pragma unroll 2
+          for (int i = et; i < BM * NG; i += 256) {
+            const int row = i / NG, g = i - row * NG;
+            const int m = m_base + row, n = n_tile * BN + p * PW + g * 8;
+            if (m < ep.M && n < ep.n_rows) {
+              float* dst = ep.partial + ((int64_t)split * ep.M + m) * ep.n_rows + n;
+              const float* src = staging + row * LDT + g * 8;
+              *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+              *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(src + 4);
+            }
+          }
+        } else if (geglu) {
+          constexpr int NV = NG / 2;
+#pragma unroll 2
+          for (int i = et; i < BM * NV; i += 256) {
+            const int row = i / NV, g = i - row * NV;
+            const int m = m_base + row;
+            if (m < ep.M) {
+              float a[8], gt[8];
+              load8(staging + row * LDT + g * 8, a);
+              load8(staging + row * LDT + (NV + g) * 8, gt);
+              const int rv = n_tile * BN + p * (PW / 2) + g * 8;
+              epilogue_geglu8(ep, m, rv, rv + BN / 2, n_tile * (BN / 2) + p * (PW / 2) + g * 8, a, gt);
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int i = et; i < BM * NG; i += 256) {
+            const int row = i / NG, g = i - row * NG;
+            const int m = m_base + row;
+            if (m < ep.M) {
+              float r[8];
+              load8(staging + row * LDT + g * 8, r);
+              epilogue_vec8(ep, m, n_tile * BN + p * PW + g * 8, r);
+            }
+          }
+        }
       }
     }
   }
@@ -341,12 +448,52 @@ __global__ void splitk_epilogue_kernel(EpiP ep, int splits) {
       float a[16], g[16];
       gather(n, a);
       gather(n + BN / 2, g);
-      epilogue_geglu16(ep, m, n, n + BN / 2, tile * (BN / 2) + c, a, g);
+      float a0[8], a1[8], g0[8], g1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a0[i] = a[i]; a1[i] = a[8 + i]; g0[i] = g[i]; g1[i] = g[8 + i]; }
+      epilogue_geglu8(ep, m, n, n + BN / 2, tile * (BN / 2) + c, a0, g0);
+      epilogue_geglu8(ep, m, n + 8, n + BN / 2 + 8, tile * (BN / 2) + c + 8, a1, g1);
     } else {
       float v[16];
       gather(n, v);
       epilogue_store16(ep, m, n, v);
     }
+  }
+}
+
+// Nearest-neighbour x2 upsample, NHWC bf16, 8 channels per thread: out[n, 2h+dy, 2w+dx, :] = in[n, h, w, :].
+// (Upsample blocks: the 3x3 conv that follows then runs on the tensor cores like any other.)
+__global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int ldx) {
+  const int vpr = C / 8;
+  const int64_t total = (int64_t)N * 4 * H * W * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpr);
+    int64_t pix = i / vpr;
+    const int ow = (int)(pix % (2 * W));
+    pix /= 2 * W;
+    const int oh = (int)(pix % (2 * H)), n = (int)(pix / (2 * H));
+    const uint4 val = *reinterpret_cast<const uint4*>(x + ((int64_t)(n * H + (oh >> 1)) * W + (ow >> 1)) * ldx + v * 8);
+    *reinterpret_cast<uint4*>(y + (i / vpr) * C + v * 8) = val;
+  }
+}
+// im2col for the three stride-2 Downsample convs: out[m, (r*3+s)*C + c] = in[n, 2p-1+r, 2q-1+s, c] (0 outside).
+// The outputs are 4x smaller than the inputs, so the 9x expansion costs little and the conv becomes a plain GEMM.
+__global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int ldx) {
+  const int vpr = C / 8, P = H / 2, Q = W / 2;
+  const int64_t total = (int64_t)N * P * Q * 9 * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpr);
+    int64_t t = i / vpr;
+    const int tap = (int)(t % 9);
+    t /= 9;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P), n = (int)(t / P);
+    const int ih = 2 * p - 1 + tap / 3, iw = 2 * q - 1 + tap % 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+      val = *reinterpret_cast<const uint4*>(x + ((int64_t)(n * H + ih) * W + iw) * ldx + v * 8);
+    *reinterpret_cast<uint4*>(y + (i / vpr) * C + v * 8) = val;
   }
 }
 
@@ -388,8 +535,17 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 bool geometry(const mkd_conv_desc* d, Geometry& g) {
   if (d->dtype != MKD_BF16) { set_error("dtype is not bf16"); return false; }
   if (d->C % BK != 0) { set_error("C=%d is not a multiple of 64", d->C); return false; }
-  if (d->stride != 1 || d->upsample) { set_error("stride/upsample convs use the generic kernel"); return false; }
   if (d->R != d->S || (d->R != 1 && d->R != 3) || d->pad != d->R / 2) { set_error("filter is not 1x1/p0 or 3x3/p1"); return false; }
+  if (d->stride != 1 || d->upsample) {
+    // Downsample (3x3 stride 2) and Upsample (nearest x2 + 3x3) run as: materialise (im2col / upsampled copy) into the
+    // workspace, then the ordinary tensor-core kernel.  Needs the workspace and even, power-of-two sizes.
+    const bool down = d->stride == 2 && !d->upsample && d->R == 3 && d->H % 2 == 0 && d->W % 2 == 0;
+    const bool up = d->stride == 1 && d->upsample && d->R == 3;
+    if (!down && !up) { set_error("stride %d / upsample %d conv is not a Downsample/Upsample shape", d->stride, d->upsample); return false; }
+    const size_t need = down ? (size_t)d->N * (d->H / 2) * (d->W / 2) * 9 * d->C * 2 : (size_t)d->N * 4 * d->H * d->W * d->C * 2;
+    if (!d->workspace || d->workspace_bytes < need + (1 << 20)) { set_error("stride-2 / upsample conv needs %zu workspace bytes", need); return false; }
+  }
+  if (d->bias && !aligned16(d->bias)) { set_error("bias alignment"); return false; }
   if (d->ldx % 8 || !aligned16(d->x) || !aligned16(d->w)) { set_error("x/w alignment"); return false; }
   if (d->y && (d->ldy % 8 || !aligned16(d->y))) { set_error("y alignment"); return false; }
   if (d->y32 && (d->ldy32 % 8 || !aligned16(d->y32))) { set_error("y32 alignment"); return false; }
@@ -398,18 +554,20 @@ bool geometry(const mkd_conv_desc* d, Geometry& g) {
   if (d->emb && (d->lde % 8 || !aligned16(d->emb))) { set_error("emb alignment"); return false; }
   g.conv = d->R == 3;
   g.P = d->H; g.Q = d->W;
-  g.M = d->N * d->H * d->W;
+  if (d->upsample) { g.P = 2 * d->H; g.Q = 2 * d->W; }
+  if (d->stride == 2) { g.P = d->H / 2; g.Q = d->W / 2; g.conv = 0; }
+  g.M = d->N * g.P * g.Q;
   g.Ktot = d->R * d->S * d->C;
   g.Kout = d->act == MKD_ACT_GEGLU ? d->K / 2 : d->K;
   if (d->K % 16 != 0 && !(d->K < 16)) { set_error("K=%d is not a multiple of 16", d->K); return false; }
   if (d->act == MKD_ACT_GEGLU && (d->geglu_block != 80 || d->K % 160)) { set_error("GEGLU needs geglu_block 80 and K %% 160 == 0"); return false; }
   if (g.conv) {
-    if (!is_pow2(d->W) || !is_pow2(d->H)) { set_error("conv H/W must be powers of two"); return false; }
-    g.Wb = d->W < BM ? d->W : BM;
-    g.Hb = BM / g.Wb < d->H ? BM / g.Wb : d->H;
+    if (!is_pow2(g.Q) || !is_pow2(g.P)) { set_error("conv H/W must be powers of two"); return false; }
+    g.Wb = g.Q < BM ? g.Q : BM;
+    g.Hb = BM / g.Wb < g.P ? BM / g.Wb : g.P;
     g.Nb = BM / (g.Wb * g.Hb);
-    g.tiles_w = d->W / g.Wb;
-    g.tiles_h = d->H / g.Hb;
+    g.tiles_w = g.Q / g.Wb;
+    g.tiles_h = g.P / g.Hb;
     g.m_tiles = g.tiles_w * g.tiles_h * ((d->N + g.Nb - 1) / g.Nb);
   } else {
     g.Wb = g.Hb = g.Nb = g.tiles_w = g.tiles_h = 1;
@@ -428,13 +586,36 @@ int pick_bn(const mkd_conv_desc* d) {
   return 64;  // ragged last tile: B rows beyond K are zero-filled by TMA, stores are masked
 }
 
-template <int BN, int STAGES>
-int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = A_BYTES + BN * BK * 2;
-  constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+template <int BN>
+int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
+  // stride-2 / upsample: rewrite the descriptor onto the materialised input living at the head of the workspace
+  mkd_conv_desc dd = *d_in;
+  mkd_conv_desc* d = &dd;
+  if (d_in->stride == 2 || d_in->upsample) {
+    const bool down = d_in->stride == 2;
+    const size_t bytes = down ? (size_t)d_in->N * g.P * g.Q * 9 * d_in->C * 2 : (size_t)d_in->N * g.P * g.Q * d_in->C * 2;
+    const int64_t vecs = (int64_t)(bytes / 16);
+    int blocks = (int)((vecs + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (down)
+      im2col_s2_kernel<<<blocks, 256, 0, stream>>>((const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx);
+    else
+      upsample2x_kernel<<<blocks, 256, 0, stream>>>((const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx);
+    MKD_CHECK_LAUNCH();
+    const size_t used = (bytes + 1023) & ~(size_t)1023;
+    dd.x = d_in->workspace;
+    dd.workspace = (char*)d_in->workspace + used;
+    dd.workspace_bytes = d_in->workspace_bytes - used;
+    dd.stride = 1;
+    dd.upsample = 0;
+    if (down) { dd.C = 9 * d_in->C; dd.R = dd.S = 1; dd.pad = 0; dd.N = 1; dd.H = 1; dd.W = g.M; dd.ldx = dd.C; }
+    else { dd.H = g.P; dd.W = g.Q; dd.ldx = d_in->C; }
+  }
+  constexpr size_t smem = Cfg<BN>::SMEM;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "gemm_tcgen05: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     configured = true;
   }
@@ -468,13 +649,14 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   mp.Wb = g.Wb; mp.Hb = g.Hb; mp.Nb = g.Nb;
   mp.tiles_w = g.tiles_w; mp.tiles_h = g.tiles_h;
   const int n_tiles = (d->K + BN - 1) / BN;
-  // split-K: only when the tile grid leaves most SMs idle and K is deep
+  // split-K: only when the tile grid leaves more than half of the SMs idle AND K is deep enough that the fp32
+  // partial round trip (2 * splits * M * N * 4 bytes) is cheaper than the idle tensor cores
   int splits = 1;
   const int tiles = g.m_tiles * n_tiles;
-  if (d->workspace && tiles < 148 && mp.kblocks >= 8 && d->K % 16 == 0) {
-    splits = (2 * 148 + tiles - 1) / tiles;              // aim at ~2 CTAs per SM
-    if (splits > mp.kblocks / 4) splits = mp.kblocks / 4;  // >= 4 K blocks per split
-    if (splits > 32) splits = 32;
+  if (d->workspace && tiles <= 74 && mp.kblocks >= 32 && d->K % 16 == 0) {
+    splits = 148 / tiles;
+    if (splits > mp.kblocks / 16) splits = mp.kblocks / 16;  // >= 16 K blocks (1024 of K) per split
+    if (splits > 16) splits = 16;
     while (splits > 1 && (size_t)splits * g.M * d->K * sizeof(float) > d->workspace_bytes) --splits;
     if (splits < 1) splits = 1;
   }
@@ -490,9 +672,11 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   ep.y32 = d->y32; ep.ldy32 = d->ldy32; ep.res_f32 = d->residual_dtype == MKD_F32;
   ep.partial = splits > 1 ? (float*)d->workspace : nullptr;
 
-  dim3 grid(g.m_tiles, n_tiles, splits);
-  MKD_REQUIRE(grid.y <= 65535 && grid.z <= 65535, MKD_E_INVALID, "gemm_tcgen05: grid too large");
-  gemm_tcgen05_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(amap, bmap, mp, ep);
+  mp.m_tiles = g.m_tiles;
+  mp.n_tiles = n_tiles;
+  mp.num_units = tiles * splits;
+  const int grid = mp.num_units < num_sms() ? mp.num_units : num_sms();
+  gemm_tcgen05_kernel<BN><<<grid, 320, smem, stream>>>(amap, bmap, mp, ep);
   MKD_CHECK_LAUNCH();
   if (splits > 1) {
     int64_t total = (int64_t)g.M * (d->K / 16);
@@ -515,11 +699,11 @@ int conv2d_tcgen05(const mkd_conv_desc* d, cudaStream_t stream) {
   Geometry g;
   MKD_REQUIRE(geometry(d, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
   switch (pick_bn(d)) {
-    case 160: return launch<160, 3>(d, g, stream);
-    case 128: return launch<128, 3>(d, g, stream);
-    case 80: return launch<80, 4>(d, g, stream);
-    case 64: return launch<64, 4>(d, g, stream);
-    default: return launch<32, 4>(d, g, stream);
+    case 160: return launch<160>(d, g, stream);
+    case 128: return launch<128>(d, g, stream);
+    case 80: return launch<80>(d, g, stream);
+    case 64: return launch<64>(d, g, stream);
+    default: return launch<32>(d, g, stream);
   }
 }
 }  // namespace mkd

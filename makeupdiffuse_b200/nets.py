@@ -177,6 +177,51 @@ class _Net(nn.Module):
     def _load_extra(self, g):
         pass
 
+    def _extra_shapes(self):
+        return {}
+
+    def upstream_shapes(self) -> dict:
+        """{upstream state-dict key: shape} this network expects (what a ControlNet / SD-1.5 checkpoint holds)"""
+        mc, ted, cd = self.mc, self.ted, self.context_dim
+        out = {"time_embed.0.weight": (ted, mc), "time_embed.0.bias": (ted,),
+               "time_embed.2.weight": (ted, ted), "time_embed.2.bias": (ted,)}
+
+        def conv(k, co, ci, r):
+            out[k + ".weight"] = (co, ci, r, r)
+            out[k + ".bias"] = (co,)
+
+        def norm(k, c):
+            out[k + ".weight"] = (c,)
+            out[k + ".bias"] = (c,)
+
+        for layer in self._all_layers():
+            kind, key = layer[0], layer[1]
+            if kind == "conv_in":
+                conv(key, layer[3], layer[2], 3)
+            elif kind in ("down", "up"):
+                conv(key, layer[2], layer[2], 3)
+            elif kind == "res":
+                cin, cout = layer[2], layer[3]
+                norm(key + ".in_layers.0", cin); conv(key + ".in_layers.2", cout, cin, 3)
+                out[key + ".emb_layers.1.weight"] = (cout, ted); out[key + ".emb_layers.1.bias"] = (cout,)
+                norm(key + ".out_layers.0", cout); conv(key + ".out_layers.3", cout, cout, 3)
+                if cin != cout:
+                    conv(key + ".skip_connection", cout, cin, 1)
+            elif kind == "st":
+                c, tb = layer[2], key + ".transformer_blocks.0."
+                norm(key + ".norm", c); conv(key + ".proj_in", c, c, 1); conv(key + ".proj_out", c, c, 1)
+                for n in ("norm1", "norm2", "norm3"):
+                    norm(tb + n, c)
+                for a, kd in (("attn1", c), ("attn2", cd)):
+                    out[tb + a + ".to_q.weight"] = (c, c)
+                    out[tb + a + ".to_k.weight"] = (c, kd)
+                    out[tb + a + ".to_v.weight"] = (c, kd)
+                    out[tb + a + ".to_out.0.weight"] = (c, c); out[tb + a + ".to_out.0.bias"] = (c,)
+                out[tb + "ff.net.0.proj.weight"] = (8 * c, c); out[tb + "ff.net.0.proj.bias"] = (8 * c,)
+                out[tb + "ff.net.2.weight"] = (c, 4 * c); out[tb + "ff.net.2.bias"] = (c,)
+        out.update(self._extra_shapes())
+        return out
+
     # ---- buffers ---------------------------------------------------------------------------------------------
     def _buf(self, name, rows, cols, dtype=None):
         key = (name, rows, cols, dtype)
@@ -372,6 +417,19 @@ class B200ControlNet(_Net):
         k = "middle_block_out.0"
         self._put(k + ".w", self._krsc(g(k + ".weight")), True); self._put(k + ".b", g(k + ".bias"))
 
+    def _extra_shapes(self):
+        out, cin = {}, self.hint_channels
+        for i, co in enumerate([c for c, _ in self.HINT] + [self.mc]):
+            out[f"input_hint_block.{2 * i}.weight"] = (co, cin, 3, 3)
+            out[f"input_hint_block.{2 * i}.bias"] = (co,)
+            cin = co
+        for j, c in enumerate(self.block_chans):
+            out[f"zero_convs.{j}.0.weight"] = (c, c, 1, 1)
+            out[f"zero_convs.{j}.0.bias"] = (c,)
+        out["middle_block_out.0.weight"] = (self._ch, self._ch, 1, 1)
+        out["middle_block_out.0.bias"] = (self._ch,)
+        return out
+
     def hint_features(self, hint):
         """input_hint_block(hint): independent of x and t, so computed once per batch of images, not once per step.
         hint: [B, 6, 8h, 8w] fp32 in [0,1] = cat(source, reference) (makeup_diffuse.py:56).  Returns [B*h*w, mc]."""
@@ -462,6 +520,10 @@ class B200ControlledUnet(_Net):
         yield from super()._all_layers()
         for blk in self.output_blocks:
             yield from blk
+
+    def _extra_shapes(self):
+        return {"out.0.weight": (self._out_ch,), "out.0.bias": (self._out_ch,),
+                "out.2.weight": (self.out_channels, self._out_ch, 3, 3), "out.2.bias": (self.out_channels,)}
 
     def _load_extra(self, g):
         self._put("out.gn.g", g("out.0.weight")); self._put("out.gn.b", g("out.0.bias"))

@@ -168,9 +168,23 @@ def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=
     return d
 
 
+PROFILE = None  # bench.py sets this to a list to time every conv2d launch in place (CUDA events on the stream)
+
+
 def conv2d(x2d, w, y2d, **kw):
     d = make_conv_desc(x2d, w, y2d, **kw)
+    if PROFILE is None:
+        L.check(L.load().mkd_conv2d(C.byref(d), _stream()), "conv2d")
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    path = L.load().mkd_conv2d_path(C.byref(d))
+    e0.record()
     L.check(L.load().mkd_conv2d(C.byref(d), _stream()), "conv2d")
+    e1.record()
+    Hi, Wi = (2 * d.H, 2 * d.W) if d.upsample else (d.H, d.W)
+    P, Q = (Hi + 2 * d.pad - d.R) // d.stride + 1, (Wi + 2 * d.pad - d.S) // d.stride + 1
+    PROFILE.append({"path": path, "flops": 2.0 * d.N * P * Q * d.K * d.R * d.S * d.C, "M": d.N * P * Q, "K": d.K,
+                    "C": d.C, "R": d.R, "stride": d.stride, "up": d.upsample, "e0": e0, "e1": e1})
 
 
 def conv2d_path(x2d, w, y2d, **kw) -> int:

@@ -42,6 +42,7 @@ class B200DDIMSampler:
         self.use_cuda_graph = use_cuda_graph
         self._cfg_cache = None
         self._graph = None
+        self.graph_launches = 0  # kernels executed through graph replays (they bypass the library's launch counter)
 
     # ---- schedule (upstream make_schedule / make_ddim_sampling_parameters) -----------------------------------
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0.0, verbose=True):
@@ -145,27 +146,39 @@ class B200DDIMSampler:
     def _eps(self, x, t, c):
         """model.apply_model(x, t, c); with use_cuda_graph the ~10^3 kernel launches of one UNet+ControlNet step are
         captured once per (cond, batch shape) and replayed (launch-bound otherwise: SURVEY.md §7 hard part 6)."""
-        if not (self.use_cuda_graph and x.is_cuda):
+        prepare = getattr(self.model, "_prepare", None)
+        if not (self.use_cuda_graph and x.is_cuda and prepare is not None):
             return self.model.apply_model(x, t, c)
+        from . import _lib
         g = self._graph
-        key = (id(c), tuple(x.shape), id(self.model))
+        # the graph only depends on shapes: every per-cond tensor it reads (hint features, cross-attention K/V) lives
+        # in a static arena buffer that model._prepare() refills in place when the cond changes
+        key = (tuple(x.shape), c["c_concat"] is None, tuple(tuple(v.shape) for v in c["c_crossattn"]), id(self.model),
+               getattr(self.model, "only_mid_control", False), tuple(getattr(self.model, "control_scales", ())))
         if g is None or g["key"] != key:
             sx, st = x.clone(), t.clone()
             self.model.apply_model(sx, st, c)  # warm-up: allocates every static buffer, fills the cond cache
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            n0 = _lib.load().mkd_launch_count()
             with torch.cuda.graph(graph):
                 out = self.model.apply_model(sx, st, c)
-            g = self._graph = {"key": key, "graph": graph, "x": sx, "t": st, "out": out, "cond": c}
+            g = self._graph = {"key": key, "graph": graph, "x": sx, "t": st, "out": out,
+                               "launches": _lib.load().mkd_launch_count() - n0}
+        prepare(c)  # no-op when the cond is unchanged; otherwise recomputes the hoisted tensors eagerly
         g["x"].copy_(x)
         g["t"].copy_(t)
         g["graph"].replay()
+        self.graph_launches += g["launches"]
         return g["out"]
 
     # ---- one x_t -> x_{t-1} update: diffmk/cddim.py:9-79 ---------------------------------------------------------
     def denoising_step(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
                        temperature=1.0, noise_dropout=0.0, score_corrector=None, corrector_kwargs=None,
-                       unconditional_guidance_scale=1.0, unconditional_conditioning=None, dynamic_threshold=None):
+                       unconditional_guidance_scale=1.0, unconditional_conditioning=None, dynamic_threshold=None,
+                       out=None):
+        """``out`` (extension, optional): tensor that receives x_prev — e.g. this rank's slice of an all-gather
+        buffer, so the last update of a sharded run lands directly where the collective reads it."""
         m = self.model
         if m.parameterization != "eps":
             raise NotImplementedError("B200 path implements the yaml's parameterization: eps (yaml:50)")
@@ -201,7 +214,7 @@ class B200DDIMSampler:
                 # dropout acts on sigma*noise*temperature in the reference; it commutes with the scalar factors
                 noise = torch.nn.functional.dropout(noise, p=noise_dropout)
             noise = noise.contiguous()
-        x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
+        x_prev, pred_x0 = (torch.empty_like(x) if out is None else out), torch.empty_like(x)
         ops.ddim_update(x, e.contiguous(), x_prev, sqrt_one_minus_at=s1m, sqrt_at=sq_at, sqrt_a_prev=sq_ap, dir_coef=dirc,
                         sigma_t=sigma, temperature=temperature, noise=noise, pred_x0=pred_x0,
                         cfg_scale=float(unconditional_guidance_scale) if cfg else None)

@@ -130,6 +130,26 @@ def test_sampler_loop_matches_oracle(faked, pair):
     assert torch.equal(so.ddim_alphas, sm.ddim_alphas) and np.array_equal(so.ddim_alphas_prev, sm.ddim_alphas_prev)
 
 
+def test_synthetic_weights_equal_the_oracle_init_and_shapes_match_upstream(pair):
+    """product-side synthetic weights (bench / smoke) are the very tensors the oracle is initialised with, and the
+    expected-shape table of the full-size nets is exactly the upstream state dict (859 520 964 / 361 279 552 params)"""
+    import math
+    from makeupdiffuse_b200.synth import synthetic_state_dict
+    from oracle import ControlNet, ControlledUnetModel
+    o, m = pair
+    sd = synthetic_state_dict(m, 0, device="cpu")
+    osd = o.state_dict()
+    assert set(sd) == {k for k in osd if k.startswith(("control_model.", "model.diffusion_model."))}
+    assert all(torch.equal(sd[k], osd[k]) for k in sd)
+    full = B200ControlLDM(dtype=torch.bfloat16, device="cpu")
+    with torch.device("meta"):
+        ocn, oun = ControlNet(), ControlledUnetModel()
+    for net, onet, total in ((full.control_model, ocn, 361_279_552), (full.model.diffusion_model, oun, 859_520_964)):
+        shapes = net.upstream_shapes()
+        assert {k: tuple(v.shape) for k, v in onet.state_dict().items()} == shapes
+        assert sum(math.prod(v) for v in shapes.values()) == total
+
+
 def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
     """the product must fail loudly, not fall back, when the CUDA extension is absent"""
     from makeupdiffuse_b200 import _lib

@@ -243,6 +243,10 @@ TC_CASES = [
     dict(N=4, H=8, W=8, C=1280, K=1280, R=1, workspace=True),              # split-K plain
     dict(N=1, H=1, W=64, C=1280, K=10240, R=1, act=L.ACT_GEGLU, workspace=True),  # split-K + GEGLU
     dict(N=2, H=32, W=32, C=320, K=320, R=1, residual=True),               # proj_out 1x1 conv
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, stride=2, workspace=True, y32="both"),   # Downsample via im2col + GEMM
+    dict(N=3, H=8, W=8, C=1280, K=1280, R=3, stride=2, workspace=True),               # deep Downsample (+ split-K)
+    dict(N=2, H=8, W=8, C=1280, K=1280, R=3, upsample=True, workspace=True),          # Upsample 8 -> 16
+    dict(N=2, H=16, W=16, C=640, K=640, R=3, upsample=True, workspace=True, ldx_extra=64, ldy_extra=640),  # 16 -> 32 into a slot
     dict(N=2, H=32, W=32, C=320, K=320, R=3, emb=True, y32="only"),        # ResBlock h -> fp32 only
     dict(N=2, H=16, W=16, C=640, K=640, R=3, residual=True, res32=True, y32="both", ldy_extra=640),  # trunk: slot + fp32
     dict(N=1, H=1, W=300, C=1280, K=320, R=1, residual=True, res32=True),  # ff2: fp32 stream in, bf16 operand out
@@ -264,11 +268,13 @@ def test_conv_auto_dispatch():
         w = torch.empty(c["K"], R, R, c["C"], device=DEV, dtype=BF)
         s = c.get("stride", 1)
         y = torch.empty(M // (s * s), c["K"], device=DEV, dtype=BF)
-        return ops.conv2d_path(x, w, y, N=c["N"], H=c["H"], W=c["W"], R=R, S=R, stride=s, pad=R // 2)
+        ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV) if c.get("ws") else None
+        return ops.conv2d_path(x, w, y, N=c["N"], H=c["H"], W=c["W"], R=R, S=R, stride=s, pad=R // 2, workspace=ws)
     assert path(N=16, H=32, W=32, C=320, K=320, R=3) == L.PATH_TCGEN05
     assert path(N=16, H=1, W=1024, C=320, K=960) == L.PATH_TCGEN05
     assert path(N=16, H=32, W=32, C=4, K=320, R=3) == L.PATH_GENERIC
-    assert path(N=16, H=32, W=32, C=320, K=320, R=3, stride=2) == L.PATH_GENERIC
+    assert path(N=16, H=32, W=32, C=320, K=320, R=3, stride=2, ws=True) == L.PATH_TCGEN05
+    assert path(N=16, H=32, W=32, C=320, K=320, R=3, stride=2) == L.PATH_GENERIC  # no workspace to materialise into
 
 
 def test_conv_rejects_bad_descriptors():
