@@ -248,9 +248,15 @@ def main():
         model.apply_model(loc["x_T"], t, cond)
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
-        agg = {}
+        other = {}
         for r in prof:
             r["ms"] = r["e0"].elapsed_time(r["e1"])
+            if r["op"] != "conv2d":
+                a = other.setdefault(r["op"], {"n": 0, "ms": 0.0, "bytes": 0})
+                a["n"] += 1; a["ms"] += r["ms"]; a["bytes"] += r["bytes"]
+        prof = [r for r in prof if r["op"] == "conv2d"]
+        agg = {}
+        for r in prof:
             key = (r["path"], r["M"], r["K"], r["C"], r["R"], r["stride"], r["up"])
             a = agg.setdefault(key, {"n": 0, "ms": 0.0, "flops": 0.0})
             a["n"] += 1; a["ms"] += r["ms"]; a["flops"] += r["flops"]
@@ -271,7 +277,10 @@ def main():
                           "tflops": round(a["flops"] / (a["ms"] / 1e3) / 1e12, 1) if a["ms"] else None})
         if args.profile_out:
             with open(args.profile_out, "w") as f:
-                json.dump({"ms_per_unet_controlnet_step": ms_model_step, "conv_table": table}, f, indent=1)
+                json.dump({"ms_per_unet_controlnet_step": ms_model_step, "conv_table": table,
+                           "other_ops": {k: {"count": v["n"], "ms": round(v["ms"], 4),
+                                             "GBps": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["ms"] else None}
+                                         for k, v in other.items()}}, f, indent=1)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of configs[0] ----------------------------------------------
     cpu = None

@@ -15,6 +15,7 @@ template <typename T>
 __global__ void attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                                  T* __restrict__ o, int Nq, int Nkv, int d, int ldq, int ldk, int ldv, int ldo,
                                  float scale) {
+  pdl_wait();
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, i = blockIdx.x * warps + warp;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
                                                        const bf16* __restrict__ v, bf16* __restrict__ o, int Nq,
                                                        int Nkv, int d, int ldq, int ldk, int ldv, int ldo,
                                                        float scale_log2e) {
+  pdl_wait();
   constexpr int PITCH = DP + 8, KS = DP / 16, NT = DP / 8;
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
@@ -259,7 +261,7 @@ int launch_mma(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int 
     configured = true;
   }
   dim3 grid((Nq + AQ - 1) / AQ, heads, B);
-  attn_mma_kernel<DP><<<grid, 128, smem, st>>>(q, k, v, o, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale * 1.4426950408889634f);
+  MKD_LAUNCH_OK(launch_pdl(attn_mma_kernel<DP>, dim3(grid), dim3(128), smem, st, q, k, v, o, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale * 1.4426950408889634f));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -294,8 +296,8 @@ extern "C" int mkd_attention(const void* q, const void* k, const void* v, void* 
     configured = true;
   }
   dim3 grid((Nq + warps - 1) / warps, heads, B);
-  attn_simt_kernel<float><<<grid, warps * 32, smem, st>>>((const float*)q, (const float*)k, (const float*)v, (float*)o, Nq,
-                                                          Nkv, d, ldq, ldk, ldv, ldo, scale);
+  MKD_LAUNCH_OK(launch_pdl(attn_simt_kernel<float>, dim3(grid), dim3(warps * 32), smem, st, (const float*)q, (const float*)k, (const float*)v, (float*)o, Nq,
+                                                          Nkv, d, ldq, ldk, ldv, ldo, scale));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }

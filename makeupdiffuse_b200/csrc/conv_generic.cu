@@ -30,6 +30,7 @@ template <typename T, bool GEGLU>
 __global__ void __launch_bounds__(256) conv_generic_kernel(ConvP p, const T* __restrict__ x, const T* __restrict__ w,
                                                            T* __restrict__ y, const float* __restrict__ bias,
                                                            const T* __restrict__ emb, const void* __restrict__ res) {
+  pdl_wait();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[GEGLU ? 2 : 1][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -170,20 +171,20 @@ int conv2d_generic(const mkd_conv_desc* d, cudaStream_t stream) {
   const bool geglu = d->act == MKD_ACT_GEGLU;
   if (d->dtype == MKD_BF16) {
     if (geglu)
-      conv_generic_kernel<bf16, true><<<grid, 256, 0, stream>>>(p, (const bf16*)d->x, (const bf16*)d->w, (bf16*)d->y,
-                                                                d->bias, (const bf16*)d->emb, d->residual);
+      MKD_LAUNCH_OK(launch_pdl(conv_generic_kernel<bf16, true>, dim3(grid), dim3(256), 0, stream, p, (const bf16*)d->x, (const bf16*)d->w, (bf16*)d->y,
+                                                                d->bias, (const bf16*)d->emb, d->residual));
     else
-      conv_generic_kernel<bf16, false><<<grid, 256, 0, stream>>>(p, (const bf16*)d->x, (const bf16*)d->w, (bf16*)d->y,
-                                                                 d->bias, (const bf16*)d->emb, d->residual);
+      MKD_LAUNCH_OK(launch_pdl(conv_generic_kernel<bf16, false>, dim3(grid), dim3(256), 0, stream, p, (const bf16*)d->x, (const bf16*)d->w, (bf16*)d->y,
+                                                                 d->bias, (const bf16*)d->emb, d->residual));
   } else {
     if (geglu)
-      conv_generic_kernel<float, true><<<grid, 256, 0, stream>>>(p, (const float*)d->x, (const float*)d->w,
+      MKD_LAUNCH_OK(launch_pdl(conv_generic_kernel<float, true>, dim3(grid), dim3(256), 0, stream, p, (const float*)d->x, (const float*)d->w,
                                                                  (float*)d->y, d->bias, (const float*)d->emb,
-                                                                 d->residual);
+                                                                 d->residual));
     else
-      conv_generic_kernel<float, false><<<grid, 256, 0, stream>>>(p, (const float*)d->x, (const float*)d->w,
+      MKD_LAUNCH_OK(launch_pdl(conv_generic_kernel<float, false>, dim3(grid), dim3(256), 0, stream, p, (const float*)d->x, (const float*)d->w,
                                                                   (float*)d->y, d->bias, (const float*)d->emb,
-                                                                  d->residual);
+                                                                  d->residual));
   }
   MKD_CHECK_LAUNCH();
   return MKD_OK;

@@ -1,6 +1,8 @@
 // Probes, the fused DDIM update (+CFG) kernel, layout conversion and the small elementwise kernels.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -13,6 +15,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MKD_PDL");
+    v = (e && strcmp(e, "1") == 0) ? 1 : 0;  // measured neutral-to-slightly-negative on this workload: opt-in
+  }
+  return v == 1;
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -41,6 +51,7 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
                                    float cfg_scale, const float* __restrict__ noise, float s1m, float sqrt_at,
                                    float sqrt_ap, float dirc, float sigma, float temp, float* __restrict__ x_prev,
                                    float* __restrict__ pred_x0, int64_t n) {
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float e = eps[i];
     if (cfg) {
@@ -65,9 +76,9 @@ extern "C" int mkd_ddim_update(const float* x, const float* eps, int cfg, float 
   int threads = 256;
   int blocks = (int)((n + threads - 1) / threads);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  ddim_update_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(x, eps, cfg, cfg_scale, noise, sqrt_one_minus_at,
+  MKD_LAUNCH_OK(launch_pdl(ddim_update_kernel, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x, eps, cfg, cfg_scale, noise, sqrt_one_minus_at,
                                                                    sqrt_at, sqrt_a_prev, dir_coef, sigma_t,
-                                                                   temperature, x_prev, pred_x0, n);
+                                                                   temperature, x_prev, pred_x0, n));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -77,6 +88,7 @@ extern "C" int mkd_ddim_update(const float* x, const float* eps, int cfg, float 
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int ld) {
+  pdl_wait();
   __shared__ float tile[32][33];
   int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -91,6 +103,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
 }
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW, int ld) {
+  pdl_wait();
   __shared__ float tile[32][33];
   int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -110,9 +123,9 @@ extern "C" int mkd_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, i
   MKD_REQUIRE(N <= 65535, MKD_E_INVALID, "nchw_to_nhwc: N too large");
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
   if (dtype == MKD_BF16)
-    nchw_to_nhwc_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, C, H * W, ld_dst);
+    MKD_LAUNCH_OK(launch_pdl(nchw_to_nhwc_kernel<bf16>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (bf16*)dst, C, H * W, ld_dst));
   else
-    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, (float*)dst, C, H * W, ld_dst);
+    MKD_LAUNCH_OK(launch_pdl(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (float*)dst, C, H * W, ld_dst));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -122,9 +135,9 @@ extern "C" int mkd_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, i
   MKD_REQUIRE(N <= 65535, MKD_E_INVALID, "nhwc_to_nchw: N too large");
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
   if (dtype == MKD_BF16)
-    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, C, H * W, ld_src);
+    MKD_LAUNCH_OK(launch_pdl(nhwc_to_nchw_kernel<bf16>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const bf16*)src, dst, C, H * W, ld_src));
   else
-    nhwc_to_nchw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, dst, C, H * W, ld_src);
+    MKD_LAUNCH_OK(launch_pdl(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const float*)src, dst, C, H * W, ld_src));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -133,6 +146,7 @@ extern "C" int mkd_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, i
 template <typename T>
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, T* __restrict__ out, int B, int dim,
                                           float neg_log_mp) {
+  pdl_wait();
   int half = dim / 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
     int b = i / half, k = i % half;
@@ -149,9 +163,9 @@ extern "C" int mkd_timestep_embedding(const int64_t* t, void* out, int dtype, in
   int n = B * (dim / 2), threads = 128, blocks = (n + threads - 1) / threads;
   float nl = -logf(max_period);
   if (dtype == MKD_BF16)
-    timestep_embedding_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>(t, (bf16*)out, B, dim, nl);
+    MKD_LAUNCH_OK(launch_pdl(timestep_embedding_kernel<bf16>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, t, (bf16*)out, B, dim, nl));
   else
-    timestep_embedding_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(t, (float*)out, B, dim, nl);
+    MKD_LAUNCH_OK(launch_pdl(timestep_embedding_kernel<float>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, t, (float*)out, B, dim, nl));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -159,6 +173,7 @@ extern "C" int mkd_timestep_embedding(const int64_t* t, void* out, int dtype, in
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void silu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n) {
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = from_f<T>(silu_f(to_f(x[i])));
 }
@@ -168,9 +183,9 @@ extern "C" int mkd_silu(const void* x, void* y, int dtype, int64_t n, mkd_stream
   int threads = 256, blocks = (int)((n + threads - 1) / threads);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (dtype == MKD_BF16)
-    silu_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n);
+    MKD_LAUNCH_OK(launch_pdl(silu_kernel<bf16>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, n));
   else
-    silu_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, n);
+    MKD_LAUNCH_OK(launch_pdl(silu_kernel<float>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const float*)x, (float*)y, n));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -178,6 +193,7 @@ extern "C" int mkd_silu(const void* x, void* y, int dtype, int64_t n, mkd_stream
 // GEGLU, 8 channels per thread (16-byte bf16 vectors).
 template <typename T>
 __global__ void geglu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t M, int inner, int ldx, int ldy) {
+  pdl_wait();
   int vpr = inner / 8;
   int64_t total = M * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -200,9 +216,9 @@ extern "C" int mkd_geglu(const void* x, void* y, int dtype, int64_t M, int inner
   int threads = 256, blocks = (int)((total + threads - 1) / threads);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (dtype == MKD_BF16)
-    geglu_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, M, inner, ldx, ldy);
+    MKD_LAUNCH_OK(launch_pdl(geglu_kernel<bf16>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, M, inner, ldx, ldy));
   else
-    geglu_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, M, inner, ldx, ldy);
+    MKD_LAUNCH_OK(launch_pdl(geglu_kernel<float>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const float*)x, (float*)y, M, inner, ldx, ldy));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -210,6 +226,7 @@ extern "C" int mkd_geglu(const void* x, void* y, int dtype, int64_t M, int inner
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t M, int C,
                            int lda, int ldb, int ldy) {
+  pdl_wait();
   int vpr = C / 8;
   int64_t total = M * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -232,9 +249,9 @@ extern "C" int mkd_add(const void* a, const void* b, void* y, int dtype, int64_t
   int threads = 256, blocks = (int)((total + threads - 1) / threads);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (dtype == MKD_BF16)
-    add_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)y, M, C, lda, ldb, ldy);
+    MKD_LAUNCH_OK(launch_pdl(add_kernel<bf16>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const bf16*)a, (const bf16*)b, (bf16*)y, M, C, lda, ldb, ldy));
   else
-    add_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)a, (const float*)b, (float*)y, M, C, lda, ldb, ldy);
+    MKD_LAUNCH_OK(launch_pdl(add_kernel<float>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const float*)a, (const float*)b, (float*)y, M, C, lda, ldb, ldy));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }

@@ -16,6 +16,7 @@
 //   * split-K (extra work units): each split writes fp32 partials to the workspace; splitk_epilogue_kernel reduces them
 //     and applies the same epilogue.  Only where the tiles cannot fill half the SMs and K is deep (the 4x4 / 8x8 levels).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 using namespace mkd;
@@ -50,7 +51,20 @@ struct MainP {
   int Wb, Hb, Nb;      // box
   int tiles_w, tiles_h;
   int m_tiles, n_tiles, num_units;  // persistent scheduler: unit -> (n_tile, m_tile, split)
+  unsigned long long* trace;        // debug: per-CTA %globaltimer stamps (mkd_debug_set_trace), else nullptr
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+// slot layout per CTA (16 x u64): 0 entry, 1 prologue done, 2 first TMA issued, 3 first full barrier, 4 unit-0 MMAs
+// committed, 5 unit-0 accumulator ready (epilogue), 6 unit-0 epilogue done, 7 last unit epilogue done, 8 exit
+#define MKD_TRACE(slot)                                                     \
+  do {                                                                      \
+    if (mp.trace) mp.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer();    \
+  } while (0)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,6 +90,28 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
           "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// multicast: the box lands at the same CTA-relative smem offset, and completes on the same CTA-relative mbarrier,
+// in every CTA of the cluster named by `mask`
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;\n" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();  // the role branches above diverged lanes of warps 0/1: reconverge before the .aligned barrier
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             int c3) {
@@ -226,15 +262,26 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
                : "r"(taddr));
 }
 
-template <int BN>
+// CL = CTAs per cluster (1 or 2).  CL == 2: the pair works on two vertically adjacent M tiles of the same N tile;
+// each CTA loads its own A tile and HALF of the shared weight tile, multicast into both CTAs' shared memory, which
+// removes 28% of the L2 -> SM traffic that bounds the large convolutions (measured: 10.7 TB/s of tile loads at CL = 1).
+// EPI selects the ONE epilogue variant an instantiation carries (a single body holding all of them was ~10^4 SASS
+// instructions and instruction-fetch bound in phase 2):
+enum { EPI_PLAIN = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_PARTIAL = 3 };
+template <int BN, int CL, int EPI>
 __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
                                                               const __grid_constant__ CUtensorMap bmap, MainP mp, EpiP ep) {
   using C = Cfg<BN>;
+  constexpr int B_HALF_BYTES = BN * BK * 2 / CL;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+  const int cl_id = blockIdx.x / CL, cl_num = gridDim.x / CL;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, PW = C::PW, NP = C::NP, LDT = C::LDT;
   constexpr int TCOLS = tmem_cols2(2 * BN);
   constexpr int NG = PW / 8;  // 8-column groups per panel
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (128B-swizzle atoms) by OFFSETTING the __shared__ array: arithmetic on it keeps the shared
+  // address space, so staging accesses compile to LDS/STS instead of generic LD/ST
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + C::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -243,13 +290,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) MKD_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&bmap)) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(full_bar + i, 1);
-      mbar_init(empty_bar + i, 1);
+      mbar_init(empty_bar + i, CL);  // a stage is free when the MMA warp of EVERY CTA that received it has released it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full_bar + i, 1);
@@ -262,17 +310,24 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast to / arrives on them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
+  // from here on global memory written by it is read (TMA loads, residuals) and its outputs may be overwritten
+  pdl_wait();
+  if (threadIdx.x == 0) MKD_TRACE(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int it = 0;
-      for (int unit = blockIdx.x; unit < mp.num_units; unit += gridDim.x) {
+      int s = 0, ph = 0;       // smem stage / phase, carried across work units
+      bool first = true;
+#pragma unroll 1
+      for (int unit = cl_id; unit < mp.num_units; unit += cl_num) {
         const int n_tile = unit % mp.n_tiles, rest = unit / mp.n_tiles;
-        const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
+        const int m_tile = (rest % mp.m_tiles) * CL + (int)cta_rank, split = rest / mp.m_tiles;
         const int kb0 = split * mp.kb_per_split, kb1 = min(mp.kblocks, kb0 + mp.kb_per_split);
         int w0 = 0, h0 = 0, n0 = 0;
         if (mp.conv) {
@@ -281,19 +336,36 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
           h0 = th * mp.Hb;
           n0 = tn * mp.Nb;
         }
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES, ph = (it / STAGES) & 1;
+        // filter-tap walk (r, sx, cb) kept incrementally: this one thread feeds a 320-cycle MMA per k-block, so the
+        // loop body must stay a handful of instructions (no integer divisions)
+        const int tap0 = kb0 / mp.cblocks;
+        int cb = kb0 - tap0 * mp.cblocks, r = tap0 / mp.S;
+        int sx = tap0 - r * mp.S;
+        const int nb = n_tile * BN + (int)cta_rank * (BN / CL);
+#pragma unroll 1
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
           mbar_expect_tx(full_bar + s, STAGE_BYTES);
           unsigned char* sa = smem + s * STAGE_BYTES;
-          if (mp.conv) {
-            const int tap = kb / mp.cblocks, cb = kb - tap * mp.cblocks;
-            const int r = tap / mp.S, sx = tap - r * mp.S;
-            tma_load_4d(&amap, full_bar + s, sa, cb * BK, w0 + sx - mp.pad, h0 + r - mp.pad, n0);
-          } else {
-            tma_load_2d(&amap, full_bar + s, sa, kb * BK, m_tile * BM);
+          if (mp.conv) tma_load_4d(&amap, full_bar + s, sa, cb * BK, w0 + sx - mp.pad, h0 + r - mp.pad, n0);
+          else tma_load_2d(&amap, full_bar + s, sa, kb * BK, m_tile * BM);
+          if (CL == 1) tma_load_2d(&bmap, full_bar + s, sa + A_BYTES, kb * BK, nb);
+          else tma_load_2d_mc(&bmap, full_bar + s, sa + A_BYTES + cta_rank * B_HALF_BYTES, kb * BK, nb, (uint16_t)((1u << CL) - 1));
+          if (first) {
+            MKD_TRACE(2);
+            first = false;
           }
-          tma_load_2d(&bmap, full_bar + s, sa + A_BYTES, kb * BK, n_tile * BN);
+          if (++cb == mp.cblocks) {
+            cb = 0;
+            if (++sx == mp.S) {
+              sx = 0;
+              ++r;
+            }
+          }
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
@@ -301,17 +373,23 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      int it = 0, j = 0;
-      for (int unit = blockIdx.x; unit < mp.num_units; unit += gridDim.x, ++j) {
+      int s = 0, ph = 0, j = 0;
+      bool first = true;
+#pragma unroll 1
+      for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
         const int split = (unit / mp.n_tiles) / mp.m_tiles;
         const int kb0 = split * mp.kb_per_split, kb1 = min(mp.kblocks, kb0 + mp.kb_per_split);
         const int ab = j & 1, use = j >> 1;
         mbar_wait(tmem_empty_bar + ab, (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES, ph = (it / STAGES) & 1;
+#pragma unroll 1
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar + s, ph);
+          if (first) {
+            MKD_TRACE(3);
+            first = false;
+          }
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
@@ -320,30 +398,70 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
             // advance K inside the 128-byte swizzle atom: +32 bytes per UMMA_K (encoded >> 4)
             umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > kb0 || k) ? 1u : 0u);
           }
-          tcgen05_commit(empty_bar + s);  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in every CTA that multicasts into it) once the MMAs above retire
+          if (CL == 1) tcgen05_commit(empty_bar + s);
+          else tcgen05_commit_mc(empty_bar + s, (uint16_t)((1u << CL) - 1));
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
         tcgen05_commit(tmem_full_bar + ab);  // accumulator of this unit complete
+        if (j == 0) MKD_TRACE(4);
       }
     }
   } else {
     // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4 =====
+    // Phase-2 work split: thread -> ONE 8-channel column group g (so its bias vector is loaded once per panel) and
+    // rows rr, rr + RPI, ... of the tile.  Consecutive threads own consecutive groups of the same row: every global
+    // access of a warp is a run of consecutive 16 / 32-byte pieces.
+    constexpr int RPI = 256 / NG;                 // rows covered per iteration (25 when NG = 10: 6 threads idle)
+    constexpr int P2_ITERS = (BM + RPI - 1) / RPI;
     const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
     const int et = threadIdx.x - 64;  // 0..255
     const int trow_idx = quad * 32 + lane;
+    const int g2 = et % NG, rr = et / NG;         // phase-2 column group / first row
+    const bool p2_active = et < RPI * NG;
     int j = 0;
-    for (int unit = blockIdx.x; unit < mp.num_units; unit += gridDim.x, ++j) {
+    for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
       const int n_tile = unit % mp.n_tiles, rest = unit / mp.n_tiles;
-      const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
+      const int m_tile = (rest % mp.m_tiles) * CL + (int)cta_rank, split = rest / mp.m_tiles;
       const int ab = j & 1, use = j >> 1;
       const int m_base = m_tile * BM;
-      mbar_wait(tmem_full_bar + ab, use & 1);
-      tcgen05_fence_after();
+      constexpr bool geglu = EPI == EPI_GEGLU;
+      constexpr bool plain = EPI == EPI_PLAIN || EPI == EPI_SILU;
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
-      const bool geglu = ep.act == MKD_ACT_GEGLU && !ep.partial;
+      bool acc_ready = false;
 #pragma unroll 1
       for (int p = 0; p < NP; ++p) {
+        // ---- prefetch: every long-latency global load of this panel is issued before the TMEM drain ----
+        const int o = n_tile * BN + p * PW + g2 * 8;  // first output channel of this thread's group (plain path)
+        const bool full8 = plain && p2_active && o + 8 <= ep.N_out;
+        float bias8[8], res[P2_ITERS][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bias8[k] = 0.f;
+        if (full8 && ep.bias) load8(ep.bias + o, bias8);
+#pragma unroll
+        for (int u = 0; u < P2_ITERS; ++u) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) res[u][k] = 0.f;
+          const int m = m_base + rr + u * RPI;
+          if (full8 && rr + u * RPI < BM && m < ep.M) {
+            if (ep.res) {
+              if (ep.res_f32) load8(static_cast<const float*>(ep.res) + (int64_t)m * ep.ldr + o, res[u]);
+              else load8(static_cast<const bf16*>(ep.res) + (int64_t)m * ep.ldr + o, res[u]);
+            }
+          }
+        }
+        if (!acc_ready) {
+          mbar_wait(tmem_full_bar + ab, use & 1);
+          if (j == 0 && et == 0) MKD_TRACE(5);
+          tcgen05_fence_after();
+          acc_ready = true;
+        }
         asm volatile("bar.sync 1, 256;\n" ::: "memory");  // previous panel fully consumed (WAR on the staging panel)
-        // ---- phase 1: this thread's row, column groups g = half, half + 2, ... of the panel ----
+        if (j == 0 && et == 0 && p == 0) MKD_TRACE(9);
+        // ---- phase 1: this thread's accumulator row, column groups g = half, half + 2, ... of the panel ----
         {
           uint32_t r[(NG + 1) / 2][8];
 #pragma unroll
@@ -357,6 +475,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
             }
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          if (j == 0 && et == 0 && p == 0) MKD_TRACE(10);
 #pragma unroll
           for (int gi = 0; gi < (NG + 1) / 2; ++gi) {
             const int g = half + 2 * gi;
@@ -373,59 +492,112 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
           if (lane == 0) mbar_arrive(tmem_empty_bar + ab);
         }
         asm volatile("bar.sync 1, 256;\n" ::: "memory");  // panel staged (RAW)
+        if (j == 0 && et == 0) MKD_TRACE(p == 0 ? 11 : 13);
         // ---- phase 2: coalesced walk over the panel ----
-        if (ep.partial) {
-#pragma unroll 2
-          for (int i = et; i < BM * NG; i += 256) {
-            const int row = i / NG, g = i - row * NG;
-            const int m = m_base + row, n = n_tile * BN + p * PW + g * 8;
-            if (m < ep.M && n < ep.n_rows) {
-              float* dst = ep.partial + ((int64_t)split * ep.M + m) * ep.n_rows + n;
-              const float* src = staging + row * LDT + g * 8;
-              *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
-              *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(src + 4);
+        if constexpr (EPI == EPI_PARTIAL) {
+          if (p2_active) {
+            const int n = n_tile * BN + p * PW + g2 * 8;
+#pragma unroll
+            for (int u = 0; u < P2_ITERS; ++u) {
+              const int row = rr + u * RPI, m = m_base + row;
+              if (row < BM && m < ep.M && n < ep.n_rows) {
+                float* dst = ep.partial + ((int64_t)split * ep.M + m) * ep.n_rows + n;
+                const float* src = staging + row * LDT + g2 * 8;
+                *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+                *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(src + 4);
+              }
             }
           }
-        } else if (geglu) {
-          constexpr int NV = NG / 2;
-#pragma unroll 2
-          for (int i = et; i < BM * NV; i += 256) {
-            const int row = i / NV, g = i - row * NV;
-            const int m = m_base + row;
-            if (m < ep.M) {
-              float a[8], gt[8];
-              load8(staging + row * LDT + g * 8, a);
-              load8(staging + row * LDT + (NV + g) * 8, gt);
-              const int rv = n_tile * BN + p * (PW / 2) + g * 8;
-              epilogue_geglu8(ep, m, rv, rv + BN / 2, n_tile * (BN / 2) + p * (PW / 2) + g * 8, a, gt);
+        } else if constexpr (geglu) {
+          constexpr int NV = NG / 2;  // value groups of the panel; their gate groups follow in the staging row
+          const int gv = et % NV, rv0 = et / NV;
+          constexpr int RPG = 256 / NV, G_ITERS = (BM + RPG - 1) / RPG;
+          if (et < RPG * NV) {
+            const int rowv = n_tile * BN + p * (PW / 2) + gv * 8;  // weight/bias row of the value channels
+            float bv[8], bg[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bv[k] = bg[k] = 0.f;
+            if (ep.bias) {
+              load8(ep.bias + rowv, bv);
+              load8(ep.bias + rowv + BN / 2, bg);
+            }
+#pragma unroll
+            for (int u = 0; u < G_ITERS; ++u) {
+              const int row = rv0 + u * RPG, m = m_base + row;
+              if (row < BM && m < ep.M) {
+                float a[8], gt[8], r[8];
+                load8(staging + row * LDT + gv * 8, a);
+                load8(staging + row * LDT + (NV + gv) * 8, gt);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = (a[k] + bv[k]) * gelu_erf_f(gt[k] + bg[k]);
+                store8(ep.y + (int64_t)m * ep.ldy + n_tile * (BN / 2) + p * (PW / 2) + gv * 8, r);
+              }
             }
           }
-        } else {
-#pragma unroll 2
-          for (int i = et; i < BM * NG; i += 256) {
-            const int row = i / NG, g = i - row * NG;
-            const int m = m_base + row;
-            if (m < ep.M) {
+        } else if (p2_active) {
+#pragma unroll
+          for (int u = 0; u < P2_ITERS; ++u) {
+            const int row = rr + u * RPI, m = m_base + row;
+            if (row < BM && m < ep.M && o < ep.N_out) {
               float r[8];
-              load8(staging + row * LDT + g * 8, r);
-              epilogue_vec8(ep, m, n_tile * BN + p * PW + g * 8, r);
+              load8(staging + row * LDT + g2 * 8, r);
+              if (full8) {
+                if (ep.emb) {  // per-sample timestep embedding (ResBlock conv1 only): small, L1/L2 resident
+                  float t[8];
+                  load8(ep.emb + (int64_t)(m / ep.pix_per_img) * ep.lde + o, t);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) r[k] += t[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = (r[k] + bias8[k]) * ep.alpha + res[u][k];
+                if constexpr (EPI == EPI_SILU) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) r[k] = silu_f(r[k]);
+                }
+                if (ep.y32) store8(ep.y32 + (int64_t)m * ep.ldy32 + o, r);
+                if (ep.y) store8(ep.y + (int64_t)m * ep.ldy + o, r);
+              } else {  // ragged channel tail (e.g. the 4-channel `out` conv): scalar, statically indexed
+                const int nimg = ep.emb ? m / ep.pix_per_img : 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  if (o + k < ep.N_out) {
+                    float t = r[k] + (ep.bias ? ep.bias[o + k] : 0.f);
+                    if (ep.emb) t += to_f(ep.emb[(int64_t)nimg * ep.lde + o + k]);
+                    t *= ep.alpha;
+                    if (ep.res)
+                      t += ep.res_f32 ? static_cast<const float*>(ep.res)[(int64_t)m * ep.ldr + o + k]
+                                      : to_f(static_cast<const bf16*>(ep.res)[(int64_t)m * ep.ldr + o + k]);
+                    if constexpr (EPI == EPI_SILU) t = silu_f(t);
+                    if (ep.y32) ep.y32[(int64_t)m * ep.ldy32 + o + k] = t;
+                    if (ep.y) ep.y[(int64_t)m * ep.ldy + o + k] = from_f<bf16>(t);
+                  }
+                }
+              }
             }
           }
         }
+        if (j == 0 && et == 0 && p == 0) MKD_TRACE(12);
+      }
+      if (et == 0) {
+        if (j == 0) MKD_TRACE(6);
+        MKD_TRACE(7);
       }
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TCOLS));
   }
+  if (threadIdx.x == 0) MKD_TRACE(8);
 }
 
 // split-K reducer: sums the fp32 partials and applies the epilogue; one thread per (row, 16 weight rows).
 template <int BN>
 __global__ void splitk_epilogue_kernel(EpiP ep, int splits) {
+  pdl_wait();
   const int groups = ep.n_rows / 16;
   const int64_t total = (int64_t)ep.M * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -464,6 +636,7 @@ __global__ void splitk_epilogue_kernel(EpiP ep, int splits) {
 // Nearest-neighbour x2 upsample, NHWC bf16, 8 channels per thread: out[n, 2h+dy, 2w+dx, :] = in[n, h, w, :].
 // (Upsample blocks: the 3x3 conv that follows then runs on the tensor cores like any other.)
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int ldx) {
+  pdl_wait();
   const int vpr = C / 8;
   const int64_t total = (int64_t)N * 4 * H * W * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -479,6 +652,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__
 // im2col for the three stride-2 Downsample convs: out[m, (r*3+s)*C + c] = in[n, 2p-1+r, 2q-1+s, c] (0 outside).
 // The outputs are 4x smaller than the inputs, so the 9x expansion costs little and the conv becomes a plain GEMM.
 __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int ldx) {
+  pdl_wait();
   const int vpr = C / 8, P = H / 2, Q = W / 2;
   const int64_t total = (int64_t)N * P * Q * 9 * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -580,14 +754,24 @@ int pick_bn(const mkd_conv_desc* d) {
   if (d->act == MKD_ACT_GEGLU) return 160;
   if (d->K % 160 == 0) return 160;
   if (d->K % 80 == 0) return 80;
-  if (d->K % 128 == 0) return 128;
   if (d->K % 64 == 0) return 64;
   if (d->K <= 32) return 32;
   return 64;  // ragged last tile: B rows beyond K are zero-filled by TMA, stores are masked
 }
 
-template <int BN>
+unsigned long long* g_trace = nullptr;
+int cluster_pref() {  // MKD_CLUSTER=2 enables the 2-CTA multicast pairs (BN = 160 shapes)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MKD_CLUSTER");
+    v = (e && atoi(e) >= 1 && atoi(e) <= 2) ? atoi(e) : 1;  // multicast pairs measured neutral on B200: opt-in
+  }
+  return v;
+}
+
+template <int BN, int CL>
 int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, MainP, EpiP);
   // stride-2 / upsample: rewrite the descriptor onto the materialised input living at the head of the workspace
   mkd_conv_desc dd = *d_in;
   mkd_conv_desc* d = &dd;
@@ -598,9 +782,9 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     int blocks = (int)((vecs + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (down)
-      im2col_s2_kernel<<<blocks, 256, 0, stream>>>((const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx);
+      MKD_LAUNCH_OK(launch_pdl(im2col_s2_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx));
     else
-      upsample2x_kernel<<<blocks, 256, 0, stream>>>((const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx);
+      MKD_LAUNCH_OK(launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx));
     MKD_CHECK_LAUNCH();
     const size_t used = (bytes + 1023) & ~(size_t)1023;
     dd.x = d_in->workspace;
@@ -615,8 +799,12 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "gemm_tcgen05: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    KernelFn all[4] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
+                       gemm_tcgen05_kernel<BN, CL, (BN == 160 ? EPI_GEGLU : EPI_PLAIN)>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>};
+    for (KernelFn f : all) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "gemm_tcgen05: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    }
     configured = true;
   }
   CUtensorMap amap, bmap;
@@ -636,7 +824,7 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)g.Ktot, (cuuint64_t)d->K};
     cuuint64_t str[1] = {(cuuint64_t)g.Ktot * 2};
-    cuuint32_t box[2] = {BK, BN};
+    cuuint32_t box[2] = {BK, BN / CL};  // CL == 2: each CTA of the pair fetches (and multicasts) half of the tile
     rc = encode(&bmap, d->w, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -652,7 +840,8 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   // split-K: only when the tile grid leaves more than half of the SMs idle AND K is deep enough that the fp32
   // partial round trip (2 * splits * M * N * 4 bytes) is cheaper than the idle tensor cores
   int splits = 1;
-  const int tiles = g.m_tiles * n_tiles;
+  const int m_groups = (g.m_tiles + CL - 1) / CL;  // M tiles per cluster row
+  const int tiles = m_groups * CL * n_tiles;
   if (d->workspace && tiles <= 74 && mp.kblocks >= 32 && d->K % 16 == 0) {
     splits = 148 / tiles;
     if (splits > mp.kblocks / 16) splits = mp.kblocks / 16;  // >= 16 K blocks (1024 of K) per split
@@ -672,22 +861,47 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   ep.y32 = d->y32; ep.ldy32 = d->ldy32; ep.res_f32 = d->residual_dtype == MKD_F32;
   ep.partial = splits > 1 ? (float*)d->workspace : nullptr;
 
-  mp.m_tiles = g.m_tiles;
+  mp.m_tiles = m_groups;
   mp.n_tiles = n_tiles;
-  mp.num_units = tiles * splits;
-  const int grid = mp.num_units < num_sms() ? mp.num_units : num_sms();
-  gemm_tcgen05_kernel<BN><<<grid, 320, smem, stream>>>(amap, bmap, mp, ep);
+  mp.trace = g_trace;
+  mp.num_units = m_groups * n_tiles * splits;  // cluster-level work units
+  const int max_clusters = num_sms() / CL;
+  const int grid = CL * (mp.num_units < max_clusters ? mp.num_units : max_clusters);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = CL;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 2 : 1;
+    KernelFn fn = gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>;
+    if (ep.partial) fn = gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>;
+    else if (ep.act == MKD_ACT_GEGLU) fn = gemm_tcgen05_kernel<BN, CL, (BN == 160 ? EPI_GEGLU : EPI_PLAIN)>;
+    else if (ep.act == MKD_ACT_SILU) fn = gemm_tcgen05_kernel<BN, CL, EPI_SILU>;
+    MKD_LAUNCH_OK(cudaLaunchKernelEx(&cfg, fn, amap, bmap, mp, ep));
+  }
   MKD_CHECK_LAUNCH();
   if (splits > 1) {
     int64_t total = (int64_t)g.M * (d->K / 16);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_epilogue_kernel<BN><<<blocks, 256, 0, stream>>>(ep, splits);
+    MKD_LAUNCH_OK(launch_pdl(splitk_epilogue_kernel<BN>, dim3(blocks), dim3(256), 0, stream, ep, splits));
     MKD_CHECK_LAUNCH();
   }
   return MKD_OK;
 }
 }  // namespace
+
+// debug hook (not part of the public header): device buffer of 148*16 u64 that the next GEMM launches stamp
+extern "C" void mkd_debug_set_trace(void* p) { g_trace = static_cast<unsigned long long*>(p); }
 
 namespace mkd {
 bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
@@ -698,12 +912,12 @@ bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
 int conv2d_tcgen05(const mkd_conv_desc* d, cudaStream_t stream) {
   Geometry g;
   MKD_REQUIRE(geometry(d, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
+  const int cl = (g.m_tiles >= 2) ? cluster_pref() : 1;  // a pair needs two M tiles to share a weight tile
   switch (pick_bn(d)) {
-    case 160: return launch<160>(d, g, stream);
-    case 128: return launch<128>(d, g, stream);
-    case 80: return launch<80>(d, g, stream);
-    case 64: return launch<64>(d, g, stream);
-    default: return launch<32>(d, g, stream);
+    case 160: return (cl == 2) ? launch<160, 2>(d, g, stream) : launch<160, 1>(d, g, stream);
+    case 80: return launch<80, 1>(d, g, stream);
+    case 64: return launch<64, 1>(d, g, stream);
+    default: return launch<32, 1>(d, g, stream);
   }
 }
 }  // namespace mkd

@@ -2,10 +2,16 @@
 //   - every global access is a 16-byte (bf16) / 32-byte (fp32) vector of 8 consecutive channels, so a warp reads
 //     512 contiguous bytes of a pixel row;
 //   - statistics are fp32; the cross-thread reductions are warp shuffles + one small smem pass;
-//   - GroupNorm runs as two launches (per-chunk partial sums -> normalise[+SiLU]); the second read of x is served
-//     by the 126 MB L2 for every tensor of the 256^2 / batch-16 workload (largest: 16*1024*960*2 B = 31 MB).
+//   - GroupNorm is ONE launch: a thread-block cluster (<= 8 CTAs) per sample; each CTA reduces its pixel chunk, the
+//     per-group partial sums are exchanged through distributed shared memory, then every CTA normalises its own chunk
+//     (the second read of x is served by L1/L2: the chunk was just touched by the same SM).  A two-launch variant
+//     (partials through global memory) covers the cases a cluster cannot: tiny batches that need > 8 chunks per
+//     sample to fill the GPU.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 using namespace mkd;
+namespace cg = cooperative_groups;
 
 namespace {
 constexpr int GN_MAX_CHUNKS = 64;  // pixel chunks per sample (partials reduced by the apply kernel)
@@ -15,6 +21,7 @@ constexpr int GN_MAX_CHUNKS = 64;  // pixel chunks per sample (partials reduced 
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partial, int HW, int C, int groups,
                                 int ldx, int rows_per_chunk, int nchunks) {
+  pdl_wait();
   extern __shared__ float sm[];  // [2][RY][C]
   const int VX = C / 8, RY = blockDim.x / VX;
   const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
@@ -25,14 +32,23 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ pa
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   if (ry < RY) {
     const T* base = x + (int64_t)n * HW * ldx + vx * 8;
-    for (int r = r0 + ry; r < r1; r += RY) {
-      float v[8];
-      load8(base + (int64_t)r * ldx, v);
+    for (int r = r0 + ry; r < r1; r += 4 * RY) {
+      float v[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += v[j];
-        q[j] += v[j] * v[j];
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * RY < r1) load8(base + (int64_t)(r + u * RY) * ldx, v[u]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[u][j];
+          q[j] += v[u][j] * v[u][j];
+        }
     }
     float* ss = sm + (int64_t)ry * C + vx * 8;
     float* qq = sm + (int64_t)(RY + ry) * C + vx * 8;
@@ -62,6 +78,7 @@ template <typename T, typename TO, bool SILU>
 __global__ void gn_apply_kernel(const T* __restrict__ x, TO* __restrict__ y, const float2* __restrict__ partial,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
                                 int groups, int ldx, int ldy, int rows_per_chunk, int nchunks, float eps) {
+  pdl_wait();
   extern __shared__ float sm[];  // scale[C], shift[C]
   float* scale = sm;
   float* shift = sm + C;
@@ -96,15 +113,125 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, TO* __restrict__ y, con
   }
   const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
   TO* yb = y + (int64_t)n * HW * ldy + vx * 8;
-  for (int r = r0 + ry; r < r1; r += RY) {
-    float v[8];
-    load8(xb + (int64_t)r * ldx, v);
+  for (int r = r0 + ry; r < r1; r += 4 * RY) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * RY < r1) load8(xb + (int64_t)(r + u * RY) * ldx, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r + u * RY < r1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = v[u][j] * sc[j] + sh[j];
+          v[u][j] = SILU ? silu_f(t) : t;
+        }
+        store8(yb + (int64_t)(r + u * RY) * ldy, v[u]);
+      }
+    }
+  }
+}
+
+// Single-launch GroupNorm: gridDim.x = cluster size = chunks per sample, blockIdx.y = sample.
+template <typename T, typename TO, bool SILU>
+__global__ void gn_cluster_kernel(const T* __restrict__ x, TO* __restrict__ y, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, int HW, int C, int groups, int ldx, int ldy,
+                                  int rows_per_chunk, float eps) {
+  pdl_wait();
+  extern __shared__ float sm[];      // phase 1: [2][RY][C] ; phase 2: scale[C], shift[C]
+  __shared__ float2 part[64];        // this CTA's (sum, sumsq) per group — read by the whole cluster via DSMEM
+  cg::cluster_group cluster = cg::this_cluster();
+  const int VX = C / 8, RY = blockDim.x / VX;
+  const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
+  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (ry < RY) {
+    for (int r = r0 + ry; r < r1; r += 4 * RY) {  // 4 independent 32-byte loads in flight per thread
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * RY < r1) load8(xb + (int64_t)(r + u * RY) * ldx, v[u]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[u][j];
+          q[j] += v[u][j] * v[u][j];
+        }
+    }
+    float* ss = sm + (int64_t)ry * C + vx * 8;
+    float* qq = sm + (int64_t)(RY + ry) * C + vx * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = v[j] * sc[j] + sh[j];
-      v[j] = SILU ? silu_f(t) : t;
+      ss[j] = s[j];
+      qq[j] = q[j];
     }
-    store8(yb + (int64_t)r * ldy, v);
+  }
+  __syncthreads();
+  const int cgs = C / groups, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < groups; g += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int i = lane; i < RY * cgs; i += 32) {
+      int r = i / cgs, c = g * cgs + i % cgs;
+      a += sm[(int64_t)r * C + c];
+      b += sm[(int64_t)(RY + r) * C + c];
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) part[g] = make_float2(a, b);
+  }
+  cluster.sync();  // every CTA's partials are published (also a CTA-wide barrier: phase-1 smem is free again)
+  float* scale = sm;
+  float* shift = sm + C;
+  const float inv_cnt = 1.0f / ((float)cgs * (float)HW);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cgs;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < nchunks; ++k) {
+      const float2 p = *cluster.map_shared_rank(&part[g], k);
+      a += p.x;
+      b += p.y;
+    }
+    const float mean = a * inv_cnt;
+    const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+    const float sc = gamma[c] * rsqrtf(var + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+  }
+  cluster.sync();  // nobody may exit (or overwrite `part`) while a peer still reads it; also publishes scale/shift
+  if (ry >= RY) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[vx * 8 + j];
+    sh[j] = shift[vx * 8 + j];
+  }
+  TO* yb = y + (int64_t)n * HW * ldy + vx * 8;
+  for (int r = r0 + ry; r < r1; r += 4 * RY) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * RY < r1) load8(xb + (int64_t)(r + u * RY) * ldx, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r + u * RY < r1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = v[u][j] * sc[j] + sh[j];
+          v[u][j] = SILU ? silu_f(t) : t;
+        }
+        store8(yb + (int64_t)(r + u * RY) * ldy, v[u]);
+      }
+    }
   }
 }
 
@@ -114,6 +241,7 @@ constexpr int LN_VPL = 8;
 template <typename T, typename TO>
 __global__ void layernorm_kernel(const T* __restrict__ x, TO* __restrict__ y, int64_t M, int C, int ldx, int ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -169,6 +297,36 @@ static int groupnorm_launch(const T* x, TO* y, int N, int HW, int C, int groups,
   int threads = VX >= 256 ? VX : (256 / VX) * VX;  // whole number of row lanes
   threads = ((threads + 31) / 32) * 32;
   const int RY = threads / VX;
+  {
+    // single-launch cluster path: P = 1, 2, 4 or 8 chunks per sample (one cluster), when that fills enough SMs
+    int P = 8;
+    while (P > 1 && HW / P < 2 * RY) P >>= 1;
+    if ((N * P >= 64 || (int64_t)HW * C <= 64 * 1024) && groups <= 64) {
+      const int rows = (HW + P - 1) / P;
+      const size_t smem = (size_t)2 * RY * C * sizeof(float) > (size_t)2 * C * sizeof(float) ? (size_t)2 * RY * C * sizeof(float)
+                                                                                                 : (size_t)2 * C * sizeof(float);
+      MKD_REQUIRE(smem <= 48 * 1024, MKD_E_INVALID, "groupnorm: C=%d too large", C);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(P, N);
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = P;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 2;
+      cudaError_t e = silu ? cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T, TO, true>, x, y, gamma, beta, HW, C, groups, ldx, ldy, rows, eps)
+                           : cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T, TO, false>, x, y, gamma, beta, HW, C, groups, ldx, ldy, rows, eps);
+      MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "groupnorm: cluster launch failed: %s", cudaGetErrorString(e));
+      MKD_CHECK_LAUNCH();
+      return MKD_OK;
+    }
+  }
   // enough CTAs to fill the machine (~4 per SM), at least 2*RY rows per chunk
   int want = (148 * 4 + N - 1) / N;
   int nchunks = HW / (2 * RY);
@@ -180,14 +338,14 @@ static int groupnorm_launch(const T* x, TO* y, int N, int HW, int C, int groups,
   dim3 grid(nchunks, N);
   size_t sm1 = (size_t)2 * RY * C * sizeof(float), sm2 = (size_t)2 * C * sizeof(float);
   MKD_REQUIRE(sm1 <= 48 * 1024 && sm2 <= 48 * 1024, MKD_E_INVALID, "groupnorm: C=%d too large", C);
-  gn_stats_kernel<T><<<grid, threads, sm1, st>>>(x, partial, HW, C, groups, ldx, rows_per_chunk, nchunks);
+  MKD_LAUNCH_OK(launch_pdl(gn_stats_kernel<T>, dim3(grid), dim3(threads), sm1, st, x, partial, HW, C, groups, ldx, rows_per_chunk, nchunks));
   MKD_CHECK_LAUNCH();
   if (silu)
-    gn_apply_kernel<T, TO, true><<<grid, threads, sm2, st>>>(x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
-                                                         rows_per_chunk, nchunks, eps);
+    MKD_LAUNCH_OK(launch_pdl(gn_apply_kernel<T, TO, true>, dim3(grid), dim3(threads), sm2, st, x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
+                                                         rows_per_chunk, nchunks, eps));
   else
-    gn_apply_kernel<T, TO, false><<<grid, threads, sm2, st>>>(x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
-                                                          rows_per_chunk, nchunks, eps);
+    MKD_LAUNCH_OK(launch_pdl(gn_apply_kernel<T, TO, false>, dim3(grid), dim3(threads), sm2, st, x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
+                                                          rows_per_chunk, nchunks, eps));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -226,11 +384,11 @@ extern "C" int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, i
   int64_t blocks = (M + warps - 1) / warps;
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
-    layernorm_kernel<bf16, bf16><<<(unsigned)blocks, warps * 32, 0, st>>>((const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps);
+    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<bf16, bf16>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps));
   else if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
-    layernorm_kernel<float, bf16><<<(unsigned)blocks, warps * 32, 0, st>>>((const float*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps);
+    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<float, bf16>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const float*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps));
   else if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
-    layernorm_kernel<float, float><<<(unsigned)blocks, warps * 32, 0, st>>>((const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps);
+    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<float, float>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps));
   else
     MKD_REQUIRE(false, MKD_E_INVALID, "layernorm: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
   MKD_CHECK_LAUNCH();

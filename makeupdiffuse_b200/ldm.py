@@ -13,6 +13,8 @@ halves because ``uc_cat = c_cat``, diffusion_makeup.py:401) and every cross-atte
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -50,6 +52,9 @@ class B200ControlLDM:
         self.sqrt_recip_alphas_cumprod = f32(np.sqrt(1.0 / ac))
         self.sqrt_recipm1_alphas_cumprod = f32(np.sqrt(1.0 / ac - 1))
         self._cond_cache = {}
+        # ControlNet trunk on a second stream, concurrent with the UNet encoder (MKD_CONCURRENT=0 serialises, for A/B runs)
+        self.concurrent = os.environ.get("MKD_CONCURRENT", "1") != "0"
+        self._side = None
 
     @property
     def device(self):
@@ -95,12 +100,31 @@ class B200ControlLDM:
         N, _, H, W = x_noisy.shape
         prep = self._prepare(cond)
         t = t.to(torch.int64).contiguous()
+        use_cn = cond["c_concat"] is not None
+        two_streams = use_cn and self.concurrent and x_noisy.is_cuda
+        pending = None
+        if two_streams:
+            # The ControlNet trunk depends only on (x, t, hint, ctx): fork it onto a second stream so its many small,
+            # latency-bound kernels fill the SMs the UNet encoder's leave idle.  Inside a CUDA-graph capture this
+            # becomes a parallel branch of the graph.
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=x_noisy.device)
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            self._side.wait_event(fork)
+            with torch.cuda.stream(self._side):
+                pending = cn.run_trunk(cn._to_nhwc(x_noisy, "x_in"), prep["hint"], t, prep["kv_cn"], N, H, W)
+                join.record(self._side)
         xin = un._to_nhwc(x_noisy, "x_in")
         slots = un.encode(xin, t, prep["kv_unet"], N, H, W)
-        if cond["c_concat"] is not None:
+        if use_cn:
+            if two_streams:
+                torch.cuda.current_stream().wait_event(join)
+            else:
+                pending = cn.run_trunk(cn._to_nhwc(x_noisy, "x_in"), prep["hint"], t, prep["kv_cn"], N, H, W)
             inject = [None] * 12 + [slots[12]] if self.only_mid_control else slots
-            cn.run(cn._to_nhwc(x_noisy, "x_in"), prep["hint"], t, prep["kv_cn"], N, H, W, inject=inject,
-                   scales=self.control_scales)
+            cn.zero_convs(pending, N, inject=inject, scales=self.control_scales)
         e = un.decode(prep["kv_unet"], N, H, W)
         eps = torch.empty(N, un.out_channels, H, W, dtype=torch.float32, device=x_noisy.device)
         ops.nhwc_to_nchw(e, eps)

@@ -445,11 +445,12 @@ class B200ControlNet(_Net):
             cur, H, W = out, Ho, Wo
         return cur
 
-    def run(self, x_nhwc, guided_hint, t, ctx_kv, N, H, W, inject=None, scales=None):
-        """x_nhwc: [N*H*W, in_ch] view.  Writes the 13 residuals to own buffers, or — when ``inject`` (13 views into
-        the UNet's skip slots) is given — accumulates ``scale_i * zero_conv_i(h)`` straight into them."""
+    def run_trunk(self, x_nhwc, guided_hint, t, ctx_kv, N, H, W):
+        """time embedding + input blocks + middle block.  Returns the 13 pending zero-conv calls
+        [(weight key, input view, index, h, w)]: the trunk touches no UNet buffer, so it can run on a second stream
+        concurrently with the UNet encoder; the zero-convs (which may inject into UNet skip slots) come after the join."""
         emb_all = self._time_embedding(t, N)
-        outs = []
+        pending = []
         cur, h, w = Act(x_nhwc), H, W
         for j, blk in enumerate(self.input_blocks):
             ch = self.block_chans[j]
@@ -458,11 +459,19 @@ class B200ControlNet(_Net):
             # h = input_blocks[0](x) + guided_hint: the add rides in conv_in's epilogue
             self._run_block(blk, cur, y, emb_all, ctx_kv, N, h, w, conv_in_residual=guided_hint if j == 0 else None)
             cur, h, w = y, ho, wo
-            outs.append(self._zero_conv(f"zero_convs.{j}.0", cur.lo, j, N, h, w, inject, scales))
+            pending.append((f"zero_convs.{j}.0", cur.lo, j, h, w))
         y = self._act("cn_mid", N * h * w, self._ch, lo=True, hi=False)
         self._run_block(self.middle, cur, y, emb_all, ctx_kv, N, h, w)
-        outs.append(self._zero_conv("middle_block_out.0", y.lo, len(self.input_blocks), N, h, w, inject, scales))
-        return outs
+        pending.append(("middle_block_out.0", y.lo, len(self.input_blocks), h, w))
+        return pending
+
+    def zero_convs(self, pending, N, inject=None, scales=None):
+        """the 13 zero-convs: into own buffers (inject None), or accumulated as scale_i * zero_conv_i(h) straight into
+        the UNet's skip slots / middle output (makeup_diffuse.py:166 + upstream `hs.pop() + control.pop()`)."""
+        return [self._zero_conv(key, x, j, N, h, w, inject, scales) for key, x, j, h, w in pending]
+
+    def run(self, x_nhwc, guided_hint, t, ctx_kv, N, H, W, inject=None, scales=None):
+        return self.zero_convs(self.run_trunk(x_nhwc, guided_hint, t, ctx_kv, N, H, W), N, inject, scales)
 
     def _zero_conv(self, key, x, j, N, h, w, inject, scales):
         ch = x.shape[1]

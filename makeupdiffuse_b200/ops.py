@@ -36,6 +36,31 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+PROFILE = None  # bench.py sets this to a list to time every launch in place (CUDA events on the stream)
+
+
+def _timed(name, nbytes_fn=None):
+    """decorator: when PROFILE is on, bracket the op with CUDA events and record (name, algorithmic bytes)"""
+    def deco(fn):
+        def wrapper(*a, **kw):
+            if PROFILE is None:
+                return fn(*a, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **kw)
+            e1.record()
+            PROFILE.append({"op": name, "bytes": nbytes_fn(*a, **kw) if nbytes_fn else 0, "e0": e0, "e1": e1})
+            return r
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
+def _nb(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
 def device_ok(device: int = 0):
     L.check(L.load().mkd_device_ok(device), "device check")
 
@@ -56,6 +81,7 @@ def ddim_update(x, eps, x_prev, *, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_
             "ddim_update")
 
 
+@_timed("nchw_to_nhwc", lambda s, d: _nb(s, d))
 def nchw_to_nhwc(src, dst2d):
     N, Cc, H, W = src.shape
     if src.dtype != torch.float32 or not src.is_contiguous():
@@ -65,6 +91,7 @@ def nchw_to_nhwc(src, dst2d):
     L.check(L.load().mkd_nchw_to_nhwc(src.data_ptr(), p, _dt(dst2d), N, Cc, H, W, ld, _stream()), "nchw_to_nhwc")
 
 
+@_timed("nhwc_to_nchw", lambda s, d: _nb(s, d))
 def nhwc_to_nchw(src2d, dst):
     N, Cc, H, W = dst.shape
     if dst.dtype != torch.float32 or not dst.is_contiguous():
@@ -74,6 +101,7 @@ def nhwc_to_nchw(src2d, dst):
     L.check(L.load().mkd_nhwc_to_nchw(p, dst.data_ptr(), _dt(src2d), N, Cc, H, W, ld, _stream()), "nhwc_to_nchw")
 
 
+@_timed("timestep_embedding", None)
 def timestep_embedding(t, out, max_period=10000.0):
     assert t.dtype == torch.int64 and t.is_contiguous() and out.is_contiguous()
     B, dim = out.shape
@@ -81,11 +109,13 @@ def timestep_embedding(t, out, max_period=10000.0):
             "timestep_embedding")
 
 
+@_timed("silu", lambda x, y: _nb(x, y))
 def silu(x, y):
     assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype
     L.check(L.load().mkd_silu(x.data_ptr(), y.data_ptr(), _dt(x), x.numel(), _stream()), "silu")
 
 
+@_timed("geglu", lambda x, y: _nb(x, y))
 def geglu(x2d, y2d):
     px, ldx = _rows(x2d)
     py, ldy = _rows(y2d)
@@ -94,6 +124,7 @@ def geglu(x2d, y2d):
     L.check(L.load().mkd_geglu(px, py, _dt(x2d), M, inner, ldx, ldy, _stream()), "geglu")
 
 
+@_timed("add", lambda a, b, y: _nb(a, b, y))
 def add(a2d, b2d, y2d):
     pa, lda = _rows(a2d)
     pb, ldb = _rows(b2d)
@@ -106,6 +137,7 @@ def groupnorm_workspace_bytes(N, groups=32) -> int:
     return int(L.load().mkd_groupnorm_workspace_bytes(N, groups))
 
 
+@_timed("groupnorm", lambda x, y, *a, **k: _nb(x, y))
 def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
     px, ldx = _rows(x2d)
     py, ldy = _rows(y2d)
@@ -116,6 +148,7 @@ def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
                                    workspace.numel() * workspace.element_size(), _stream()), "groupnorm")
 
 
+@_timed("layernorm", lambda x, y, *a, **k: _nb(x, y))
 def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
     px, ldx = _rows(x2d)
     py, ldy = _rows(y2d)
@@ -168,9 +201,6 @@ def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=
     return d
 
 
-PROFILE = None  # bench.py sets this to a list to time every conv2d launch in place (CUDA events on the stream)
-
-
 def conv2d(x2d, w, y2d, **kw):
     d = make_conv_desc(x2d, w, y2d, **kw)
     if PROFILE is None:
@@ -183,7 +213,7 @@ def conv2d(x2d, w, y2d, **kw):
     e1.record()
     Hi, Wi = (2 * d.H, 2 * d.W) if d.upsample else (d.H, d.W)
     P, Q = (Hi + 2 * d.pad - d.R) // d.stride + 1, (Wi + 2 * d.pad - d.S) // d.stride + 1
-    PROFILE.append({"path": path, "flops": 2.0 * d.N * P * Q * d.K * d.R * d.S * d.C, "M": d.N * P * Q, "K": d.K,
+    PROFILE.append({"op": "conv2d", "path": path, "flops": 2.0 * d.N * P * Q * d.K * d.R * d.S * d.C, "M": d.N * P * Q, "K": d.K,
                     "C": d.C, "R": d.R, "stride": d.stride, "up": d.upsample, "e0": e0, "e1": e1})
 
 
@@ -199,6 +229,7 @@ def run_conv_desc(d: L.ConvDesc):
     L.check(L.load().mkd_conv2d(C.byref(d), _stream()), "conv2d")
 
 
+@_timed("attention", lambda q, k, v, o, **kw: _nb(q, k, v, o))
 def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
     pq, ldq = _rows(q2d)
     pk, ldk = _rows(k2d)

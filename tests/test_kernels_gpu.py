@@ -102,7 +102,9 @@ def test_silu_geglu_add(dt):
 @pytest.mark.parametrize("N,HW,C,ld,silu,eps", [(2, 1024, 320, 320, True, 1e-5), (3, 256, 960, 960, True, 1e-5),
                                                  (2, 64, 1920, 1920, False, 1e-6), (16, 16, 2560, 2560, True, 1e-5),
                                                  (2, 1024, 320, 640, True, 1e-5), (1, 64, 64, 64, True, 1e-5),
-                                                 (5, 4096, 320, 320, False, 1e-6), (2, 100, 128, 136, True, 1e-5)])
+                                                 (5, 4096, 320, 320, False, 1e-6), (2, 100, 128, 136, True, 1e-5),
+                                                 (16, 1024, 320, 320, True, 1e-5), (16, 256, 1920, 1920, True, 1e-5),
+                                                 (16, 64, 1280, 2560, False, 1e-6), (12, 4096, 320, 320, True, 1e-5)])
 def test_groupnorm(dt, N, HW, C, ld, silu, eps):
     dt, dto = dt if isinstance(dt, tuple) else (dt, dt)  # (fp32 trunk in, bf16 operand out) is the bf16 path's common case
     buf = rnd(N * HW, ld, dt=dt, seed=1) * 1.7 + 0.4

@@ -1,0 +1,88 @@
+"""Micro-benchmark of the tcgen05 conv/GEMM kernel on the shapes that dominate one UNet+ControlNet eval.
+Back-to-back launches between two CUDA events (no host gaps), L2 kept warm or flushed (--flush)."""
+import argparse
+import math
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from makeupdiffuse_b200 import _lib as L  # noqa: E402
+from makeupdiffuse_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--only", default="")
+ap.add_argument("--flush", action="store_true")
+a = ap.parse_args()
+DEV = "cuda"
+ws = torch.empty(96 << 20, dtype=torch.uint8, device=DEV)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+
+SHAPES = {
+    # name: (N, H, W, C, K, R, epilogue)
+    "sq320_res32": (16, 32, 32, 320, 320, 1, "res32"),
+    "sq320_plain": (16, 32, 32, 320, 320, 1, "plain"),
+    "sq640_res32": (16, 16, 16, 640, 640, 1, "res32"),
+    "sq1280_res32": (16, 8, 8, 1280, 1280, 1, "res32"),
+    "sq1280_m256": (16, 4, 4, 1280, 1280, 1, "plain"),
+    "conv320": (16, 32, 32, 320, 320, 3, "emb32"),
+    "conv640": (16, 16, 16, 640, 640, 3, "emb32"),
+    "conv1280": (16, 8, 8, 1280, 1280, 3, "emb32"),
+    "conv1280_4x4": (16, 4, 4, 1280, 1280, 3, "emb32"),
+    "conv2560_4x4": (16, 4, 4, 2560, 1280, 3, "emb32"),
+    "ff1_320": (16, 32, 32, 320, 2560, 1, "geglu"),
+    "ff2_320": (16, 32, 32, 1280, 320, 1, "res32"),
+    "qkv_320": (16, 32, 32, 320, 960, 1, "plain"),
+    "big_k": (16, 32, 32, 960, 320, 3, "emb32"),
+}
+for name, (N, H, W, C, K, R, epi) in SHAPES.items():
+    if a.only and a.only not in name:
+        continue
+    M = N * H * W
+    x = torch.randn(M, C, device=DEV).bfloat16()
+    w = (torch.randn(K, R, R, C, device=DEV) / math.sqrt(C * R * R)).bfloat16()
+    bias = torch.randn(K, device=DEV)
+    kw = dict(N=N, H=H, W=W, R=R, S=R, pad=R // 2, bias=bias, workspace=ws)
+    Ko = K
+    if epi == "plain":
+        y = torch.empty(M, K, device=DEV, dtype=torch.bfloat16)
+        args = (x, w, y)
+    elif epi == "res32":
+        r = torch.randn(M, K, device=DEV)
+        args = (x, w, None)
+        kw.update(residual=r, y32=r)
+    elif epi == "emb32":
+        e = torch.randn(N, K, device=DEV).bfloat16()
+        y32 = torch.empty(M, K, device=DEV)
+        args = (x, w, None)
+        kw.update(emb=e, y32=y32)
+    elif epi == "geglu":
+        Ko = K // 2
+        y = torch.empty(M, Ko, device=DEV, dtype=torch.bfloat16)
+        args = (x, w, y)
+        kw.update(act=L.ACT_GEGLU, geglu_block=80)
+    d = ops.make_conv_desc(*args, **kw)
+    for _ in range(3):
+        ops.run_conv_desc(d)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.flush:
+        tot = 0.0
+        for _ in range(a.iters):
+            flush.zero_()
+            e0.record()
+            ops.run_conv_desc(d)
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        us = 1e3 * tot / a.iters
+    else:
+        e0.record()
+        for _ in range(a.iters):
+            ops.run_conv_desc(d)
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / a.iters
+    fl = 2.0 * M * K * C * R * R
+    print(f"{name:14s} M={M:6d} N={K:5d} K={C * R * R:6d} {epi:6s}: {us:8.1f} us  {fl / us / 1e6:8.1f} TFLOP/s", flush=True)
