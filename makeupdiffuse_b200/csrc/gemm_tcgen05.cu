@@ -52,6 +52,9 @@ struct MainP {
   int tiles_w, tiles_h;
   int m_tiles, n_tiles, num_units;  // persistent scheduler: unit -> (n_tile, m_tile, split)
   unsigned long long* trace;        // debug: per-CTA %globaltimer stamps (mkd_debug_set_trace), else nullptr
+  int half_dw, half_dh, half_dn;    // CL == 2: coordinate offset of rank 1's half of the A box (conv mode)
+  int commit_every;                 // G: smem slots are released with one tcgen05.commit per G k-blocks
+  int debug;                        // debug timing experiments (results invalid): 1 = skip B loads, 2 = skip MMA issue
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -91,17 +94,78 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
           "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// multicast: the box lands at the same CTA-relative smem offset, and completes on the same CTA-relative mbarrier,
-// in every CTA of the cluster named by `mask`
+// ---- TMA multicast (CTA pair sharing the A tile) ----------------------------------------------------------------
+// the box lands at the same CTA-relative smem offset, and completes on the same CTA-relative mbarrier, in every CTA of
+// the cluster named by `mask`
 __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;\n" ::
           "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6, %7}], [%2], %3;\n" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
+}
+// ---- cta_group::2 (CTA pair) forms: kept for reference, the pair kernel now shares A by multicast instead ------------------------------------------------------------------------------
+// Shared-window addresses carry the CTA rank in bit 24: clearing it names the same offset in the pair's leader (rank 0).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// 2-SM TMA loads: data lands in the ISSUING CTA's smem, the transaction bytes complete on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// one MMA for the pair: D[256 x N] (rows 0-127 in the leader's TMEM, 128-255 in the peer's), A 128 rows from each
+// CTA's smem, B N/2 rows from each CTA's smem (same smem offsets in both)
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// one lane of a converged warp (the loops around it stay warp-uniform, so their operands live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -157,8 +221,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BN
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int bn, int m = BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
@@ -241,15 +305,21 @@ __device__ __forceinline__ void epilogue_geglu8(const EpiP& e, int m, int row_va
 //                 phase 1  TMEM -> registers -> fp32 staging panel in smem (thread = accumulator row)
 //                 phase 2  256 threads walk the panel row-major, 8 channels each: coalesced bias / emb / residual
 //                          loads and bf16 / fp32 stores (consecutive threads -> consecutive 16 / 32 bytes)
-template <int BN> struct Cfg {
-  static constexpr int PW = (BN % 80 == 0) ? 80 : (BN >= 64 ? 64 : 32);  // staging panel width (columns)
+enum { EPI_PLAIN = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_PARTIAL = 3 };
+// Shared-memory budget: the main loop is bound by how many bytes are in flight per SM (slot round trip = TMA latency
+// under load + MMA + two barrier wake-ups ~ 1800+ cycles), so the staging panel is kept narrow (40 columns, 22 KB) and
+// every remaining byte of the 227 KB goes to pipeline stages.
+template <int BN, int CL, int EPI> struct Cfg {
+  // staging panel width (columns); GEGLU needs value + gate groups side by side (even group count)
+  static constexpr int PW = (BN % 80 == 0) ? (EPI == EPI_GEGLU ? 80 : 40) : (BN >= 64 ? 64 : 32);
   static constexpr int NP = BN / PW;
   static constexpr int LDT = PW + 4;                                      // +4 floats: conflict-free phase-1 writes
   static constexpr int STAGE_BYTES = A_BYTES + BN * BK * 2;
-  static constexpr int STAGES = (BN > 128) ? 4 : 5;
   static constexpr int STAGING_BYTES = BM * LDT * 4;
-  static constexpr int TCOLS = tmem_cols(2 * BN);                         // two accumulator buffers
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - STAGING_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(STAGES >= 3 && SMEM <= 227 * 1024, "shared memory budget");
 };
 __host__ __device__ constexpr int tmem_cols2(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -262,17 +332,17 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
                : "r"(taddr));
 }
 
-// CL = CTAs per cluster (1 or 2).  CL == 2: the pair works on two vertically adjacent M tiles of the same N tile;
-// each CTA loads its own A tile and HALF of the shared weight tile, multicast into both CTAs' shared memory, which
-// removes 28% of the L2 -> SM traffic that bounds the large convolutions (measured: 10.7 TB/s of tile loads at CL = 1).
+// CL = CTAs per cluster (1 or 2).  CL == 2: the pair works on the SAME M tile and two adjacent N tiles; each CTA
+// fetches half of the shared A tile (64 rows) and TMA-multicasts it into both CTAs' shared memory.
+// Why A: timing the main loop with the MMAs and the B loads removed still gave 216 ns per k-block = 16 KB of A per SM
+// x 148 SMs = 11.2 TB/s, the L2 -> SM bandwidth cap; B tiles are requested by many CTAs at once and dedup in L2, A
+// tiles are private to an M tile.  (Sharing B instead — by multicast or by cta_group::2 — measured no gain.)
 // EPI selects the ONE epilogue variant an instantiation carries (a single body holding all of them was ~10^4 SASS
-// instructions and instruction-fetch bound in phase 2):
-enum { EPI_PLAIN = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_PARTIAL = 3 };
+// instructions and instruction-fetch bound in phase 2).
 template <int BN, int CL, int EPI>
-__global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
+__global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
                                                               const __grid_constant__ CUtensorMap bmap, MainP mp, EpiP ep) {
-  using C = Cfg<BN>;
-  constexpr int B_HALF_BYTES = BN * BK * 2 / CL;
+  using C = Cfg<BN, CL, EPI>;
   const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
   const int cl_id = blockIdx.x / CL, cl_num = gridDim.x / CL;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, PW = C::PW, NP = C::NP, LDT = C::LDT;
@@ -289,15 +359,17 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 11 warps: 0 A-producer, 1 MMA, 2-9 epilogue, 10 B-producer
   if (threadIdx.x == 0) MKD_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&bmap)) : "memory");
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(full_bar + i, 1);
-      mbar_init(empty_bar + i, CL);  // a stage is free when the MMA warp of EVERY CTA that received it has released it
+      mbar_init(full_bar + i, 2);    // the A and the B producer warp
+      // release ring: entry q is completed by the q-th release commit (one per G k-blocks, in order); CL == 2: the
+      // peer multicasts into these slots too, so both MMA warps must release
+      mbar_init(empty_bar + i, CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full_bar + i, 1);
@@ -319,15 +391,20 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
   pdl_wait();
   if (threadIdx.x == 0) MKD_TRACE(1);
 
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int s = 0, ph = 0;       // smem stage / phase, carried across work units
+  if (warp == 0 || warp == 10) {
+    // ===== TMA producers: warp 0 streams A, warp 10 streams B.  The whole warp walks the loop (warp-uniform ->
+    // operands stay in uniform registers), one elected lane issues. =====
+    const bool do_a = warp == 0;
+    {
+      int s = 0;               // smem slot, carried across work units
+      int it = 0, rel = 0, rq = 0, rph = 0;  // global k-block counter; releases seen; ring index / phase of the next one
+      const int G = min(mp.commit_every, STAGES - 1);  // G >= STAGES would deadlock the ring
       bool first = true;
 #pragma unroll 1
       for (int unit = cl_id; unit < mp.num_units; unit += cl_num) {
-        const int n_tile = unit % mp.n_tiles, rest = unit / mp.n_tiles;
-        const int m_tile = (rest % mp.m_tiles) * CL + (int)cta_rank, split = rest / mp.m_tiles;
+        // unit -> (n group fastest, m_tile, split); a CL == 2 pair shares m_tile and takes n tiles 2*ng, 2*ng + 1
+        const int n_tile = (unit % mp.n_tiles) * CL + (int)cta_rank, rest = unit / mp.n_tiles;
+        const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
         const int kb0 = split * mp.kb_per_split, kb1 = min(mp.kblocks, kb0 + mp.kb_per_split);
         int w0 = 0, h0 = 0, n0 = 0;
         if (mp.conv) {
@@ -335,26 +412,52 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
           w0 = tw * mp.Wb;
           h0 = th * mp.Hb;
           n0 = tn * mp.Nb;
+          if (CL == 2 && cta_rank == 1) {  // this CTA fetches (and multicasts) the second half of the A box
+            w0 += mp.half_dw;
+            h0 += mp.half_dh;
+            n0 += mp.half_dn;
+          }
         }
-        // filter-tap walk (r, sx, cb) kept incrementally: this one thread feeds a 320-cycle MMA per k-block, so the
-        // loop body must stay a handful of instructions (no integer divisions)
+        const int m0 = m_tile * BM + (CL == 2 ? (int)cta_rank * (BM / 2) : 0);
+        // filter-tap walk (r, sx, cb) kept incrementally: no integer divisions in the k loop
         const int tap0 = kb0 / mp.cblocks;
         int cb = kb0 - tap0 * mp.cblocks, r = tap0 / mp.S;
         int sx = tap0 - r * mp.S;
-        const int nb = n_tile * BN + (int)cta_rank * (BN / CL);
+        const int nb = n_tile * BN;
 #pragma unroll 1
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar + s, ph ^ 1);
-          mbar_expect_tx(full_bar + s, STAGE_BYTES);
-          unsigned char* sa = smem + s * STAGE_BYTES;
-          if (mp.conv) tma_load_4d(&amap, full_bar + s, sa, cb * BK, w0 + sx - mp.pad, h0 + r - mp.pad, n0);
-          else tma_load_2d(&amap, full_bar + s, sa, kb * BK, m_tile * BM);
-          if (CL == 1) tma_load_2d(&bmap, full_bar + s, sa + A_BYTES, kb * BK, nb);
-          else tma_load_2d_mc(&bmap, full_bar + s, sa + A_BYTES + cta_rank * B_HALF_BYTES, kb * BK, nb, (uint16_t)((1u << CL) - 1));
-          if (first) {
-            MKD_TRACE(2);
-            first = false;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          // slot s was last used by k-block it - STAGES; k-blocks [0, rel * G) have been released by the MMA warp
+          while (it - STAGES >= rel * G) {
+            mbar_wait(empty_bar + rq, rph);
+            ++rel;
+            if (++rq == STAGES) {
+              rq = 0;
+              rph ^= 1;
+            }
           }
+          unsigned char* sa = smem + s * STAGE_BYTES;
+          if (elect_one()) {
+            if (do_a) {
+              mbar_expect_tx(full_bar + s, A_BYTES);  // CL == 2: my half + the peer's half both land here
+              if (CL == 1) {
+                if (mp.conv) tma_load_4d(&amap, full_bar + s, sa, cb * BK, w0 + sx - mp.pad, h0 + r - mp.pad, n0);
+                else tma_load_2d(&amap, full_bar + s, sa, kb * BK, m0);
+              } else {
+                unsigned char* dst = sa + cta_rank * (A_BYTES / 2);
+                if (mp.conv) tma_load_4d_mc(&amap, full_bar + s, dst, cb * BK, w0 + sx - mp.pad, h0 + r - mp.pad, n0, (uint16_t)3);
+                else tma_load_2d_mc(&amap, full_bar + s, dst, kb * BK, m0, (uint16_t)3);
+              }
+              if (first) MKD_TRACE(2);
+            } else {
+              if (mp.debug & 1) mbar_arrive(full_bar + s);
+              else {
+                mbar_expect_tx(full_bar + s, STAGE_BYTES - A_BYTES);
+                tma_load_2d(&bmap, full_bar + s, sa + A_BYTES, kb * BK, nb);
+              }
+            }
+          }
+          __syncwarp();
+          first = false;
           if (++cb == mp.cblocks) {
             cb = 0;
             if (++sx == mp.S) {
@@ -362,18 +465,17 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
               ++r;
             }
           }
-          if (++s == STAGES) {
-            s = 0;
-            ph ^= 1;
-          }
+          if (++s == STAGES) s = 0;
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+    // ===== MMA issuer; warp-uniform loop, one elected lane issues =====
+    {
+      constexpr uint32_t idesc = make_idesc(BN, BM);
       int s = 0, ph = 0, j = 0;
+      int g = 0, cq = 0;  // k-blocks since the last release commit; ring index of the next one
+      const int G = min(mp.commit_every, STAGES - 1);
       bool first = true;
 #pragma unroll 1
       for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
@@ -386,31 +488,43 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll 1
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar + s, ph);
-          if (first) {
-            MKD_TRACE(3);
-            first = false;
-          }
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+          const bool release = ++g == G;  // tcgen05.commit -> mbarrier sustains only ~1 per 200 ns: release G slots at once
+          if (release) g = 0;
+          if (elect_one()) {
+            if (first) MKD_TRACE(3);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance K inside the 128-byte swizzle atom: +32 bytes per UMMA_K (encoded >> 4)
-            umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > kb0 || k) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (mp.debug & 2) break;
+              // advance K inside the 128-byte swizzle atom: +32 bytes per UMMA_K (encoded >> 4)
+              umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > kb0 || k) ? 1u : 0u);
+            }
+            // frees the last G smem slots once the MMAs issued so far retire (they retire in order);
+            // CL == 2: in both CTAs — each multicasts into the other
+            if (release) {
+              if (CL == 1) tcgen05_commit(empty_bar + cq);
+              else tcgen05_commit_mc(empty_bar + cq, (uint16_t)3);
+            }
           }
-          // frees this smem stage (in every CTA that multicasts into it) once the MMAs above retire
-          if (CL == 1) tcgen05_commit(empty_bar + s);
-          else tcgen05_commit_mc(empty_bar + s, (uint16_t)((1u << CL) - 1));
+          __syncwarp();
+          if (release && ++cq == STAGES) cq = 0;
+          first = false;
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        tcgen05_commit(tmem_full_bar + ab);  // accumulator of this unit complete
-        if (j == 0) MKD_TRACE(4);
+        // accumulator of this unit complete (CL == 2: tell both CTAs' epilogue warps)
+        if (elect_one()) {
+          tcgen05_commit(tmem_full_bar + ab);
+          if (j == 0) MKD_TRACE(4);
+        }
+        __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4 =====
     // Phase-2 work split: thread -> ONE 8-channel column group g (so its bias vector is loaded once per panel) and
     // rows rr, rr + RPI, ... of the tile.  Consecutive threads own consecutive groups of the same row: every global
@@ -424,8 +538,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     const bool p2_active = et < RPI * NG;
     int j = 0;
     for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
-      const int n_tile = unit % mp.n_tiles, rest = unit / mp.n_tiles;
-      const int m_tile = (rest % mp.m_tiles) * CL + (int)cta_rank, split = rest / mp.m_tiles;
+      const int n_tile = (unit % mp.n_tiles) * CL + (int)cta_rank, rest = unit / mp.n_tiles;
+      const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
       const int ab = j & 1, use = j >> 1;
       const int m_base = m_tile * BM;
       constexpr bool geglu = EPI == EPI_GEGLU;
@@ -760,11 +874,11 @@ int pick_bn(const mkd_conv_desc* d) {
 }
 
 unsigned long long* g_trace = nullptr;
-int cluster_pref() {  // MKD_CLUSTER=2 enables the 2-CTA multicast pairs (BN = 160 shapes)
+int cluster_pref() {  // MKD_CLUSTER=2 selects the A-multicast CTA-pair kernel for BN = 160 (measured ~2 % slower: opt-in)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MKD_CLUSTER");
-    v = (e && atoi(e) >= 1 && atoi(e) <= 2) ? atoi(e) : 1;  // multicast pairs measured neutral on B200: opt-in
+    v = (e && atoi(e) >= 1 && atoi(e) <= 2) ? atoi(e) : 1;
   }
   return v;
 }
@@ -795,36 +909,43 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     if (down) { dd.C = 9 * d_in->C; dd.R = dd.S = 1; dd.pad = 0; dd.N = 1; dd.H = 1; dd.W = g.M; dd.ldx = dd.C; }
     else { dd.H = g.P; dd.W = g.Q; dd.ldx = d_in->C; }
   }
-  constexpr size_t smem = Cfg<BN>::SMEM;
-  static_assert(smem <= 227 * 1024, "shared memory budget");
+  constexpr int EG = (BN == 160 ? EPI_GEGLU : EPI_PLAIN);
+  const KernelFn all[4] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
+                           gemm_tcgen05_kernel<BN, CL, EG>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>};
+  const size_t smems[4] = {Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_SILU>::SMEM, Cfg<BN, CL, EG>::SMEM,
+                           Cfg<BN, CL, EPI_PARTIAL>::SMEM};
   static bool configured = false;
   if (!configured) {
-    KernelFn all[4] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
-                       gemm_tcgen05_kernel<BN, CL, (BN == 160 ? EPI_GEGLU : EPI_PLAIN)>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>};
-    for (KernelFn f : all) {
-      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "gemm_tcgen05: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    for (int i = 0; i < 4; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems[i]);
+      MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "gemm_tcgen05: cudaFuncSetAttribute(%zu): %s", smems[i], cudaGetErrorString(e));
     }
     configured = true;
   }
   CUtensorMap amap, bmap;
   int rc;
+  int half_dw = 0, half_dh = 0, half_dn = 0;
   if (g.conv) {
     cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t str[3] = {(cuuint64_t)d->ldx * 2, (cuuint64_t)d->ldx * 2 * d->W, (cuuint64_t)d->ldx * 2 * d->W * d->H};
     cuuint32_t box[4] = {BK, (cuuint32_t)g.Wb, (cuuint32_t)g.Hb, (cuuint32_t)g.Nb};
+    if (CL == 2) {  // each CTA of the pair fetches half of the 128-pixel box: split its outermost non-trivial dimension
+      if (g.Nb >= 2) { box[3] = g.Nb / 2; half_dn = g.Nb / 2; }
+      else if (g.Hb >= 2) { box[2] = g.Hb / 2; half_dh = g.Hb / 2; }
+      else { box[1] = g.Wb / 2; half_dw = g.Wb / 2; }
+    }
     rc = encode(&amap, d->x, 4, dims, str, box);
   } else {
     cuuint64_t dims[2] = {(cuuint64_t)d->C, (cuuint64_t)g.M};
     cuuint64_t str[1] = {(cuuint64_t)d->ldx * 2};
-    cuuint32_t box[2] = {BK, BM};
+    cuuint32_t box[2] = {BK, BM / CL};
     rc = encode(&amap, d->x, 2, dims, str, box);
   }
   if (rc) return rc;
   {
     cuuint64_t dims[2] = {(cuuint64_t)g.Ktot, (cuuint64_t)d->K};
     cuuint64_t str[1] = {(cuuint64_t)g.Ktot * 2};
-    cuuint32_t box[2] = {BK, BN / CL};  // CL == 2: each CTA of the pair fetches (and multicasts) half of the tile
+    cuuint32_t box[2] = {BK, BN};
     rc = encode(&bmap, d->w, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -840,8 +961,8 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   // split-K: only when the tile grid leaves more than half of the SMs idle AND K is deep enough that the fp32
   // partial round trip (2 * splits * M * N * 4 bytes) is cheaper than the idle tensor cores
   int splits = 1;
-  const int m_groups = (g.m_tiles + CL - 1) / CL;  // M tiles per cluster row
-  const int tiles = m_groups * CL * n_tiles;
+  const int n_groups = (n_tiles + CL - 1) / CL;  // N tiles per cluster (a pair takes two adjacent N tiles)
+  const int tiles = g.m_tiles * n_groups * CL;
   if (d->workspace && tiles <= 74 && mp.kblocks >= 32 && d->K % 16 == 0) {
     splits = 148 / tiles;
     if (splits > mp.kblocks / 16) splits = mp.kblocks / 16;  // >= 16 K blocks (1024 of K) per split
@@ -861,17 +982,31 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   ep.y32 = d->y32; ep.ldy32 = d->ldy32; ep.res_f32 = d->residual_dtype == MKD_F32;
   ep.partial = splits > 1 ? (float*)d->workspace : nullptr;
 
-  mp.m_tiles = m_groups;
-  mp.n_tiles = n_tiles;
+  mp.m_tiles = g.m_tiles;
+  mp.n_tiles = n_groups;
+  mp.half_dw = half_dw; mp.half_dh = half_dh; mp.half_dn = half_dn;
   mp.trace = g_trace;
-  mp.num_units = m_groups * n_tiles * splits;  // cluster-level work units
+  {
+    static int ge = -1;  // MKD_COMMIT_EVERY overrides the release granularity (experiments)
+    if (ge < 0) {
+      const char* e = getenv("MKD_COMMIT_EVERY");
+      ge = e ? atoi(e) : 0;
+    }
+    mp.commit_every = ge > 0 ? ge : 1;  // measured: G = 1, 2, 3 give identical k-block times
+  }
+  {
+    const char* e = g_trace ? getenv("MKD_DEBUG") : nullptr;  // only honoured together with the trace hook
+    mp.debug = e ? atoi(e) : 0;
+  }
+  mp.num_units = g.m_tiles * n_groups * splits;  // cluster-level work units
   const int max_clusters = num_sms() / CL;
   const int grid = CL * (mp.num_units < max_clusters ? mp.num_units : max_clusters);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(320);
-    cfg.dynamicSmemBytes = smem;
+    cfg.blockDim = dim3(352);
+    const int variant = ep.partial ? 3 : (ep.act == MKD_ACT_GEGLU ? 2 : (ep.act == MKD_ACT_SILU ? 1 : 0));
+    cfg.dynamicSmemBytes = smems[variant];
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -882,11 +1017,7 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CL > 1 ? 2 : 1;
-    KernelFn fn = gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>;
-    if (ep.partial) fn = gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>;
-    else if (ep.act == MKD_ACT_GEGLU) fn = gemm_tcgen05_kernel<BN, CL, (BN == 160 ? EPI_GEGLU : EPI_PLAIN)>;
-    else if (ep.act == MKD_ACT_SILU) fn = gemm_tcgen05_kernel<BN, CL, EPI_SILU>;
-    MKD_LAUNCH_OK(cudaLaunchKernelEx(&cfg, fn, amap, bmap, mp, ep));
+    MKD_LAUNCH_OK(cudaLaunchKernelEx(&cfg, all[variant], amap, bmap, mp, ep));
   }
   MKD_CHECK_LAUNCH();
   if (splits > 1) {
@@ -912,7 +1043,7 @@ bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
 int conv2d_tcgen05(const mkd_conv_desc* d, cudaStream_t stream) {
   Geometry g;
   MKD_REQUIRE(geometry(d, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
-  const int cl = (g.m_tiles >= 2) ? cluster_pref() : 1;  // a pair needs two M tiles to share a weight tile
+  const int cl = (d->K > 160) ? cluster_pref() : 1;  // a pair needs two N tiles to share an A tile
   switch (pick_bn(d)) {
     case 160: return (cl == 2) ? launch<160, 2>(d, g, stream) : launch<160, 1>(d, g, stream);
     case 80: return launch<80, 1>(d, g, stream);

@@ -15,8 +15,12 @@ DEV = "cuda"
 NAMES = ["entry", "prologue", "tma0 issued", "full0", "mma u0 done", "acc0 ready", "epi u0 done", "epi last done", "exit",
          "p0 bar1", "p0 tmem ld", "p0 staged", "p0 phase2", "p1 staged"]
 ORDER = [0, 1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 6, 7, 8]
-for name, (N, H, W, C, K, R) in {"sq320": (16, 32, 32, 320, 320, 1), "conv320": (16, 32, 32, 320, 320, 3),
-                                 "tiny": (1, 1, 128, 64, 160, 1), "sq1280_m256": (16, 4, 4, 1280, 1280, 1)}.items():
+SHAPES = {"sq320": (16, 32, 32, 320, 320, 1), "conv320": (16, 32, 32, 320, 320, 3),
+          "tiny": (1, 1, 128, 64, 160, 1), "sq1280_m256": (16, 4, 4, 1280, 1280, 1)}
+if len(sys.argv) > 1 and sys.argv[1] == "nsweep":  # same A, K = 2880; N-tile = 160 / 80 / 64 / 32 (BN picked from N)
+    SHAPES = {"N320_bn160": (16, 32, 32, 320, 320, 3), "N240_bn80": (16, 32, 32, 320, 240, 3),
+              "N256_bn64": (16, 32, 32, 320, 256, 3), "N32_bn32": (16, 32, 32, 320, 32, 3)}
+for name, (N, H, W, C, K, R) in SHAPES.items():
     M = N * H * W
     x = torch.randn(M, C, device=DEV).bfloat16()
     w = (torch.randn(K, R, R, C, device=DEV) / math.sqrt(C * R * R)).bfloat16()
@@ -36,6 +40,9 @@ for name, (N, H, W, C, K, R) in {"sq320": (16, 32, 32, 320, 320, 1), "conv320": 
     t = tr.cpu().reshape(148, 16)[:, :14]
     used = t[:, 0] > 0
     t0 = int(t[used, 0].min())
+    kbl = C * R * R // 64
+    mm = t[used][:, 4].double() - t[used][:, 3].double()
+    print(f"== {name}: k-blocks/unit {kbl}, main loop of unit 0: median {float(mm.median()) / 1e3:.2f} us -> {float(mm.median()) / kbl:.0f} ns per k-block")
     print(f"== {name}: event time {1e3 * e0.elapsed_time(e1):.1f} us, CTAs {int(used.sum())}; times in us since first CTA entry")
     for slot in ORDER:
         nm = NAMES[slot]
