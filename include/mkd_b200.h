@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 2
+#define MKD_ABI_VERSION 3
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 
@@ -86,6 +86,13 @@ int mkd_groupnorm(const void* x, void* y, int x_dtype, int y_dtype, int N, int H
                   int ldy, const float* gamma, const float* beta, float eps, int silu, void* workspace,
                   size_t workspace_bytes, mkd_stream_t stream);
 
+/* GroupNorm as ONE streaming pass, for inputs whose producer (mkd_conv2d with `stats`) already emitted per-tile
+ * column sums: stats[((n * tiles_per_sample + t) * stats_ld + c) * 2 + {0,1}], HW == 128 * tiles_per_sample.
+ * Same arithmetic as mkd_groupnorm otherwise (fp32 statistics, var = E[x^2] - mean^2 clamped at 0). */
+int mkd_groupnorm_apply(const void* x, void* y, int x_dtype, int y_dtype, int N, int HW, int C, int groups, int ldx,
+                        int ldy, const float* gamma, const float* beta, float eps, int silu, const float* stats,
+                        int stats_ld, int tiles_per_sample, mkd_stream_t stream);
+
 /* ---- LayerNorm over the last dim (BasicTransformerBlock.norm1/2/3) ---------------------------------------- */
 int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,
                   const float* gamma, const float* beta, float eps, mkd_stream_t stream);
@@ -130,6 +137,12 @@ typedef struct mkd_conv_desc {
   float* y32;         /* optional fp32 copy of the output (same values before rounding); `y` may then be NULL */
   void* workspace; /* split-K partials (tcgen05 path); may be NULL -> no split-K */
   size_t workspace_bytes;
+  /* optional GroupNorm statistics of the output, fused into the tcgen05 epilogue (act must be NONE, K % 8 == 0):
+   * stats[(t * stats_ld + k) * 2 + {0, 1}] = (sum, sum of squares) over rows [128 t, 128 t + 128) of the values
+   * stored for output channel k.  The consumer is mkd_groupnorm_apply.  `stats` may point into a wider statistics
+   * row (stats_ld > K) the same way `y` may point into a concat buffer.  Not available on the generic path. */
+  float* stats;
+  int stats_ld;
 } mkd_conv_desc;
 
 int mkd_conv2d(const mkd_conv_desc* d, mkd_stream_t stream);

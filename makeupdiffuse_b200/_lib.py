@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmkd_b200.so")
 MKD_BF16, MKD_F32 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ConvDesc(C.Structure):
@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
         ("bias", C.c_void_p), ("emb", C.c_void_p), ("residual", C.c_void_p),
         ("residual_dtype", C.c_int), ("ldy32", C.c_int), ("y32", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("stats", C.c_void_p), ("stats_ld", C.c_int),
     ]
 
 
@@ -53,6 +54,7 @@ PROTOTYPES = {
     "mkd_add": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp]),
     "mkd_groupnorm_workspace_bytes": (_sz, [_i, _i]),
     "mkd_groupnorm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _sz, _vp]),
+    "mkd_groupnorm_apply": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _i, _vp]),
     "mkd_layernorm": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _vp, _vp, _f, _vp]),
     "mkd_conv2d": (_i, [C.POINTER(ConvDesc), _vp]),
     "mkd_conv2d_path": (_i, [C.POINTER(ConvDesc)]),

@@ -5,6 +5,8 @@
 //                        double-buffered cp.async smem ring in tiles of 64 keys, QK^T and PV on the warp-level
 //                        tensor-core path (mma.sync m16n8k16, fp32 accumulate), online softmax in registers.
 //   attn_simt_kernel<T>  one warp per query, used by the fp32 check mode (and any head dim the mma kernel lacks).
+#include <stdlib.h>
+
 #include "common.cuh"
 using namespace mkd;
 
@@ -265,6 +267,14 @@ int launch_mma(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int 
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
+bool attn_force_mma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MKD_ATTN");
+    v = (e && e[0] == 'm') ? 1 : 0;
+  }
+  return v == 1;
+}
 }  // namespace
 
 extern "C" int mkd_attention(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads, int Nq,
@@ -279,6 +289,10 @@ extern "C" int mkd_attention(const void* q, const void* k, const void* v, void* 
   if (dtype == MKD_BF16) {
     const bf16 *qq = (const bf16*)q, *kk = (const bf16*)k, *vv = (const bf16*)v;
     bf16* oo = (bf16*)o;
+    // production path: tcgen05 / TMEM / TMA flash attention (attention_tcgen05.cu); MKD_ATTN=mma selects the older
+    // warp-level mma.sync kernel below (kept for A/B measurements)
+    if (attention_tcgen05_supported(d, ldq, ldk, ldv) && !attn_force_mma())
+      return attention_tcgen05(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
     if (d <= 16) return launch_mma<16>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
     if (d <= 32) return launch_mma<32>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
     if (d <= 48) return launch_mma<48>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);

@@ -1,0 +1,360 @@
+// SpatialTransformer attention on the 5th-generation tensor cores (sm_100a): flash-style, S = Q K^T and O += P V are
+// tcgen05.mma with TMEM accumulators, Q / K / V tiles arrive by TMA, the Nq x Nkv score matrix never leaves the SM.
+// (upstream CrossAttention: sim = q k^T * d^-1/2 -> softmax in fp32 -> @ v; self: Nkv = Nq = H*W, cross: Nkv = 77.)
+//
+//   CTA = one (batch, head) x NWG * 128 queries.  Warps:
+//     0 .. 4*NWG-1   softmax warpgroups: thread = one query row = one TMEM lane, so no cross-thread reduction exists.
+//                    Per 128-key tile: pull the S row out of TMEM into registers (which frees the S buffer at once),
+//                    row max, p = exp2(..) -> bf16 into a 128B-swizzled K-major smem tile (the A operand of the PV MMA),
+//                    fp32 row sum.  O accumulates in TMEM across the key tiles; the flash rescale of O is LAZY: the
+//                    running max is only raised when it grew by more than 2^8 (p <= 256 is harmless in bf16 / fp32,
+//                    the final O / l is the same number), so the TMEM read-modify-write of O is rare.
+//     4*NWG          TMA producer (one lane): Q once, then a K ring and a V ring.
+//     4*NWG + 1      MMA issuer (one lane; owns the 512 TMEM columns): S_wg(t+1) = Q K(t+1)^T is issued as soon as
+//                    warpgroup wg has S_wg(t) in registers, so the tensor pipe runs a tile ahead of the exp2 phase;
+//                    PV_wg(t) follows when P_wg(t) is published.
+//   Operands: Q, K tiles are [128 rows][64 channels] boxes per 64-channel chunk, K-major for the QK^T MMA; the V tile is
+//   the same box read as an MN-major B operand (N = head dim), so no transpose pass exists.  Head dims that are not a
+//   multiple of 64 rely on the tensor map: dim 0 of the map is the head dim itself, so the rest of the 64-wide box is
+//   zero-filled by the TMA unit (zeros add nothing to QK^T and give zero O columns that are never stored).
+//   Keys beyond Nkv in the last tile are zero-filled the same way and masked to -inf before the softmax.
+#include <cuda.h>
+
+#include "tcgen05.cuh"
+using namespace mkd;
+using namespace mkd::tc;
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128;
+constexpr int CH = 128 * 128;  // bytes of one [128 rows][64 bf16] chunk
+
+template <int DN> struct ACfg {
+  static constexpr int DCH = (DN + 63) / 64;                 // 64-channel chunks of the head dim
+  static constexpr int NWG = DCH <= 2 ? 2 : 1;               // softmax warpgroups (query tiles) per CTA
+  static constexpr int ST = DCH == 1 ? 2 : 1;                // K / V ring depth
+  static constexpr int OSTR = (DN + 31) / 32 * 32;           // TMEM column stride between the O accumulators
+  static constexpr int THREADS = 32 * (4 * NWG + 2);
+  static constexpr int NBAR = 5 * NWG + 4 * ST;              // q_full, s_full, s_free, p_full, o_full | k/v full/empty
+  static constexpr size_t SMEM = (size_t)(NWG * DCH + 2 * ST * DCH + 2 * NWG) * CH + NBAR * 8 + 16 + 1024;
+  static_assert(NWG * 128 + NWG * OSTR <= 512, "TMEM columns");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+
+template <int DN>
+__global__ void __launch_bounds__(ACfg<DN>::THREADS, 1)
+    attn_tcgen05_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                        const __grid_constant__ CUtensorMap vmap, bf16* __restrict__ o, int Nq, int Nkv, int d, int ldo,
+                        float sl2) {
+  using C = ACfg<DN>;
+  constexpr int DCH = C::DCH, NWG = C::NWG, ST = C::ST;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* Qs = smem;                         // [NWG][DCH] chunks
+  unsigned char* Ks = Qs + NWG * DCH * CH;          // [ST][DCH]
+  unsigned char* Vs = Ks + ST * DCH * CH;           // [ST][DCH]
+  unsigned char* Ps = Vs + ST * DCH * CH;           // [NWG][2]  (128 queries x 128 keys bf16)
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(Ps + NWG * 2 * CH);
+  uint64_t* s_full = q_full + NWG;
+  uint64_t* s_free = s_full + NWG;
+  uint64_t* p_full = s_free + NWG;
+  uint64_t* o_full = p_full + NWG;
+  uint64_t* k_full = o_full + NWG;
+  uint64_t* k_empty = k_full + ST;
+  uint64_t* v_full = k_empty + ST;
+  uint64_t* v_empty = v_full + ST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + ST);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_PROD = 4 * NWG, W_MMA = 4 * NWG + 1;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (BQ * NWG);
+  const int T = (Nkv + BKV - 1) / BKV;
+  const int nwg = (NWG == 2 && q0 + BQ < Nq) ? 2 : 1;  // warpgroups with at least one real query
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&qmap);
+    prefetch_tensormap(&kmap);
+    prefetch_tensormap(&vmap);
+    for (int i = 0; i < NWG; ++i) {
+      mbar_init(q_full + i, 1);
+      mbar_init(s_full + i, 1);
+      mbar_init(s_free + i, 4);  // one arrival per softmax warp
+      mbar_init(p_full + i, 4);
+      mbar_init(o_full + i, 1);
+    }
+    for (int i = 0; i < ST; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(k_empty + i, 1);
+      mbar_init(v_full + i, 1);
+      mbar_init(v_empty + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  if (warp == W_PROD) {
+    if (lane == 0) {
+      for (int wg = 0; wg < nwg; ++wg) {
+        mbar_expect_tx(q_full + wg, DCH * CH);
+        for (int c = 0; c < DCH; ++c) tma_load_4d(&qmap, q_full + wg, Qs + (wg * DCH + c) * CH, c * 64, h, q0 + wg * BQ, b);
+      }
+      for (int t = 0; t < T; ++t) {
+        const int st = t % ST, u = t / ST;
+        if (t >= ST) mbar_wait(k_empty + st, (u - 1) & 1);
+        mbar_expect_tx(k_full + st, DCH * CH);
+        for (int c = 0; c < DCH; ++c) tma_load_4d(&kmap, k_full + st, Ks + (st * DCH + c) * CH, c * 64, h, t * BKV, b);
+        if (t >= ST) mbar_wait(v_empty + st, (u - 1) & 1);
+        mbar_expect_tx(v_full + st, DCH * CH);
+        for (int c = 0; c < DCH; ++c) tma_load_4d(&vmap, v_full + st, Vs + (st * DCH + c) * CH, c * 64, h, t * BKV, b);
+      }
+    }
+  } else if (warp == W_MMA) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = idesc_bf16(BQ, BKV, false);
+      constexpr uint32_t idesc_o = idesc_bf16(BQ, DN, true);
+      const int ksteps = (d + 15) >> 4;  // 16-channel steps of the QK^T contraction (zero-filled beyond d)
+      auto issue_s = [&](int wg, int st) {
+        const uint32_t a = smem_u32(Qs + wg * DCH * CH), bk = smem_u32(Ks + st * DCH * CH);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * CH + (uint32_t)(ks & 3) * 32;
+          mma_bf16_ss(tmem_base + (uint32_t)(wg * BKV), smem_desc_sw128(a + off), smem_desc_sw128(bk + off), idesc_s, ks > 0);
+        }
+      };
+      auto issue_pv = [&](int wg, int st, int kvalid, bool accumulate) {
+        const uint32_t a = smem_u32(Ps + wg * 2 * CH), bv = smem_u32(Vs + st * DCH * CH);
+        const int steps = (min(kvalid, BKV) + 15) >> 4;  // keys beyond Nkv carry P = 0: skip whole 16-key steps
+        for (int kk = 0; kk < steps; ++kk) {
+          const uint32_t aoff = (uint32_t)(kk >> 2) * CH + (uint32_t)(kk & 3) * 32;
+          mma_bf16_ss(tmem_base + (uint32_t)(NWG * BKV + wg * C::OSTR), smem_desc_sw128(a + aoff),
+                      smem_desc_sw128(bv + (uint32_t)kk * 2048, CH), idesc_o, accumulate || kk > 0);
+        }
+      };
+      for (int wg = 0; wg < nwg; ++wg) mbar_wait(q_full + wg, 0);
+      mbar_wait(k_full + 0, 0);
+      fence_after();
+      for (int wg = 0; wg < nwg; ++wg) {
+        issue_s(wg, 0);
+        commit(s_full + wg);
+      }
+      commit(k_empty + 0);
+      for (int t = 0; t < T; ++t) {
+        const int st = t % ST;
+        if (t + 1 < T) {  // S(t+1) as soon as the warpgroup holds S(t) in registers
+          const int st1 = (t + 1) % ST;
+          mbar_wait(k_full + st1, ((t + 1) / ST) & 1);
+          for (int wg = 0; wg < nwg; ++wg) {
+            mbar_wait(s_free + wg, t & 1);
+            fence_after();
+            issue_s(wg, st1);
+            commit(s_full + wg);
+          }
+          commit(k_empty + st1);
+        }
+        mbar_wait(v_full + st, (t / ST) & 1);
+        for (int wg = 0; wg < nwg; ++wg) {
+          mbar_wait(p_full + wg, t & 1);  // P_wg(t) is in smem and any rescale of O_wg is done
+          fence_after();
+          issue_pv(wg, st, Nkv - t * BKV, t > 0);
+          commit(o_full + wg);
+        }
+        commit(v_empty + st);
+      }
+    }
+  } else if ((warp >> 2) < nwg) {
+    // ===== softmax warpgroup: thread = query row =====
+    const int wg = warp >> 2, row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + (uint32_t)(wg * BKV);
+    const uint32_t tO = tmem_base + lane_base + (uint32_t)(NWG * BKV + wg * C::OSTR);
+    unsigned char* Pw = Ps + wg * 2 * CH + row * 128;
+    const uint32_t swz = (uint32_t)(row & 7);
+    float m_used = -INFINITY, l = 0.f;  // running (lazily raised) row max, row sum of p
+
+    for (int t = 0; t < T; ++t) {
+      mbar_wait(s_full + wg, t & 1);
+      fence_after();
+      const int kvalid = Nkv - t * BKV;  // < 128 only in the last tile
+      uint32_t v[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32_nowait(tS + c * 32, v[c]);
+      tmem_ld_wait();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free + wg);  // the S buffer may be overwritten by Q K(t+1)^T now
+      if (kvalid < BKV) {  // keys beyond Nkv (zero-filled K rows): -inf -> p = 0
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c][i] = (c * 32 + i >= kvalid) ? 0xff800000u : v[c][i];
+        }
+      }
+      // ---- row max (8 independent chains) ----
+      float mx8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx8[i] = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[c][i]));
+      }
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      if (t > 0) {  // PV(t-1) has retired: O(t-1) is complete and the P tile may be rewritten
+        mbar_wait(o_full + wg, (t - 1) & 1);
+        fence_after();
+      }
+      // ---- lazy rescale: raise the running max only when it grew by more than 2^8 (warp-uniform decision, the
+      //      TMEM accesses below are warp-collective) ----
+      if (__any_sync(0xffffffffu, (mx - m_used) * sl2 > 8.0f)) {
+        const float m_new = fmaxf(m_used, mx);
+        const float corr = ex2((m_used - m_new) * sl2);  // first tile: ex2(-inf) = 0
+        l *= corr;
+        m_used = m_new;
+        if (t > 0) {
+#pragma unroll
+          for (int g = 0; g < DN / 16; ++g) {
+            uint32_t r[16];
+            tmem_ld16_nowait(tO + g * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+            tmem_st16(tO + g * 16, r);
+          }
+          tmem_st_wait();
+        }
+      }
+      // ---- p = exp2((s - max) * scale * log2 e) -> bf16 -> swizzled smem; fp32 row sum (4 chains) ----
+      const float mb = m_used * sl2;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(v[c][i]), sl2, -mb));
+          const float p1 = ex2(fmaf(__uint_as_float(v[c][i + 1]), sl2, -mb));
+          sum4[(i >> 1) & 3] += p0 + p1;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint32_t u = (uint32_t)(c * 4 + jj);  // 16-byte unit (8 keys) of the 128-key row
+          unsigned char* dst = Pw + (u >> 3) * CH + (((u & 7) ^ swz) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+        }
+      }
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      fence_before();            // TMEM accesses above ordered before the MMA warp's PV(t)
+      fence_proxy_async_smem();  // P visible to the tensor core's operand fetch
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + wg);
+    }
+    mbar_wait(o_full + wg, (T - 1) & 1);
+    fence_after();
+    const int q = q0 + wg * BQ + row;
+    const float inv = 1.0f / l;
+    bf16* dst = o + ((int64_t)b * Nq + q) * ldo + h * d;
+#pragma unroll
+    for (int g = 0; g < DN / 16; ++g) {
+      uint32_t r[16];
+      tmem_ld16_nowait(tO + g * 16, r);  // warp-collective: every lane loads, only real rows / channels store
+      tmem_ld_wait();
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        if (q < Nq && g * 16 + hlf * 8 < d) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[hlf * 8 + i]) * inv;
+          store8(dst + g * 16 + hlf * 8, f);
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+// (head dim, heads, tokens, batch) view of a [batch * tokens, ld] matrix whose head h occupies columns [h*d, (h+1)*d)
+int head_map(CUtensorMap* map, const bf16* base, int d, int heads, int ntok, int B, int ld) {
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)ntok, (cuuint64_t)B};
+  cuuint64_t str[3] = {(cuuint64_t)d * 2, (cuuint64_t)ld * 2, (cuuint64_t)ntok * ld * 2};
+  cuuint32_t box[4] = {64, 1, 128, 1};
+  return tma_encode_bf16(map, base, 4, dims, str, box);
+}
+
+template <int DN>
+int launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d, int ldq, int ldk,
+           int ldv, int ldo, float scale, cudaStream_t st) {
+  using C = ACfg<DN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_kernel<DN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "attention_tcgen05: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  CUtensorMap qm, km, vm;
+  int rc;
+  if ((rc = head_map(&qm, q, d, heads, Nq, B, ldq))) return rc;
+  if ((rc = head_map(&km, k, d, heads, Nkv, B, ldk))) return rc;
+  if ((rc = head_map(&vm, v, d, heads, Nkv, B, ldv))) return rc;
+  dim3 grid((Nq + BQ * C::NWG - 1) / (BQ * C::NWG), heads, B);
+  MKD_LAUNCH_OK(launch_pdl(attn_tcgen05_kernel<DN>, grid, dim3(C::THREADS), C::SMEM, st, qm, km, vm, o, Nq, Nkv, d, ldo,
+                           scale * 1.4426950408889634f));
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+}  // namespace
+
+namespace mkd {
+int tma_encode_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box) {
+  EncodeFn fn = get_encode();
+  MKD_REQUIRE(fn != nullptr, MKD_E_CUDA, "cuTensorMapEncodeTiled entry point not found (driver too old?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MKD_REQUIRE(r == CUDA_SUCCESS, MKD_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return MKD_OK;
+}
+
+bool attention_tcgen05_supported(int d, int ldq, int ldk, int ldv) {
+  return d % 8 == 0 && d >= 8 && d <= 160 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0;
+}
+
+// bf16 attention on tcgen05; q / k / v / o are [B * N, ld] matrices, head h in columns [h*d, (h+1)*d)
+int attention_tcgen05(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d,
+                      int ldq, int ldk, int ldv, int ldo, float scale, cudaStream_t st) {
+  const int dn = (d + 15) / 16 * 16;
+  if (dn <= 16) return launch<16>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+  if (dn <= 32) return launch<32>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+  if (dn <= 48) return launch<48>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+  if (dn <= 64) return launch<64>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+  if (dn <= 80) return launch<80>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+  if (dn <= 128) return launch<128>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+  return launch<160>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+}
+}  // namespace mkd

@@ -127,5 +127,8 @@ inline int num_sms() { return 148; }  // B200
 int conv2d_generic(const mkd_conv_desc* d, cudaStream_t stream);
 int conv2d_tcgen05(const mkd_conv_desc* d, cudaStream_t stream);
 bool conv2d_tcgen05_supported(const mkd_conv_desc* d);
+bool attention_tcgen05_supported(int d, int ldq, int ldk, int ldv);
+int attention_tcgen05(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d,
+                      int ldq, int ldk, int ldv, int ldo, float scale, cudaStream_t st);
 
 }  // namespace mkd

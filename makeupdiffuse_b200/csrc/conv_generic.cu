@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvP p, const T* __r
 
 namespace mkd {
 int conv2d_generic(const mkd_conv_desc* d, cudaStream_t stream) {
+  MKD_REQUIRE(d->stats == nullptr, MKD_E_INVALID, "conv2d: fused GroupNorm statistics need the tcgen05 path (%s)", mkd_last_error());
   ConvP p;
   p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.K = d->K; p.R = d->R; p.S = d->S;
   p.stride = d->stride; p.pad = d->pad; p.up = d->upsample ? 1 : 0;

@@ -40,6 +40,8 @@ struct EpiP {
   const bf16* emb;
   const void* res;   // bf16 or fp32 (res_f32)
   float* partial;    // split-K workspace or nullptr
+  float2* stats;     // optional per-(128-row tile, channel) partial (sum, sum of squares) of the stored values
+  int stats_ld;      // float2 elements per tile row of `stats`
 };
 
 struct MainP {
@@ -305,7 +307,11 @@ __device__ __forceinline__ void epilogue_geglu8(const EpiP& e, int m, int row_va
 //                 phase 1  TMEM -> registers -> fp32 staging panel in smem (thread = accumulator row)
 //                 phase 2  256 threads walk the panel row-major, 8 channels each: coalesced bias / emb / residual
 //                          loads and bf16 / fp32 stores (consecutive threads -> consecutive 16 / 32 bytes)
-enum { EPI_PLAIN = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_PARTIAL = 3 };
+enum { EPI_PLAIN = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_PARTIAL = 3, EPI_STATS = 4 };
+// EPI_STATS = EPI_PLAIN + GroupNorm statistics of the output: every tile also emits, per output channel, the sum and
+// the sum of squares of the fp32 values it stored (column sums over its 128 rows), so that the GroupNorm that consumes
+// this tensor is a single streaming pass (mkd_groupnorm_apply) instead of reduce + normalise.  Deterministic: one
+// (tile, channel) slot per partial, fixed summation order, no atomics.
 // Shared-memory budget: the main loop is bound by how many bytes are in flight per SM (slot round trip = TMA latency
 // under load + MMA + two barrier wake-ups ~ 1800+ cycles), so the staging panel is kept narrow (40 columns, 22 KB) and
 // every remaining byte of the 227 KB goes to pipeline stages.
@@ -543,7 +549,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
       const int ab = j & 1, use = j >> 1;
       const int m_base = m_tile * BM;
       constexpr bool geglu = EPI == EPI_GEGLU;
-      constexpr bool plain = EPI == EPI_PLAIN || EPI == EPI_SILU;
+      constexpr bool plain = EPI == EPI_PLAIN || EPI == EPI_SILU || EPI == EPI_STATS;
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
       bool acc_ready = false;
 #pragma unroll 1
@@ -608,6 +614,11 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
         asm volatile("bar.sync 1, 256;\n" ::: "memory");  // panel staged (RAW)
         if (j == 0 && et == 0) MKD_TRACE(p == 0 ? 11 : 13);
         // ---- phase 2: coalesced walk over the panel ----
+        [[maybe_unused]] float st_s[8], st_q[8];  // EPI_STATS: this thread's column partials over its rows
+        if constexpr (EPI == EPI_STATS) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) st_s[k] = st_q[k] = 0.f;
+        }
         if constexpr (EPI == EPI_PARTIAL) {
           if (p2_active) {
             const int n = n_tile * BN + p * PW + g2 * 8;
@@ -668,6 +679,13 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
                   for (int k = 0; k < 8; ++k) r[k] = silu_f(r[k]);
                 }
+                if constexpr (EPI == EPI_STATS) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    st_s[k] += r[k];
+                    st_q[k] = fmaf(r[k], r[k], st_q[k]);
+                  }
+                }
                 if (ep.y32) store8(ep.y32 + (int64_t)m * ep.ldy32 + o, r);
                 if (ep.y) store8(ep.y + (int64_t)m * ep.ldy + o, r);
               } else {  // ragged channel tail (e.g. the 4-channel `out` conv): scalar, statically indexed
@@ -688,6 +706,33 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
                 }
               }
             }
+          }
+        }
+        if constexpr (EPI == EPI_STATS) {
+          // column sums of this panel: per-thread partials (8 channels x {sum, sumsq}) -> smem (the staging panel is
+          // free once every thread is past phase 2) -> 4 lanes per channel (stat x row half) -> one float2 per channel
+          constexpr int RP = 257;  // pitch of the 16 partial planes: conflict-free writes
+          static_assert(16 * RP <= BM * LDT, "stats scratch must fit the staging panel");
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          if (p2_active) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              staging[k * RP + et] = st_s[k];
+              staging[(8 + k) * RP + et] = st_q[k];
+            }
+          }
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          if (et < 4 * PW) {  // whole warps (PW is a multiple of 8)
+            const int c = et >> 2, stat = (et >> 1) & 1, hf = et & 1;
+            const int plane = stat * 8 + (c & 7), gq = c >> 3;
+            constexpr int HALF = (RPI + 1) / 2;
+            const int r0 = hf * HALF, r1 = hf ? RPI : HALF;
+            float acc = 0.f;
+            for (int r = r0; r < r1; ++r) acc += staging[plane * RP + r * NG + gq];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);             // both row halves
+            const float sq = __shfl_down_sync(0xffffffffu, acc, 2);  // lane 4c gets the sum of squares from lane 4c + 2
+            const int ch = n_tile * BN + p * PW + c;
+            if ((et & 3) == 0 && ch < ep.N_out) ep.stats[(int64_t)m_tile * ep.stats_ld + ch] = make_float2(acc, sq);
           }
         }
         if (j == 0 && et == 0 && p == 0) MKD_TRACE(12);
@@ -840,6 +885,10 @@ bool geometry(const mkd_conv_desc* d, Geometry& g) {
   if (d->act == MKD_ACT_GEGLU && !d->y) { set_error("GEGLU writes the bf16 output only"); return false; }
   if (d->residual && (d->ldr % 8 || !aligned16(d->residual))) { set_error("residual alignment"); return false; }
   if (d->emb && (d->lde % 8 || !aligned16(d->emb))) { set_error("emb alignment"); return false; }
+  if (d->stats && (d->act != MKD_ACT_NONE || d->K % 8 || d->stats_ld < d->K || ((uintptr_t)d->stats & 7))) {
+    set_error("stats needs act == NONE, K %% 8 == 0, stats_ld >= K, 8-byte aligned pointer");
+    return false;
+  }
   g.conv = d->R == 3;
   g.P = d->H; g.Q = d->W;
   if (d->upsample) { g.P = 2 * d->H; g.Q = 2 * d->W; }
@@ -910,13 +959,15 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     else { dd.H = g.P; dd.W = g.Q; dd.ldx = d_in->C; }
   }
   constexpr int EG = (BN == 160 ? EPI_GEGLU : EPI_PLAIN);
-  const KernelFn all[4] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
-                           gemm_tcgen05_kernel<BN, CL, EG>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>};
-  const size_t smems[4] = {Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_SILU>::SMEM, Cfg<BN, CL, EG>::SMEM,
-                           Cfg<BN, CL, EPI_PARTIAL>::SMEM};
+  constexpr int NV = 5;
+  const KernelFn all[NV] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
+                            gemm_tcgen05_kernel<BN, CL, EG>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>,
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS>};
+  const size_t smems[NV] = {Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_SILU>::SMEM, Cfg<BN, CL, EG>::SMEM,
+                            Cfg<BN, CL, EPI_PARTIAL>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM};
   static bool configured = false;
   if (!configured) {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems[i]);
       MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "gemm_tcgen05: cudaFuncSetAttribute(%zu): %s", smems[i], cudaGetErrorString(e));
     }
@@ -963,7 +1014,7 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   int splits = 1;
   const int n_groups = (n_tiles + CL - 1) / CL;  // N tiles per cluster (a pair takes two adjacent N tiles)
   const int tiles = g.m_tiles * n_groups * CL;
-  if (d->workspace && tiles <= 74 && mp.kblocks >= 32 && d->K % 16 == 0) {
+  if (d->workspace && tiles <= 74 && mp.kblocks >= 32 && d->K % 16 == 0 && !d->stats) {  // (the reducer emits no stats)
     splits = 148 / tiles;
     if (splits > mp.kblocks / 16) splits = mp.kblocks / 16;  // >= 16 K blocks (1024 of K) per split
     if (splits > 16) splits = 16;
@@ -981,6 +1032,7 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   ep.y = (bf16*)d->y; ep.bias = d->bias; ep.emb = (const bf16*)d->emb; ep.res = d->residual;
   ep.y32 = d->y32; ep.ldy32 = d->ldy32; ep.res_f32 = d->residual_dtype == MKD_F32;
   ep.partial = splits > 1 ? (float*)d->workspace : nullptr;
+  ep.stats = reinterpret_cast<float2*>(d->stats); ep.stats_ld = d->stats_ld;
 
   mp.m_tiles = g.m_tiles;
   mp.n_tiles = n_groups;
@@ -1005,7 +1057,7 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(352);
-    const int variant = ep.partial ? 3 : (ep.act == MKD_ACT_GEGLU ? 2 : (ep.act == MKD_ACT_SILU ? 1 : 0));
+    const int variant = ep.partial ? 3 : ep.stats ? 4 : (ep.act == MKD_ACT_GEGLU ? 2 : (ep.act == MKD_ACT_SILU ? 1 : 0));
     cfg.dynamicSmemBytes = smems[variant];
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];

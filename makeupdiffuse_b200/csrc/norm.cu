@@ -235,6 +235,89 @@ __global__ void gn_cluster_kernel(const T* __restrict__ x, TO* __restrict__ y, c
   }
 }
 
+// GroupNorm as one streaming pass: the producer's GEMM epilogue already emitted, per 128-row tile and channel, the
+// (sum, sum of squares) of the values it stored (mkd_conv_desc.stats).  Prologue: per-channel totals of this sample
+// (fixed order: deterministic) -> 32 group statistics (one warp per group) -> per-channel scale / shift in smem; then
+// y = act(x * scale + shift) over this CTA's row chunk, 8 channels per thread, 4 rows in flight.
+template <typename T, typename TO, bool SILU>
+__global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ y, const float2* __restrict__ stats,
+                                      int stats_ld, int tiles, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int HW, int C, int groups, int ldx, int ldy,
+                                      int rows_per_chunk, float eps) {
+  pdl_wait();
+  extern __shared__ float sm[];  // scale[C], shift[C], then float2 csum[C] (dead after the prologue)
+  float* scale = sm;
+  float* shift = sm + C;
+  float2* csum = reinterpret_cast<float2*>(sm + 2 * C);
+  __shared__ float2 gstat[64];   // (mean, rstd) per group
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int cgs = C / groups, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float2* p = stats + (int64_t)n * tiles * stats_ld + c;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < tiles; ++k) {
+      const float2 v = p[(int64_t)k * stats_ld];
+      a += v.x;
+      b += v.y;
+    }
+    csum[c] = make_float2(a, b);
+  }
+  __syncthreads();
+  const float inv_cnt = 1.0f / ((float)cgs * (float)HW);
+  for (int g = warp; g < groups; g += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int i = lane; i < cgs; i += 32) {
+      const float2 v = csum[g * cgs + i];
+      a += v.x;
+      b += v.y;
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      const float mean = a * inv_cnt;
+      const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+      gstat[g] = make_float2(mean, rsqrtf(var + eps));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float2 ms = gstat[c / cgs];
+    const float sc = gamma[c] * ms.y;
+    scale[c] = sc;
+    shift[c] = beta[c] - ms.x * sc;
+  }
+  __syncthreads();
+  const int VX = C / 8, RY = blockDim.x / VX;
+  const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
+  if (ry >= RY) return;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[vx * 8 + j];
+    sh[j] = shift[vx * 8 + j];
+  }
+  const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
+  TO* yb = y + (int64_t)n * HW * ldy + vx * 8;
+  for (int r = r0 + ry; r < r1; r += 4 * RY) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * RY < r1) load8(xb + (int64_t)(r + u * RY) * ldx, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r + u * RY < r1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = v[u][j] * sc[j] + sh[j];
+          v[u][j] = SILU ? silu_f(t) : t;
+        }
+        store8(yb + (int64_t)(r + u * RY) * ldy, v[u]);
+      }
+    }
+  }
+}
+
 // LayerNorm: one warp per row, the row lives in registers between the mean and the variance pass
 // (exact two-pass variance, like the reference).  C <= 8 * 32 * LN_VPL.
 constexpr int LN_VPL = 8;
@@ -371,6 +454,56 @@ extern "C" int mkd_groupnorm(const void* x, void* y, int x_dtype, int y_dtype, i
   if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
     return groupnorm_launch<float, float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, st);
   MKD_REQUIRE(false, MKD_E_INVALID, "groupnorm: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
+}
+
+template <typename T, typename TO>
+static int gn_apply_launch(const T* x, TO* y, int N, int HW, int C, int groups, int ldx, int ldy, const float* gamma,
+                           const float* beta, float eps, int silu, const float2* stats, int stats_ld, int tiles,
+                           cudaStream_t st) {
+  const int VX = C / 8;
+  int threads = VX >= 256 ? VX : (256 / VX) * VX;
+  threads = ((threads + 31) / 32) * 32;
+  const int RY = threads / VX;
+  // ~2 CTAs per SM, each streaming at least 4 * RY rows (one full set of loads in flight per thread)
+  int nchunks = (2 * 148 + N - 1) / N;
+  if (nchunks > HW / (4 * RY)) nchunks = HW / (4 * RY);
+  if (nchunks < 1) nchunks = 1;
+  const int rows = (HW + nchunks - 1) / nchunks;
+  nchunks = (HW + rows - 1) / rows;
+  const size_t smem = (size_t)4 * C * sizeof(float);
+  MKD_REQUIRE(smem <= 48 * 1024, MKD_E_INVALID, "groupnorm_apply: C=%d too large", C);
+  dim3 grid(nchunks, N);
+  if (silu)
+    MKD_LAUNCH_OK(launch_pdl(gn_apply_stats_kernel<T, TO, true>, grid, dim3(threads), smem, st, x, y, stats, stats_ld, tiles, gamma, beta, HW, C,
+                             groups, ldx, ldy, rows, eps));
+  else
+    MKD_LAUNCH_OK(launch_pdl(gn_apply_stats_kernel<T, TO, false>, grid, dim3(threads), smem, st, x, y, stats, stats_ld, tiles, gamma, beta, HW, C,
+                             groups, ldx, ldy, rows, eps));
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+extern "C" int mkd_groupnorm_apply(const void* x, void* y, int x_dtype, int y_dtype, int N, int HW, int C, int groups,
+                                   int ldx, int ldy, const float* gamma, const float* beta, float eps, int silu,
+                                   const float* stats, int stats_ld, int tiles_per_sample, mkd_stream_t stream) {
+  MKD_REQUIRE(x && y && gamma && beta && stats && N > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64, MKD_E_INVALID,
+              "groupnorm_apply: bad args");
+  MKD_REQUIRE(C % groups == 0 && C % 8 == 0 && C <= 8 * 1024, MKD_E_INVALID,
+              "groupnorm_apply: C=%d must be a multiple of groups=%d and of 8", C, groups);
+  MKD_REQUIRE(N <= 65535 && HW == 128 * tiles_per_sample && stats_ld >= C, MKD_E_INVALID,
+              "groupnorm_apply: HW=%d must be 128 * tiles_per_sample=%d, stats_ld=%d >= C", HW, tiles_per_sample, stats_ld);
+  MKD_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && ldx >= C && ldy >= C &&
+                  ((uintptr_t)stats & 7) == 0,
+              MKD_E_ALIGN, "groupnorm_apply: ld must be a multiple of 8 (>= C), pointers 16B aligned, stats 8B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float2* sp = reinterpret_cast<const float2*>(stats);
+  if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
+    return gn_apply_launch<bf16, bf16>((const bf16*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, st);
+  if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
+    return gn_apply_launch<float, bf16>((const float*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, st);
+  if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
+    return gn_apply_launch<float, float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, st);
+  MKD_REQUIRE(false, MKD_E_INVALID, "groupnorm_apply: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
 }
 
 extern "C" int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,

@@ -124,7 +124,8 @@ class B200ControlLDM:
             else:
                 pending = cn.run_trunk(cn._to_nhwc(x_noisy, "x_in"), prep["hint"], t, prep["kv_cn"], N, H, W)
             inject = [None] * 12 + [slots[12]] if self.only_mid_control else slots
-            cn.zero_convs(pending, N, inject=inject, scales=self.control_scales)
+            cn.zero_convs(pending, N, inject=inject, scales=self.control_scales, inject_st=un.skip_slot_stats(N, H, W))
+            un.note_slots_rewritten([j for j, s in enumerate(inject) if s is not None], with_stats=True)
         e = un.decode(prep["kv_unet"], N, H, W)
         eps = torch.empty(N, un.out_channels, H, W, dtype=torch.float32, device=x_noisy.device)
         ops.nhwc_to_nchw(e, eps)

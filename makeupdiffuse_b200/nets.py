@@ -20,6 +20,7 @@ There is no PyTorch compute fallback: without the CUDA library these classes can
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -35,11 +36,14 @@ class Act:
     ``lo`` — activation dtype (bf16), what tensor-core A operands and the decoder's concat slots read;
     ``hi`` — fp32 copy written by the same epilogue, what norms and residual adds read, so that the residual
              stream is not re-rounded at every block (that rounding, not the bf16 MMAs, dominated the eps error).
-    In the fp32 check mode only ``lo`` (fp32) exists."""
-    __slots__ = ("lo", "hi")
+    In the fp32 check mode only ``lo`` (fp32) exists.
+    ``st`` — optional GroupNorm statistics of the tensor, [rows / 128, C, 2] fp32: per-tile column (sum, sumsq) emitted
+             by the epilogue that produced it (mkd_conv_desc.stats), so the consuming GroupNorm is one streaming pass.
+             ``None`` means "not produced": the consumer then runs the full (reduce + normalise) GroupNorm kernel."""
+    __slots__ = ("lo", "hi", "st")
 
-    def __init__(self, lo=None, hi=None):
-        self.lo, self.hi = lo, hi
+    def __init__(self, lo=None, hi=None, st=None):
+        self.lo, self.hi, self.st = lo, hi, st
 
     def src(self):
         return self.hi if self.hi is not None else self.lo
@@ -88,6 +92,7 @@ class _Net(nn.Module):
         self.middle = [("res", "middle_block.0", ch, ch), ("st", "middle_block.1", ch), ("res", "middle_block.2", ch, ch)]
         self._ch, self._ds = ch, ds
         self._attn_res = tuple(attention_resolutions)
+        self.fused_gn_stats = os.environ.get("MKD_FUSED_GN", "1") != "0"  # MKD_FUSED_GN=0: always the two-phase GroupNorm
         self._channel_mult, self._nrb = tuple(channel_mult), num_res_blocks
         self.w: dict[str, torch.Tensor] = {}
         self._bufs: dict = {}
@@ -234,6 +239,25 @@ class _Net(nn.Module):
     def _gn_ws(self, N):
         return self._buf("gn_ws", 1, ops.groupnorm_workspace_bytes(N) // 4, torch.float32)
 
+    def _stats_ok(self, N, H, W):
+        """fused GroupNorm statistics: bf16 path, whole 128-row tiles per sample (so a tile never spans two samples)"""
+        return self._hi and self.fused_gn_stats and (H * W) % 128 == 0
+
+    def _stats(self, name, rows, cols):
+        key = ("st_" + name, rows, cols)
+        b = self._bufs.get(key)
+        if b is None:
+            b = torch.zeros(rows // 128, cols, 2, dtype=torch.float32, device=self._device)
+            self._bufs[key] = b
+        return b
+
+    def _gn(self, x, y, N, gamma, beta, eps, silu):
+        """x: Act (or (tensor, stats) via Act); GroupNorm(+SiLU) of x into the bf16 operand buffer y"""
+        if x.st is not None:
+            ops.groupnorm_apply(x.src(), y, N, gamma, beta, eps, silu, x.st)
+        else:
+            ops.groupnorm(x.src(), y, N, gamma, beta, eps, silu, self._gn_ws(N))
+
     # ---- building blocks ---------------------------------------------------------------------------------------
     def _conv(self, x, wkey, y, N, H, W, R=1, **kw):
         """y: activation-dtype output view or None; kw may carry y32= (fp32 copy), residual=, emb=, act= ..."""
@@ -278,20 +302,20 @@ class _Net(nn.Module):
         _, key, cin, cout = layer
         M = N * H * W
         t1 = self._buf("gn_a", M, cin)
-        ops.groupnorm(x.src(), t1, N, self.w[key + ".gn1.g"], self.w[key + ".gn1.b"], 1e-5, True, self._gn_ws(N))
+        self._gn(x, t1, N, self.w[key + ".gn1.g"], self.w[key + ".gn1.b"], 1e-5, True)
         h_lo, h_hi = self._side("res_h", M, cout)
+        h_st = self._stats("res_h", M, cout) if self._stats_ok(N, H, W) else None
         e = emb_all[:, self._emb_off[key]:self._emb_off[key] + cout]
-        self._conv(t1, key + ".c1", h_lo, N, H, W, R=3, emb=e, y32=h_hi)
+        self._conv(t1, key + ".c1", h_lo, N, H, W, R=3, emb=e, y32=h_hi, stats=h_st)
         t2 = self._buf("gn_b", M, cout)
-        ops.groupnorm(h_hi if h_hi is not None else h_lo, t2, N, self.w[key + ".gn2.g"], self.w[key + ".gn2.b"], 1e-5,
-                      True, self._gn_ws(N))
+        self._gn(Act(h_lo, h_hi, h_st), t2, N, self.w[key + ".gn2.g"], self.w[key + ".gn2.b"], 1e-5, True)
         if cin != cout:
             s_lo, s_hi = self._side("res_sk", M, cout)
             self._conv(x.lo, key + ".sk", s_lo, N, H, W, R=1, y32=s_hi)
             sk = s_hi if s_hi is not None else s_lo
         else:
             sk = x.src()
-        self._conv(t2, key + ".c2", y.lo, N, H, W, R=3, residual=sk, y32=y.hi)
+        self._conv(t2, key + ".c2", y.lo, N, H, W, R=3, residual=sk, y32=y.hi, stats=y.st)
 
     def _st(self, layer, x, y, ctx_kv, N, H, W):
         """x, y: Act.  The token stream xs (x += attn1, += attn2, += ff) lives in fp32 until its last update, which
@@ -300,7 +324,7 @@ class _Net(nn.Module):
         M, hd = N * H * W, ch // self.heads
         scale = hd ** -0.5
         n = self._buf("st_n", M, ch)
-        ops.groupnorm(x.src(), n, N, self.w[key + ".gn.g"], self.w[key + ".gn.b"], 1e-6, False, self._gn_ws(N))
+        self._gn(x, n, N, self.w[key + ".gn.g"], self.w[key + ".gn.b"], 1e-6, False)
         x_lo, x_hi = self._side("st_x", M, ch)
         xs = x_hi if x_hi is not None else x_lo           # the stream every LN / residual reads
         o_lo, o_hi = (None, xs) if self._hi else (xs, None)  # how an in-place update of xs is written
@@ -329,7 +353,7 @@ class _Net(nn.Module):
         self._linear(ln, key + ".ff1", ff, act=L.ACT_GEGLU, geglu_block=_geglu_block(inner))
         xa = self._buf("st_xa", M, ch) if self._hi else xs  # proj_out's A operand (activation dtype)
         self._linear(ff, key + ".ff2", xa, residual=xs)
-        self._conv(xa, key + ".po", y.lo, N, H, W, R=1, residual=x.src(), y32=y.hi)
+        self._conv(xa, key + ".po", y.lo, N, H, W, R=1, residual=x.src(), y32=y.hi, stats=y.st)
 
     def context_kv(self, context):
         """attn2 K/V projections of the (step-invariant) text context for every SpatialTransformer: hoisted out of
@@ -370,21 +394,25 @@ class _Net(nn.Module):
             kind = layer[0]
             if not last:
                 lo, hi = self._needs(layers[li + 1])
-                out = self._act(f"pp{li % 2}", N * H * W, layer[3] if kind == "res" else layer[2], lo=lo, hi=hi)
+                cout = layer[3] if kind == "res" else layer[2]
+                out = self._act(f"pp{li % 2}", N * H * W, cout, lo=lo, hi=hi)
+                if hi and kind != "up" and self._stats_ok(N, H, W):  # the next layer starts with a GroupNorm
+                    out.st = self._stats(f"pp{li % 2}", N * H * W, cout)
             else:
                 out = y
             if kind == "conv_in":
+                out.st = None  # C = 4 runs on the generic kernel, which emits no statistics
                 self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, residual=conv_in_residual, y32=out.hi)
             elif kind == "res":
                 self._res(layer, cur, out, emb_all, N, H, W)
             elif kind == "st":
                 self._st(layer, cur, out, ctx_kv, N, H, W)
             elif kind == "down":
-                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, stride=2, y32=out.hi)
+                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, stride=2, y32=out.hi, stats=out.st)
                 H, W = H // 2, W // 2
             elif kind == "up":
                 assert last
-                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, upsample=True, y32=out.hi)
+                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, upsample=True, y32=out.hi, stats=out.st)
                 H, W = 2 * H, 2 * W
             cur = out
         return H, W
@@ -456,6 +484,8 @@ class B200ControlNet(_Net):
             ch = self.block_chans[j]
             ho, wo = (h // 2, w // 2) if blk[0][0] == "down" else (h, w)
             y = self._act(f"cn_h{j}", N * ho * wo, ch, lo=True, hi=self._next_needs_hi(j))
+            if self._next_needs_hi(j) and self._stats_ok(N, ho, wo):
+                y.st = self._stats(f"cn_h{j}", N * ho * wo, ch)
             # h = input_blocks[0](x) + guided_hint: the add rides in conv_in's epilogue
             self._run_block(blk, cur, y, emb_all, ctx_kv, N, h, w, conv_in_residual=guided_hint if j == 0 else None)
             cur, h, w = y, ho, wo
@@ -465,22 +495,26 @@ class B200ControlNet(_Net):
         pending.append(("middle_block_out.0", y.lo, len(self.input_blocks), h, w))
         return pending
 
-    def zero_convs(self, pending, N, inject=None, scales=None):
+    def zero_convs(self, pending, N, inject=None, scales=None, inject_st=None):
         """the 13 zero-convs: into own buffers (inject None), or accumulated as scale_i * zero_conv_i(h) straight into
-        the UNet's skip slots / middle output (makeup_diffuse.py:166 + upstream `hs.pop() + control.pop()`)."""
-        return [self._zero_conv(key, x, j, N, h, w, inject, scales) for key, x, j, h, w in pending]
+        the UNet's skip slots / middle output (makeup_diffuse.py:166 + upstream `hs.pop() + control.pop()`).
+        inject_st[j]: statistics view of slot j — the injecting epilogue re-emits the GroupNorm partials of the
+        values it leaves in the slot (the decoder's GroupNorm reads those)."""
+        return [self._zero_conv(key, x, j, N, h, w, inject, scales, None if inject_st is None else inject_st[j])
+                for key, x, j, h, w in pending]
 
     def run(self, x_nhwc, guided_hint, t, ctx_kv, N, H, W, inject=None, scales=None):
         return self.zero_convs(self.run_trunk(x_nhwc, guided_hint, t, ctx_kv, N, H, W), N, inject, scales)
 
-    def _zero_conv(self, key, x, j, N, h, w, inject, scales):
+    def _zero_conv(self, key, x, j, N, h, w, inject, scales, st=None):
         ch = x.shape[1]
         if inject is None:
             out = self._buf(f"cn_out{j}", N * h * w, ch)
             self._conv(x, key, out, N, h, w, R=1)
             return (out, h, w)
         if inject[j] is not None:
-            self._conv(x, key, inject[j], N, h, w, R=1, residual=inject[j], alpha=1.0 if scales is None else scales[j])
+            self._conv(x, key, inject[j], N, h, w, R=1, residual=inject[j], alpha=1.0 if scales is None else scales[j],
+                       stats=st)
         return None
 
     def forward(self, x, hint, timesteps, context, **kwargs):
@@ -557,32 +591,70 @@ class B200ControlledUnet(_Net):
         slots.append(cat0[:, :ch0])
         return slots
 
+    def _cat_stats(self, i, N, H, W):
+        """GroupNorm statistics of concat buffer i ([tiles, C_h + C_skip, 2]) or None when the level has no whole tiles"""
+        cat, _, ds = self._cat(i, N, H, W)
+        if not self._stats_ok(N, H // ds, W // ds):
+            return None
+        return self._stats(f"cat{i}", cat.shape[0], cat.shape[1])
+
+    def skip_slot_stats(self, N, H, W):
+        """statistics views matching skip_slots(): the channel slice of the concat statistics each slot owns"""
+        nb = len(self.input_blocks)
+        out = []
+        for j in range(nb):
+            st = self._cat_stats(nb - 1 - j, N, H, W)
+            out.append(None if st is None else st[:, self.cat_split[nb - 1 - j][0]:, :])
+        st0 = self._cat_stats(0, N, H, W)
+        out.append(None if st0 is None else st0[:, :self.cat_split[0][0], :])
+        return out
+
+    def note_slots_rewritten(self, js, with_stats):
+        """slots js were updated after encode(): by injecting epilogues that re-emitted their statistics (True) or by
+        a plain add (False, the reference call form with an explicit `control` list)"""
+        for j in js:
+            self._slot_ok[j] = bool(with_stats) and self._slot_st[j] is not None
+
     def encode(self, x_nhwc, t, ctx_kv, N, H, W):
         self._emb_cur = self._time_embedding(t, N)
         slots = self.skip_slots(N, H, W)
+        self._slot_st = self.skip_slot_stats(N, H, W)
+        self._slot_ok = [False] * len(slots)
         cur, h, w = Act(x_nhwc), H, W
         for j, blk in enumerate(self.input_blocks):
             # bf16 copy straight into the decoder's concat slot; fp32 copy for the next block's norm / identity skip
             y = Act(slots[j], self._buf(f"enc{j}_32", slots[j].shape[0], slots[j].shape[1], torch.float32)
-                    if self._hi and self._next_needs_hi(j) else None)
+                    if self._hi and self._next_needs_hi(j) else None, self._slot_st[j])
             h, w = self._run_block(blk, cur, y, self._emb_cur, ctx_kv, N, h, w)
+            self._slot_ok[j] = y.st is not None
             cur = y
-        self._run_block(self.middle, cur, Act(slots[-1]), self._emb_cur, ctx_kv, N, h, w)
+        y = Act(slots[-1], None, self._slot_st[-1])
+        self._run_block(self.middle, cur, y, self._emb_cur, ctx_kv, N, h, w)
+        self._slot_ok[-1] = y.st is not None
         return slots
 
     def decode(self, ctx_kv, N, H, W):
         nb = len(self.output_blocks)
+        nslots = len(self.input_blocks)
+        h_ok = self._slot_ok[nslots]  # statistics of the h half of concat 0 (= the middle-block output)
         for i, blk in enumerate(self.output_blocks):
             cat, _, ds = self._cat(i, N, H, W)
+            cat_st = self._cat_stats(i, N, H, W)
+            if not (h_ok and self._slot_ok[nslots - 1 - i]):
+                cat_st = None  # some part of the concat was not produced with statistics: full GroupNorm kernel
             if i + 1 < nb:
                 nxt, nch, _ = self._cat(i + 1, N, H, W)
-                y = Act(nxt[:, :nch])
+                nst = self._cat_stats(i + 1, N, H, W)
+                y = Act(nxt[:, :nch], None, None if nst is None else nst[:, :nch, :])
             else:
                 y = self._act("dec_out", N * H * W, self._out_ch, lo=False, hi=True)  # only the out GroupNorm reads it
-            self._run_block(blk, Act(cat), y, self._emb_cur, ctx_kv, N, H // ds, W // ds)
+                if self._stats_ok(N, H, W):
+                    y.st = self._stats("dec_out", N * H * W, self._out_ch)
+            self._run_block(blk, Act(cat, None, cat_st), y, self._emb_cur, ctx_kv, N, H // ds, W // ds)
+            h_ok = y.st is not None
         M = N * H * W
         g = self._buf("gn_a", M, self._out_ch)
-        ops.groupnorm(y.src(), g, N, self.w["out.gn.g"], self.w["out.gn.b"], 1e-5, True, self._gn_ws(N))
+        self._gn(y, g, N, self.w["out.gn.g"], self.w["out.gn.b"], 1e-5, True)
         eo = self._buf("eps_nhwc", M, 8)
         self._conv(g, "out.2", eo[:, :self.out_channels], N, H, W, R=3)
         return eo[:, :self.out_channels]
@@ -599,6 +671,7 @@ class B200ControlledUnet(_Net):
             for j in idx:
                 c = self._to_nhwc(control[j], f"ctl_in{j}")
                 ops.add(slots[j], c, slots[j])
+            self.note_slots_rewritten(idx, with_stats=False)
         e = self.decode(ctx_kv, N, H, W)
         out = torch.empty(N, self.out_channels, H, W, dtype=torch.float32, device=e.device)
         ops.nhwc_to_nchw(e, out)

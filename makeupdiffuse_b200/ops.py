@@ -148,6 +148,21 @@ def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
                                    workspace.numel() * workspace.element_size(), _stream()), "groupnorm")
 
 
+@_timed("groupnorm_apply", lambda x, y, *a, **k: _nb(x, y))
+def groupnorm_apply(x2d, y2d, N, gamma, beta, eps, silu, stats, groups=32):
+    """GroupNorm whose statistics were emitted by the producing conv2d(..., stats=): ``stats`` is a
+    [N * HW / 128, C, 2] fp32 view (row pitch may exceed C when it is a channel slice of a concat's statistics)."""
+    px, ldx = _rows(x2d)
+    py, ldy = _rows(y2d)
+    M, Cc = x2d.shape
+    assert M % N == 0 and (M // N) % 128 == 0 and y2d.shape == x2d.shape
+    assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[1:] == (Cc, 2) and stats.stride(2) == 1
+    assert stats.stride(1) == 2 and stats.shape[0] == M // 128 and stats.stride(0) % 2 == 0
+    L.check(L.load().mkd_groupnorm_apply(px, py, _dt(x2d), _dt(y2d), N, M // N, Cc, groups, ldx, ldy, gamma.data_ptr(),
+                                         beta.data_ptr(), float(eps), int(bool(silu)), stats.data_ptr(),
+                                         stats.stride(0) // 2, (M // N) // 128, _stream()), "groupnorm_apply")
+
+
 @_timed("layernorm", lambda x, y, *a, **k: _nb(x, y))
 def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
     px, ldx = _rows(x2d)
@@ -160,7 +175,7 @@ def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
 
 def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None,
                    residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None,
-                   y32=None) -> L.ConvDesc:
+                   y32=None, stats=None) -> L.ConvDesc:
     """y2d: output in the activation dtype (or None); y32: optional fp32 copy of the same result."""
     px, ldx = _rows(x2d)
     Cc = x2d.shape[1]
@@ -198,6 +213,10 @@ def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=
         d.residual, d.ldr, d.residual_dtype = pr, ldr, _dt(residual)
     if workspace is not None:
         d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    if stats is not None:  # [ceil(M_out / 128), K, 2] fp32 view: GroupNorm partials of the output (mkd_conv_desc.stats)
+        assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[1:] == (K, 2)
+        assert stats.stride(2) == 1 and stats.stride(1) == 2 and stats.stride(0) % 2 == 0
+        d.stats, d.stats_ld = stats.data_ptr(), stats.stride(0) // 2
     return d
 
 

@@ -73,12 +73,32 @@ def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
     y2d.copy_(r.permute(0, 2, 1).reshape(M, C))
 
 
+def groupnorm_apply(x2d, y2d, N, gamma, beta, eps, silu, stats, groups=32):
+    """mkd_groupnorm_apply: statistics come from the producer's per-tile (sum, sumsq) partials, not from x"""
+    M, C = x2d.shape
+    tiles = (M // N) // 128
+    assert stats.shape == (M // 128, C, 2)
+    tot = stats.float().reshape(N, tiles, C, 2).sum(1)                      # [N, C, 2]
+    cg = C // groups
+    gsum = tot.reshape(N, groups, cg, 2).sum(2)                             # [N, groups, 2]
+    cnt = cg * (M // N)
+    mean = gsum[..., 0] / cnt
+    var = (gsum[..., 1] / cnt - mean * mean).clamp_min(0)
+    rstd = torch.rsqrt(var + eps)
+    mean_c = mean.repeat_interleave(cg, 1)[:, None, :]
+    rstd_c = rstd.repeat_interleave(cg, 1)[:, None, :]
+    r = (x2d.float().reshape(N, M // N, C) - mean_c) * rstd_c * gamma + beta
+    if silu:
+        r = F.silu(r)
+    y2d.copy_(r.reshape(M, C))
+
+
 def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
     y2d.copy_(F.layer_norm(x2d.float(), (x2d.shape[1],), gamma, beta, eps))
 
 
 def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None, residual=None,
-           alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None, y32=None):
+           alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None, y32=None, stats=None):
     C = x2d.shape[1]
     K = w.shape[0]
     assert x2d.shape[0] == N * H * W and w.numel() == K * R * S * C
@@ -101,6 +121,11 @@ def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, b
         acc = acc + residual.float()
     if act == L.ACT_SILU:
         acc = F.silu(acc)
+    if stats is not None:  # per-128-row-tile column (sum, sumsq) of the stored values (mkd_conv_desc.stats)
+        assert act == L.ACT_NONE and C >= 64 and Mo % 128 == 0 and stats.shape == (Mo // 128, K, 2)
+        t = acc.reshape(Mo // 128, 128, K)
+        stats[..., 0] = t.sum(1)
+        stats[..., 1] = (t * t).sum(1)
     assert y2d is not None or y32 is not None
     for out in (y2d, y32):
         if out is not None:
@@ -115,4 +140,4 @@ def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
 
 
 ALL = ["device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
-       "silu", "geglu", "add", "groupnorm", "layernorm", "conv2d", "attention"]
+       "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "conv2d", "attention"]

@@ -288,11 +288,76 @@ def test_conv_rejects_bad_descriptors():
         ops.conv2d(x, w, x[:, :32], N=1, H=8, W=8)  # 32-column view cannot hold K=64 output channels
 
 
+# ---- GroupNorm statistics fused into the producing epilogue + the one-pass apply kernel ------------------------------
+STATS_CASES = [
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, emb=True),                      # ResBlock conv1 -> h (fp32 only) + stats
+    dict(N=3, H=16, W=16, C=640, K=640, R=3, residual=True, slot=(640, 1280)),  # conv2 into a concat slot + stats slice
+    dict(N=2, H=32, W=32, C=320, K=320, R=1, inplace=True),                  # zero-conv injection re-emitting stats
+    dict(N=1, H=64, W=64, C=320, K=320, R=1, residual=True),                 # 512^2 level
+    dict(N=2, H=16, W=16, C=1280, K=640, R=3, upsample=False, emb=True),     # C_in != C_out
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, stride=2),                      # Downsample (im2col + GEMM), 16x16 out
+    dict(N=2, H=8, W=8, C=640, K=640, R=3, up=True),                         # Upsample 8 -> 16
+]
+
+
+@pytest.mark.parametrize("case", STATS_CASES)
+def test_conv_stats_and_groupnorm_apply(case):
+    """conv2d(stats=) must emit, per 128-row tile and channel, the (sum, sumsq) of exactly the fp32 values it stored;
+    groupnorm_apply on those statistics must equal F.group_norm of the stored tensor."""
+    N, H, W, C, K, R = (case[k] for k in "NHWCKR")
+    stride, up = case.get("stride", 1), case.get("up", False)
+    Ho, Wo = (2 * H, 2 * W) if up else (H // stride, W // stride)
+    M, Mo = N * H * W, N * Ho * Wo
+    x = rnd(M, C, dt=BF, seed=1)
+    w = (rnd(K, R, R, C, dt=F32, seed=2) / math.sqrt(C * R * R)).to(BF)
+    b = rnd(K, seed=3)
+    e = rnd(N, K, dt=BF, seed=4) if case.get("emb") else None
+    off, width = case.get("slot", (0, K))
+    yb = rnd(Mo, width, dt=BF, seed=5)
+    y = yb[:, off:off + K]
+    y32 = torch.empty(Mo, K, device=DEV)
+    res = y if case.get("inplace") else (rnd(Mo, K, dt=F32, seed=6) if case.get("residual") else None)
+    stb = torch.full((Mo // 128, width, 2), -7.0, device=DEV)
+    st = stb[:, off:off + K, :]
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV)
+    ops.conv2d(x, w, y, N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=up, bias=b, emb=e, residual=res,
+               alpha=0.5 if case.get("inplace") else 1.0, workspace=ws, y32=y32, stats=st)
+    t = y32.reshape(Mo // 128, 128, K)
+    ref = torch.stack([t.sum(1), (t * t).sum(1)], -1)
+    assert rel(st[..., 0], ref[..., 0]) < 1e-5 and rel(st[..., 1], ref[..., 1]) < 1e-5
+    if off:  # columns outside the slice untouched
+        assert bool((stb[:, :off] == -7.0).all())
+    # determinism: a second run writes bit-identical statistics
+    st1 = st.clone()
+    if not case.get("inplace"):
+        ops.conv2d(x, w, y, N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=up, bias=b, emb=e, residual=res,
+                   workspace=ws, y32=y32, stats=st)
+        assert torch.equal(st, st1)
+    for silu in (True, False):
+        for src in (y32, y):
+            g, bt = rnd(K, seed=7) + 1.0, rnd(K, seed=8)
+            out = torch.empty(Mo, K, device=DEV, dtype=BF)
+            ops.groupnorm_apply(src, out, Nn := N, g, bt, 1e-5, silu, st)
+            r = F.group_norm(y32.reshape(N, Ho * Wo, K).permute(0, 2, 1), 32, g, bt, 1e-5)
+            r = (F.silu(r) if silu else r).permute(0, 2, 1).reshape(Mo, K)
+            assert rel(out, r) < 6e-3, (silu, src.dtype, rel(out, r))
+
+
+def test_conv_stats_rejected_on_generic_path():
+    x = rnd(256, 4, dt=BF)
+    w = rnd(64, 3, 3, 4, dt=BF)
+    y = torch.empty(256, 64, device=DEV, dtype=BF)
+    with pytest.raises(RuntimeError, match="statistics|stats"):
+        ops.conv2d(x, w, y, N=1, H=16, W=16, R=3, S=3, pad=1, stats=torch.zeros(2, 64, 2, device=DEV))
+
+
 # ---- attention -------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [BF, F32])
 @pytest.mark.parametrize("B,heads,Nq,Nkv,d", [(2, 8, 1024, 1024, 40), (2, 8, 256, 256, 80), (3, 8, 64, 64, 160),
                                                (2, 8, 16, 16, 160), (2, 8, 1024, 77, 40), (2, 8, 64, 77, 160),
-                                               (1, 4, 100, 77, 16), (1, 4, 64, 64, 32), (2, 2, 200, 130, 64)])
+                                               (1, 4, 100, 77, 16), (1, 4, 64, 64, 32), (2, 2, 200, 130, 64),
+                                               (1, 8, 4096, 4096, 40), (2, 8, 300, 300, 8), (1, 3, 513, 257, 96),
+                                               (1, 2, 129, 128, 128)])
 def test_attention(dt, B, heads, Nq, Nkv, d):
     C = heads * d
     self_attn = Nq == Nkv
