@@ -19,6 +19,7 @@
 //   zero-filled by the TMA unit (zeros add nothing to QK^T and give zero O columns that are never stored).
 //   Keys beyond Nkv in the last tile are zero-filled the same way and masked to -inf before the softmax.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tcgen05.cuh"
 using namespace mkd;
@@ -29,11 +30,16 @@ namespace {
 constexpr int BQ = 128, BKV = 128;
 constexpr int CH = 128 * 128;  // bytes of one [128 rows][64 bf16] chunk
 
-template <int DN> struct ACfg {
+// NWG = softmax warpgroups (128-query tiles) per CTA, ST = K / V ring depth.  Two shapes are used:
+//   <DN, 1, 1>  80 KB of smem and 256 TMEM columns for head dims <= 64: TWO CTAs share an SM, so one CTA's start-up,
+//               barrier round trips and non-exp2 phases are covered by the other's exp2 phase (the MUFU pipe is the
+//               bound of this kernel); also what the small maps and the 77-key cross attention want (more CTAs);
+//   <DN, 2, .>  one CTA per SM with two warpgroups sharing every K / V tile (halves the K/V traffic).
+template <int DN, int NWG_, int ST_> struct ACfg {
   static constexpr int DCH = (DN + 63) / 64;                 // 64-channel chunks of the head dim
-  static constexpr int NWG = DCH <= 2 ? 2 : 1;               // softmax warpgroups (query tiles) per CTA
-  static constexpr int ST = DCH == 1 ? 2 : 1;                // K / V ring depth
+  static constexpr int NWG = NWG_, ST = ST_;
   static constexpr int OSTR = (DN + 31) / 32 * 32;           // TMEM column stride between the O accumulators
+  static constexpr int TCOLS = NWG * 128 + NWG * OSTR <= 256 ? 256 : 512;
   static constexpr int THREADS = 32 * (4 * NWG + 2);
   static constexpr int NBAR = 5 * NWG + 4 * ST;              // q_full, s_full, s_free, p_full, o_full | k/v full/empty
   static constexpr size_t SMEM = (size_t)(NWG * DCH + 2 * ST * DCH + 2 * NWG) * CH + NBAR * 8 + 16 + 1024;
@@ -41,12 +47,12 @@ template <int DN> struct ACfg {
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
-template <int DN>
-__global__ void __launch_bounds__(ACfg<DN>::THREADS, 1)
+template <int DN, int NWG_, int ST_>
+__global__ void __launch_bounds__(ACfg<DN, NWG_, ST_>::THREADS, ACfg<DN, NWG_, ST_>::TCOLS == 256 ? 2 : 1)
     attn_tcgen05_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                         const __grid_constant__ CUtensorMap vmap, bf16* __restrict__ o, int Nq, int Nkv, int d, int ldo,
                         float sl2) {
-  using C = ACfg<DN>;
+  using C = ACfg<DN, NWG_, ST_>;
   constexpr int DCH = C::DCH, NWG = C::NWG, ST = C::ST;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(ACfg<DN>::THREADS, 1)
     }
     fence_barrier_init();
   }
-  if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
+  if (warp == W_MMA) tmem_alloc<C::TCOLS>(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(ACfg<DN>::THREADS, 1)
   __syncthreads();
   if (warp == W_MMA) {
     fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<C::TCOLS>(tmem_base);
   }
 }
 
@@ -305,13 +311,13 @@ int head_map(CUtensorMap* map, const bf16* base, int d, int heads, int ntok, int
   return tma_encode_bf16(map, base, 4, dims, str, box);
 }
 
-template <int DN>
+template <int DN, int NWG, int ST>
 int launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d, int ldq, int ldk,
            int ldv, int ldo, float scale, cudaStream_t st) {
-  using C = ACfg<DN>;
+  using C = ACfg<DN, NWG, ST>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_kernel<DN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_kernel<DN, NWG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "attention_tcgen05: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
@@ -321,7 +327,7 @@ int launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int head
   if ((rc = head_map(&km, k, d, heads, Nkv, B, ldk))) return rc;
   if ((rc = head_map(&vm, v, d, heads, Nkv, B, ldv))) return rc;
   dim3 grid((Nq + BQ * C::NWG - 1) / (BQ * C::NWG), heads, B);
-  MKD_LAUNCH_OK(launch_pdl(attn_tcgen05_kernel<DN>, grid, dim3(C::THREADS), C::SMEM, st, qm, km, vm, o, Nq, Nkv, d, ldo,
+  MKD_LAUNCH_OK(launch_pdl(attn_tcgen05_kernel<DN, NWG, ST>, grid, dim3(C::THREADS), C::SMEM, st, qm, km, vm, o, Nq, Nkv, d, ldo,
                            scale * 1.4426950408889634f));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
@@ -349,12 +355,23 @@ bool attention_tcgen05_supported(int d, int ldq, int ldk, int ldv) {
 int attention_tcgen05(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d,
                       int ldq, int ldk, int ldv, int ldo, float scale, cudaStream_t st) {
   const int dn = (d + 15) / 16 * 16;
-  if (dn <= 16) return launch<16>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-  if (dn <= 32) return launch<32>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-  if (dn <= 48) return launch<48>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-  if (dn <= 64) return launch<64>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-  if (dn <= 80) return launch<80>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-  if (dn <= 128) return launch<128>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-  return launch<160>(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+  static int pair = -1;  // MKD_ATTN_PAIR=1: two warpgroups per CTA also for head dims <= 64 (A/B measurements)
+  if (pair < 0) {
+    const char* e = getenv("MKD_ATTN_PAIR");
+    pair = (e && e[0] == '1') ? 1 : 0;
+  }
+#define MKD_ATTN_ARGS q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st
+  if (dn <= 64 && !pair) {
+    if (dn <= 16) return launch<16, 1, 1>(MKD_ATTN_ARGS);
+    if (dn <= 32) return launch<32, 1, 1>(MKD_ATTN_ARGS);
+    if (dn <= 48) return launch<48, 1, 1>(MKD_ATTN_ARGS);
+    return launch<64, 1, 1>(MKD_ATTN_ARGS);
+  }
+  if (dn <= 48) return launch<48, 2, 2>(MKD_ATTN_ARGS);
+  if (dn <= 64) return launch<64, 2, 2>(MKD_ATTN_ARGS);
+  if (dn <= 80) return launch<80, 2, 1>(MKD_ATTN_ARGS);
+  if (dn <= 128) return launch<128, 2, 1>(MKD_ATTN_ARGS);
+  return launch<160, 1, 1>(MKD_ATTN_ARGS);
+#undef MKD_ATTN_ARGS
 }
 }  // namespace mkd

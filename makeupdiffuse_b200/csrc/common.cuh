@@ -77,6 +77,22 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU for the bf16 path's fused GEGLU epilogue: erf by Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. a
+// GELU error <= 0.75e-7 |x| — four orders below the bf16 rounding of the result) in ~16 instructions, 2 of them MUFU,
+// where erff() costs ~40 and made the FF1 epilogue issue-bound (profiles/r01_ncu_full_ff1.txt).  The fp32 check mode
+// keeps erff().
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);  // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

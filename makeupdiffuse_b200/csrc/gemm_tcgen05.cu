@@ -293,7 +293,7 @@ __device__ __forceinline__ void epilogue_geglu8(const EpiP& e, int m, int row_va
   for (int i = 0; i < 8; ++i) {
     float av = a[i] + (e.bias ? e.bias[row_val + i] : 0.f);
     float gv = g[i] + (e.bias ? e.bias[row_gate + i] : 0.f);
-    r[i] = av * gelu_erf_f(gv);
+    r[i] = av * gelu_erf_fast(gv);
   }
   store8(e.y + (int64_t)m * e.ldy + o, r);
 }
@@ -322,9 +322,12 @@ template <int BN, int CL, int EPI> struct Cfg {
   static constexpr int LDT = PW + 4;                                      // +4 floats: conflict-free phase-1 writes
   static constexpr int STAGE_BYTES = A_BYTES + BN * BK * 2;
   static constexpr int STAGING_BYTES = BM * LDT * 4;
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - STAGING_BYTES;
+  // EPI_STATS: 16 planes (8 channels x {sum, sumsq}) of per-thread column partials, pitch 257 floats
+  static constexpr int STATS_PITCH = 257;
+  static constexpr int SCRATCH_BYTES = EPI == 4 /*EPI_STATS*/ ? 16 * STATS_PITCH * 4 : 0;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - STAGING_BYTES - SCRATCH_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + SCRATCH_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(STAGES >= 3 && SMEM <= 227 * 1024, "shared memory budget");
 };
 __host__ __device__ constexpr int tmem_cols2(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -359,7 +362,8 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
   // address space, so staging accesses compile to LDS/STS instead of generic LD/ST
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + C::STAGING_BYTES);
+  [[maybe_unused]] float* scratch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + C::STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + C::STAGING_BYTES + C::SCRATCH_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
@@ -542,6 +546,24 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
     const int trow_idx = quad * 32 + lane;
     const int g2 = et % NG, rr = et / NG;         // phase-2 column group / first row
     const bool p2_active = et < RPI * NG;
+    // EPI_STATS: column sums of a panel are reduced one barrier LATER (after the next panel's first barrier), out of a
+    // scratch area of their own, so the statistics add no barrier to the drain loop
+    [[maybe_unused]] int pend_mtile = -1, pend_ch0 = 0;
+    [[maybe_unused]] auto reduce_pending = [&]() {
+      constexpr int RP = C::STATS_PITCH;
+      if (et < 4 * PW) {  // 4 lanes per channel: {sum, sumsq} x two row halves; whole warps (PW is a multiple of 8)
+        const int c = et >> 2, stat = (et >> 1) & 1, hf = et & 1;
+        const int plane = stat * 8 + (c & 7), gq = c >> 3;
+        constexpr int HALF = (RPI + 1) / 2;
+        const int r0 = hf * HALF, r1 = hf ? RPI : HALF;
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r) acc += scratch[plane * RP + r * NG + gq];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);             // both row halves
+        const float sq = __shfl_down_sync(0xffffffffu, acc, 2);  // lane 4c gets the sum of squares from lane 4c + 2
+        const int ch = pend_ch0 + c;
+        if ((et & 3) == 0 && ch < ep.N_out) ep.stats[(int64_t)pend_mtile * ep.stats_ld + ch] = make_float2(acc, sq);
+      }
+    };
     int j = 0;
     for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
       const int n_tile = (unit % mp.n_tiles) * CL + (int)cta_rank, rest = unit / mp.n_tiles;
@@ -581,6 +603,9 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
         }
         asm volatile("bar.sync 1, 256;\n" ::: "memory");  // previous panel fully consumed (WAR on the staging panel)
         if (j == 0 && et == 0 && p == 0) MKD_TRACE(9);
+        if constexpr (EPI == EPI_STATS) {
+          if (pend_mtile >= 0) reduce_pending();  // every thread's partials of the previous panel are in `scratch`
+        }
         // ---- phase 1: this thread's accumulator row, column groups g = half, half + 2, ... of the panel ----
         {
           uint32_t r[(NG + 1) / 2][8];
@@ -654,7 +679,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
                 load8(staging + row * LDT + gv * 8, a);
                 load8(staging + row * LDT + (NV + gv) * 8, gt);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) r[k] = (a[k] + bv[k]) * gelu_erf_f(gt[k] + bg[k]);
+                for (int k = 0; k < 8; ++k) r[k] = (a[k] + bv[k]) * gelu_erf_fast(gt[k] + bg[k]);
                 store8(ep.y + (int64_t)m * ep.ldy + n_tile * (BN / 2) + p * (PW / 2) + gv * 8, r);
               }
             }
@@ -709,31 +734,18 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
           }
         }
         if constexpr (EPI == EPI_STATS) {
-          // column sums of this panel: per-thread partials (8 channels x {sum, sumsq}) -> smem (the staging panel is
-          // free once every thread is past phase 2) -> 4 lanes per channel (stat x row half) -> one float2 per channel
-          constexpr int RP = 257;  // pitch of the 16 partial planes: conflict-free writes
-          static_assert(16 * RP <= BM * LDT, "stats scratch must fit the staging panel");
-          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          // this thread's column partials -> scratch (read after the next barrier; the previous reduce, which read
+          // the same scratch, ran before this panel's "staged" barrier, so there is no WAR hazard)
+          constexpr int RP = C::STATS_PITCH;
           if (p2_active) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              staging[k * RP + et] = st_s[k];
-              staging[(8 + k) * RP + et] = st_q[k];
+              scratch[k * RP + et] = st_s[k];
+              scratch[(8 + k) * RP + et] = st_q[k];
             }
           }
-          asm volatile("bar.sync 1, 256;\n" ::: "memory");
-          if (et < 4 * PW) {  // whole warps (PW is a multiple of 8)
-            const int c = et >> 2, stat = (et >> 1) & 1, hf = et & 1;
-            const int plane = stat * 8 + (c & 7), gq = c >> 3;
-            constexpr int HALF = (RPI + 1) / 2;
-            const int r0 = hf * HALF, r1 = hf ? RPI : HALF;
-            float acc = 0.f;
-            for (int r = r0; r < r1; ++r) acc += staging[plane * RP + r * NG + gq];
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);             // both row halves
-            const float sq = __shfl_down_sync(0xffffffffu, acc, 2);  // lane 4c gets the sum of squares from lane 4c + 2
-            const int ch = n_tile * BN + p * PW + c;
-            if ((et & 3) == 0 && ch < ep.N_out) ep.stats[(int64_t)m_tile * ep.stats_ld + ch] = make_float2(acc, sq);
-          }
+          pend_mtile = m_tile;
+          pend_ch0 = n_tile * BN + p * PW;
         }
         if (j == 0 && et == 0 && p == 0) MKD_TRACE(12);
       }
@@ -741,6 +753,10 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
         if (j == 0) MKD_TRACE(6);
         MKD_TRACE(7);
       }
+    }
+    if constexpr (EPI == EPI_STATS) {  // statistics of the very last panel
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      if (pend_mtile >= 0) reduce_pending();
     }
   }
   tcgen05_fence_before();

@@ -235,6 +235,70 @@ __global__ void gn_cluster_kernel(const T* __restrict__ x, TO* __restrict__ y, c
   }
 }
 
+// Small feature maps (8x8, 4x4 levels: C = 1280 / 2560): one CTA per (sample, group).  The group's HW x (C/groups)
+// values (at most GG_VPT vectors of 8 per thread) are read ONCE into registers, block-reduced with an exact two-pass
+// variance, and normalised from registers: one read, one write, no cluster, no workspace.
+constexpr int GG_THREADS = 128, GG_VPT = 5;
+template <typename T, typename TO, bool SILU>
+__global__ void __launch_bounds__(GG_THREADS) gn_group_kernel(const T* __restrict__ x, TO* __restrict__ y,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              int HW, int C, int groups, int ldx, int ldy, float eps) {
+  pdl_wait();
+  __shared__ float red[2][GG_THREADS / 32];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int cgs = C / groups, vpr = cgs / 8, nv = HW * vpr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const T* xb = x + (int64_t)n * HW * ldx + g * cgs;
+  float v[GG_VPT][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < GG_VPT; ++i) {
+    const int idx = threadIdx.x + i * GG_THREADS;
+    if (idx < nv) {
+      load8(xb + (int64_t)(idx / vpr) * ldx + (idx % vpr) * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[0][warp] = s;
+  __syncthreads();
+  const float inv_cnt = 1.0f / (float)(nv * 8);
+  const float mean = (red[0][0] + red[0][1] + red[0][2] + red[0][3]) * inv_cnt;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < GG_VPT; ++i) {
+    if (threadIdx.x + i * GG_THREADS < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  q = warp_sum(q);
+  if (lane == 0) red[1][warp] = q;
+  __syncthreads();
+  const float rstd = rsqrtf((red[1][0] + red[1][1] + red[1][2] + red[1][3]) * inv_cnt + eps);
+  TO* yb = y + (int64_t)n * HW * ldy + g * cgs;
+#pragma unroll
+  for (int i = 0; i < GG_VPT; ++i) {
+    const int idx = threadIdx.x + i * GG_THREADS;
+    if (idx < nv) {
+      const int c = (idx % vpr) * 8;
+      float ga[8], be[8], o[8];
+      load8(gamma + g * cgs + c, ga);
+      load8(beta + g * cgs + c, be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = (v[i][j] - mean) * rstd * ga[j] + be[j];
+        o[j] = SILU ? silu_f(t) : t;
+      }
+      store8(yb + (int64_t)(idx / vpr) * ldy + c, o);
+    }
+  }
+}
+
 // GroupNorm as one streaming pass: the producer's GEMM epilogue already emitted, per 128-row tile and channel, the
 // (sum, sum of squares) of the values it stored (mkd_conv_desc.stats).  Prologue: per-channel totals of this sample
 // (fixed order: deterministic) -> 32 group statistics (one warp per group) -> per-channel scale / shift in smem; then
@@ -380,6 +444,16 @@ static int groupnorm_launch(const T* x, TO* y, int N, int HW, int C, int groups,
   int threads = VX >= 256 ? VX : (256 / VX) * VX;  // whole number of row lanes
   threads = ((threads + 31) / 32) * 32;
   const int RY = threads / VX;
+  if ((C / groups) % 8 == 0 && HW * (C / groups / 8) <= GG_THREADS * GG_VPT && aligned16(gamma) && aligned16(beta)) {
+    // small maps: one CTA per (sample, group), the group lives in registers
+    dim3 grid(groups, N);
+    if (silu)
+      MKD_LAUNCH_OK(launch_pdl(gn_group_kernel<T, TO, true>, grid, dim3(GG_THREADS), 0, st, x, y, gamma, beta, HW, C, groups, ldx, ldy, eps));
+    else
+      MKD_LAUNCH_OK(launch_pdl(gn_group_kernel<T, TO, false>, grid, dim3(GG_THREADS), 0, st, x, y, gamma, beta, HW, C, groups, ldx, ldy, eps));
+    MKD_CHECK_LAUNCH();
+    return MKD_OK;
+  }
   {
     // single-launch cluster path: P = 1, 2, 4 or 8 chunks per sample (one cluster), when that fills enough SMs
     int P = 8;

@@ -118,15 +118,41 @@ class B200ControlLDM:
                 join.record(self._side)
         xin = un._to_nhwc(x_noisy, "x_in")
         slots = un.encode(xin, t, prep["kv_unet"], N, H, W)
+        before_block = None
         if use_cn:
+            nb = len(un.input_blocks)
+            inject = [None] * nb + [slots[nb]] if self.only_mid_control else slots
+            inject_st = un.skip_slot_stats(N, H, W)
             if two_streams:
-                torch.cuda.current_stream().wait_event(join)
+                # The 13 injecting zero-convs stay on the side stream, issued in the order the decoder consumes the
+                # slots (middle output first, then hs.pop() order) with one event each: the decoder's deep, SM-starved
+                # blocks start after the first two and overlap the rest.
+                main = torch.cuda.current_stream()
+                enc_done = torch.cuda.Event()
+                enc_done.record(main)
+                evs = {}
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(enc_done)  # the encoder has written every slot the epilogues add into
+                    for item in sorted(pending, key=lambda p: -p[2]):
+                        if inject[item[2]] is None:
+                            continue
+                        cn.zero_convs([item], N, inject=inject, scales=self.control_scales, inject_st=inject_st)
+                        evs[item[2]] = torch.cuda.Event()
+                        evs[item[2]].record(self._side)
+                    tail = torch.cuda.Event()
+                    tail.record(self._side)
+
+                def before_block(i):  # decoder block i reads slot nb-1-i (block 0 also the injected middle output)
+                    for j in ([nb] if i == 0 else []) + [nb - 1 - i]:
+                        if j in evs:
+                            main.wait_event(evs.pop(j))
+                    if i == nb - 1:
+                        main.wait_event(tail)  # joins the side stream whatever was injected
             else:
                 pending = cn.run_trunk(cn._to_nhwc(x_noisy, "x_in"), prep["hint"], t, prep["kv_cn"], N, H, W)
-            inject = [None] * 12 + [slots[12]] if self.only_mid_control else slots
-            cn.zero_convs(pending, N, inject=inject, scales=self.control_scales, inject_st=un.skip_slot_stats(N, H, W))
+                cn.zero_convs(pending, N, inject=inject, scales=self.control_scales, inject_st=inject_st)
             un.note_slots_rewritten([j for j, s in enumerate(inject) if s is not None], with_stats=True)
-        e = un.decode(prep["kv_unet"], N, H, W)
+        e = un.decode(prep["kv_unet"], N, H, W, before_block=before_block)
         eps = torch.empty(N, un.out_channels, H, W, dtype=torch.float32, device=x_noisy.device)
         ops.nhwc_to_nchw(e, eps)
         if not return_all:

@@ -633,11 +633,14 @@ class B200ControlledUnet(_Net):
         self._slot_ok[-1] = y.st is not None
         return slots
 
-    def decode(self, ctx_kv, N, H, W):
+    def decode(self, ctx_kv, N, H, W, before_block=None):
+        """before_block(i): optional hook run before output block i is enqueued (stream waits on pending injections)"""
         nb = len(self.output_blocks)
         nslots = len(self.input_blocks)
         h_ok = self._slot_ok[nslots]  # statistics of the h half of concat 0 (= the middle-block output)
         for i, blk in enumerate(self.output_blocks):
+            if before_block is not None:
+                before_block(i)
             cat, _, ds = self._cat(i, N, H, W)
             cat_st = self._cat_stats(i, N, H, W)
             if not (h_ok and self._slot_ok[nslots - 1 - i]):

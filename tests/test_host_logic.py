@@ -198,3 +198,22 @@ def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         _lib.load()
+
+
+def test_interpolation_sweep_hints():
+    """configs[4] assembly: reference-major order, source first, wrap-around blend, validation errors"""
+    from makeupdiffuse_b200.sweep import interpolation_cond, interpolation_hints
+    g = torch.Generator().manual_seed(0)
+    src, refs = torch.rand(3, 16, 16, generator=g), torch.rand(8, 3, 16, 16, generator=g)
+    ws = [0.0, 0.25, 0.5, 0.75, 1.0]
+    hint = interpolation_hints(src, refs, ws)
+    assert hint.shape == (40, 6, 16, 16)
+    assert torch.equal(hint[:, :3], src[None].expand(40, -1, -1, -1))
+    assert torch.equal(hint[0, 3:], refs[0]) and torch.equal(hint[4, 3:], refs[1]) and torch.equal(hint[39, 3:], refs[0])
+    torch.testing.assert_close(hint[5 * 3 + 2, 3:], 0.5 * refs[3] + 0.5 * refs[4])
+    cond = interpolation_cond(src, refs, ws, torch.randn(1, 77, 32, generator=g))
+    assert cond["c_crossattn"][0].shape == (40, 77, 32) and cond["c_concat"][0].shape == (40, 6, 16, 16)
+    with pytest.raises(ValueError):
+        interpolation_hints(src, refs, [1.5])
+    with pytest.raises(ValueError):
+        interpolation_hints(torch.rand(2, 3, 16, 16), refs, ws)

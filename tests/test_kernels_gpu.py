@@ -104,7 +104,9 @@ def test_silu_geglu_add(dt):
                                                  (2, 1024, 320, 640, True, 1e-5), (1, 64, 64, 64, True, 1e-5),
                                                  (5, 4096, 320, 320, False, 1e-6), (2, 100, 128, 136, True, 1e-5),
                                                  (16, 1024, 320, 320, True, 1e-5), (16, 256, 1920, 1920, True, 1e-5),
-                                                 (16, 64, 1280, 2560, False, 1e-6), (12, 4096, 320, 320, True, 1e-5)])
+                                                 (16, 64, 1280, 2560, False, 1e-6), (12, 4096, 320, 320, True, 1e-5),
+                                                 (16, 64, 2560, 2560, True, 1e-5), (3, 64, 256, 512, True, 1e-5),
+                                                 (2, 16, 1280, 1280, False, 1e-6)])
 def test_groupnorm(dt, N, HW, C, ld, silu, eps):
     dt, dto = dt if isinstance(dt, tuple) else (dt, dt)  # (fp32 trunk in, bf16 operand out) is the bf16 path's common case
     buf = rnd(N * HW, ld, dt=dt, seed=1) * 1.7 + 0.4

@@ -217,9 +217,33 @@ def test_eta_nonzero_uses_reference_noise_stream(tiny):
     assert rel(out, ref) < 1e-3
 
 
-@pytest.mark.parametrize("h,B", [(32, 2)])
+def test_interpolation_sweep_config5(tiny):
+    """BASELINE.json configs[4]: 1 source x R references x blend weights, 20-step DDIM, one batch through the sampler"""
+    from makeupdiffuse_b200.sweep import interpolation_cond
+    h, S = 16, 20
+    g = torch.Generator(device=DEV).manual_seed(31)
+    src = torch.rand(1, 3, 8 * h, 8 * h, device=DEV, generator=g)
+    refs = torch.rand(2, 3, 8 * h, 8 * h, device=DEV, generator=g)
+    ctx = torch.randn(1, 77, 64, device=DEV, generator=g)
+    cond = interpolation_cond(src, refs, [0.0, 0.5, 1.0], ctx)
+    B = cond["c_concat"][0].shape[0]
+    assert B == 6
+    # w = 1 of reference k is w = 0 of reference k + 1: identical hints -> identical samples
+    assert torch.equal(cond["c_concat"][0][2], cond["c_concat"][0][3])
+    x = torch.randn(1, 4, h, h, device=DEV, generator=g).expand(B, -1, -1, -1).contiguous()
+    with torch.no_grad():
+        ref, _ = MKDDIMSampler(tiny.oracle).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    a, _ = B200DDIMSampler(tiny.f32, use_cuda_graph=True).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    b, _ = B200DDIMSampler(tiny.bf16, use_cuda_graph=True).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    assert torch.equal(a[2], a[3]) and torch.equal(b[2], b[3])
+    p32, p16 = psnr(a, ref), psnr(b, ref)
+    print(f"interpolation sweep (S=20) PSNR vs oracle: fp32-check {p32:.1f} dB, bf16 {p16:.1f} dB")
+    assert p32 > 60 and p16 > 25, (p32, p16)
+
+
+@pytest.mark.parametrize("h,B", [(32, 2), (64, 1)])
 def test_full_size_parity(h, B):
-    """yaml-sized networks (859.5 M + 361.3 M parameters), 256^2 images: teacher-forced eps parity"""
+    """yaml-sized networks (859.5 M + 361.3 M parameters), 256^2 and 512^2 (configs[3]) images: teacher-forced eps parity"""
     full = Bundle({})
     cond, x = make_cond(B, h, 768, seed=1)
     for step in (981, 501, 1):
