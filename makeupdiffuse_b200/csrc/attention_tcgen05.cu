@@ -30,46 +30,53 @@ namespace {
 constexpr int BQ = 128, BKV = 128;
 constexpr int CH = 128 * 128;  // bytes of one [128 rows][64 bf16] chunk
 
-// NWG = softmax warpgroups (128-query tiles) per CTA, ST = K / V ring depth.  Two shapes are used:
-//   <DN, 1, 1>  80 KB of smem and 256 TMEM columns for head dims <= 64: TWO CTAs share an SM, so one CTA's start-up,
-//               barrier round trips and non-exp2 phases are covered by the other's exp2 phase (the MUFU pipe is the
-//               bound of this kernel); also what the small maps and the 77-key cross attention want (more CTAs);
-//   <DN, 2, .>  one CTA per SM with two warpgroups sharing every K / V tile (halves the K/V traffic).
-template <int DN, int NWG_, int ST_> struct ACfg {
+// NWG = softmax warpgroups (128-query tiles) per CTA, KST / VST = K and V ring depths.  Two shapes are used:
+//   <DN, 1, 2, 2>  112 KB of smem and 256 TMEM columns for head dims <= 64: TWO CTAs share an SM, so one CTA's start-up,
+//                  barrier round trips and non-exp2 phases are covered by the other's exp2 phase (the MUFU pipe is the
+//                  bound of this kernel); also what the small maps and the 77-key cross attention want (more CTAs).
+//                  K and V are double-buffered: S(t+1) = Q K(t+1)^T is issued a whole tile ahead, and with single
+//                  slots every TMA round trip (~1 us = one tile of exp2 work) sat on the critical path (profiled: the
+//                  softmax warps spent 27 % of their samples waiting for S, 11 % for O).
+//   <DN, 2, ., .>  one CTA per SM with two warpgroups sharing every K / V tile (halves the K/V traffic).
+template <int DN, int NWG_, int KST_, int VST_> struct ACfg {
   static constexpr int DCH = (DN + 63) / 64;                 // 64-channel chunks of the head dim
-  static constexpr int NWG = NWG_, ST = ST_;
+  static constexpr int NWG = NWG_, KST = KST_, VST = VST_;
   static constexpr int OSTR = (DN + 31) / 32 * 32;           // TMEM column stride between the O accumulators
   static constexpr int TCOLS = NWG * 128 + NWG * OSTR <= 256 ? 256 : 512;
   static constexpr int THREADS = 32 * (4 * NWG + 2);
-  static constexpr int NBAR = 5 * NWG + 4 * ST;              // q_full, s_full, s_free, p_full, o_full | k/v full/empty
-  static constexpr size_t SMEM = (size_t)(NWG * DCH + 2 * ST * DCH + 2 * NWG) * CH + NBAR * 8 + 16 + 1024;
+  static constexpr int NBAR = 5 * NWG + 2 * KST + 2 * VST;   // q_full, s_full, s_free, p_full, o_full | k/v full/empty
+  static constexpr size_t SMEM = (size_t)(NWG * DCH + (KST + VST) * DCH + 2 * NWG) * CH + NBAR * 8 + 16;
   static_assert(NWG * 128 + NWG * OSTR <= 512, "TMEM columns");
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
-template <int DN, int NWG_, int ST_>
-__global__ void __launch_bounds__(ACfg<DN, NWG_, ST_>::THREADS, ACfg<DN, NWG_, ST_>::TCOLS == 256 ? 2 : 1)
+template <int DN, int NWG_, int KST_, int VST_>
+__global__ void __launch_bounds__(ACfg<DN, NWG_, KST_, VST_>::THREADS, ACfg<DN, NWG_, KST_, VST_>::TCOLS == 256 ? 2 : 1)
     attn_tcgen05_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                         const __grid_constant__ CUtensorMap vmap, bf16* __restrict__ o, int Nq, int Nkv, int d, int ldo,
                         float sl2) {
-  using C = ACfg<DN, NWG_, ST_>;
-  constexpr int DCH = C::DCH, NWG = C::NWG, ST = C::ST;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using C = ACfg<DN, NWG_, KST_, VST_>;
+  constexpr int DCH = C::DCH, NWG = C::NWG, KST = C::KST, VST = C::VST;
+  // 128B-swizzle atoms need 1024-byte alignment; the kernel has no static shared memory, so the aligned dynamic array
+  // starts the CTA's window (checked: a misplaced base traps instead of corrupting operands).  No slack bytes: with
+  // 112 KB + barriers two CTAs fit one SM exactly.
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   unsigned char* Qs = smem;                         // [NWG][DCH] chunks
-  unsigned char* Ks = Qs + NWG * DCH * CH;          // [ST][DCH]
-  unsigned char* Vs = Ks + ST * DCH * CH;           // [ST][DCH]
-  unsigned char* Ps = Vs + ST * DCH * CH;           // [NWG][2]  (128 queries x 128 keys bf16)
+  unsigned char* Ks = Qs + NWG * DCH * CH;          // [KST][DCH]
+  unsigned char* Vs = Ks + KST * DCH * CH;          // [VST][DCH]
+  unsigned char* Ps = Vs + VST * DCH * CH;          // [NWG][2]  (128 queries x 128 keys bf16)
   uint64_t* q_full = reinterpret_cast<uint64_t*>(Ps + NWG * 2 * CH);
   uint64_t* s_full = q_full + NWG;
   uint64_t* s_free = s_full + NWG;
   uint64_t* p_full = s_free + NWG;
   uint64_t* o_full = p_full + NWG;
   uint64_t* k_full = o_full + NWG;
-  uint64_t* k_empty = k_full + ST;
-  uint64_t* v_full = k_empty + ST;
-  uint64_t* v_empty = v_full + ST;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + ST);
+  uint64_t* k_empty = k_full + KST;
+  uint64_t* v_full = k_empty + KST;
+  uint64_t* v_empty = v_full + VST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + VST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int W_PROD = 4 * NWG, W_MMA = 4 * NWG + 1;
@@ -88,9 +95,11 @@ __global__ void __launch_bounds__(ACfg<DN, NWG_, ST_>::THREADS, ACfg<DN, NWG_, S
       mbar_init(p_full + i, 4);
       mbar_init(o_full + i, 1);
     }
-    for (int i = 0; i < ST; ++i) {
+    for (int i = 0; i < KST; ++i) {
       mbar_init(k_full + i, 1);
       mbar_init(k_empty + i, 1);
+    }
+    for (int i = 0; i < VST; ++i) {
       mbar_init(v_full + i, 1);
       mbar_init(v_empty + i, 1);
     }
@@ -109,13 +118,13 @@ __global__ void __launch_bounds__(ACfg<DN, NWG_, ST_>::THREADS, ACfg<DN, NWG_, S
         for (int c = 0; c < DCH; ++c) tma_load_4d(&qmap, q_full + wg, Qs + (wg * DCH + c) * CH, c * 64, h, q0 + wg * BQ, b);
       }
       for (int t = 0; t < T; ++t) {
-        const int st = t % ST, u = t / ST;
-        if (t >= ST) mbar_wait(k_empty + st, (u - 1) & 1);
-        mbar_expect_tx(k_full + st, DCH * CH);
-        for (int c = 0; c < DCH; ++c) tma_load_4d(&kmap, k_full + st, Ks + (st * DCH + c) * CH, c * 64, h, t * BKV, b);
-        if (t >= ST) mbar_wait(v_empty + st, (u - 1) & 1);
-        mbar_expect_tx(v_full + st, DCH * CH);
-        for (int c = 0; c < DCH; ++c) tma_load_4d(&vmap, v_full + st, Vs + (st * DCH + c) * CH, c * 64, h, t * BKV, b);
+        const int ks = t % KST, vs = t % VST;
+        if (t >= KST) mbar_wait(k_empty + ks, (t / KST - 1) & 1);
+        mbar_expect_tx(k_full + ks, DCH * CH);
+        for (int c = 0; c < DCH; ++c) tma_load_4d(&kmap, k_full + ks, Ks + (ks * DCH + c) * CH, c * 64, h, t * BKV, b);
+        if (t >= VST) mbar_wait(v_empty + vs, (t / VST - 1) & 1);
+        mbar_expect_tx(v_full + vs, DCH * CH);
+        for (int c = 0; c < DCH; ++c) tma_load_4d(&vmap, v_full + vs, Vs + (vs * DCH + c) * CH, c * 64, h, t * BKV, b);
       }
     }
   } else if (warp == W_MMA) {
@@ -148,10 +157,10 @@ __global__ void __launch_bounds__(ACfg<DN, NWG_, ST_>::THREADS, ACfg<DN, NWG_, S
       }
       commit(k_empty + 0);
       for (int t = 0; t < T; ++t) {
-        const int st = t % ST;
+        const int st = t % VST;
         if (t + 1 < T) {  // S(t+1) as soon as the warpgroup holds S(t) in registers
-          const int st1 = (t + 1) % ST;
-          mbar_wait(k_full + st1, ((t + 1) / ST) & 1);
+          const int st1 = (t + 1) % KST;
+          mbar_wait(k_full + st1, ((t + 1) / KST) & 1);
           for (int wg = 0; wg < nwg; ++wg) {
             mbar_wait(s_free + wg, t & 1);
             fence_after();
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(ACfg<DN, NWG_, ST_>::THREADS, ACfg<DN, NWG_, S
           }
           commit(k_empty + st1);
         }
-        mbar_wait(v_full + st, (t / ST) & 1);
+        mbar_wait(v_full + st, (t / VST) & 1);
         for (int wg = 0; wg < nwg; ++wg) {
           mbar_wait(p_full + wg, t & 1);  // P_wg(t) is in smem and any rescale of O_wg is done
           fence_after();
@@ -311,13 +320,13 @@ int head_map(CUtensorMap* map, const bf16* base, int d, int heads, int ntok, int
   return tma_encode_bf16(map, base, 4, dims, str, box);
 }
 
-template <int DN, int NWG, int ST>
+template <int DN, int NWG, int KST, int VST>
 int launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d, int ldq, int ldk,
            int ldv, int ldo, float scale, cudaStream_t st) {
-  using C = ACfg<DN, NWG, ST>;
+  using C = ACfg<DN, NWG, KST, VST>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_kernel<DN, NWG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_kernel<DN, NWG, KST, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "attention_tcgen05: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
@@ -327,7 +336,7 @@ int launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int head
   if ((rc = head_map(&km, k, d, heads, Nkv, B, ldk))) return rc;
   if ((rc = head_map(&vm, v, d, heads, Nkv, B, ldv))) return rc;
   dim3 grid((Nq + BQ * C::NWG - 1) / (BQ * C::NWG), heads, B);
-  MKD_LAUNCH_OK(launch_pdl(attn_tcgen05_kernel<DN, NWG, ST>, grid, dim3(C::THREADS), C::SMEM, st, qm, km, vm, o, Nq, Nkv, d, ldo,
+  MKD_LAUNCH_OK(launch_pdl(attn_tcgen05_kernel<DN, NWG, KST, VST>, grid, dim3(C::THREADS), C::SMEM, st, qm, km, vm, o, Nq, Nkv, d, ldo,
                            scale * 1.4426950408889634f));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
@@ -362,16 +371,16 @@ int attention_tcgen05(const bf16* q, const bf16* k, const bf16* v, bf16* o, int 
   }
 #define MKD_ATTN_ARGS q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st
   if (dn <= 64 && !pair) {
-    if (dn <= 16) return launch<16, 1, 1>(MKD_ATTN_ARGS);
-    if (dn <= 32) return launch<32, 1, 1>(MKD_ATTN_ARGS);
-    if (dn <= 48) return launch<48, 1, 1>(MKD_ATTN_ARGS);
-    return launch<64, 1, 1>(MKD_ATTN_ARGS);
+    if (dn <= 16) return launch<16, 1, 2, 2>(MKD_ATTN_ARGS);
+    if (dn <= 32) return launch<32, 1, 2, 2>(MKD_ATTN_ARGS);
+    if (dn <= 48) return launch<48, 1, 2, 2>(MKD_ATTN_ARGS);
+    return launch<64, 1, 2, 2>(MKD_ATTN_ARGS);
   }
-  if (dn <= 48) return launch<48, 2, 2>(MKD_ATTN_ARGS);
-  if (dn <= 64) return launch<64, 2, 2>(MKD_ATTN_ARGS);
-  if (dn <= 80) return launch<80, 2, 1>(MKD_ATTN_ARGS);
-  if (dn <= 128) return launch<128, 2, 1>(MKD_ATTN_ARGS);
-  return launch<160, 1, 1>(MKD_ATTN_ARGS);
+  if (dn <= 48) return launch<48, 2, 2, 2>(MKD_ATTN_ARGS);
+  if (dn <= 64) return launch<64, 2, 2, 2>(MKD_ATTN_ARGS);
+  if (dn <= 80) return launch<80, 2, 2, 1>(MKD_ATTN_ARGS);
+  if (dn <= 128) return launch<128, 2, 2, 1>(MKD_ATTN_ARGS);
+  return launch<160, 1, 2, 1>(MKD_ATTN_ARGS);
 #undef MKD_ATTN_ARGS
 }
 }  // namespace mkd

@@ -431,6 +431,74 @@ __global__ void layernorm_kernel(const T* __restrict__ x, TO* __restrict__ y, in
     }
   }
 }
+// LayerNorm for the transformer widths of this model, C = 40 * LPR with LPR = 8 / 16 / 32 lanes per row (C = 320 / 640 /
+// 1280): every lane owns exactly 5 vectors of 8 channels, so all 32 lanes are busy (the generic kernel leaves 24 of 32
+// lanes idle on the second vector of a 320-wide row) and 32 / LPR rows share a warp; 5 independent 32-byte loads in
+// flight per lane; sub-warp shuffles for the statistics (exact two-pass variance).
+template <typename T, typename TO, int LPR>
+__global__ void __launch_bounds__(256) layernorm5_kernel(const T* __restrict__ x, TO* __restrict__ y, int64_t M, int ldx,
+                                                         int ldy, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps) {
+  pdl_wait();
+  constexpr int RPW = 32 / LPR, C = 40 * LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < M;  // inactive lanes still take part in the shuffles
+  float v[5][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    if (ok) load8(x + row * ldx + (sub + i * LPR) * 8, v[i]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / (float)C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[i][j] - mean;
+      q = fmaf(d, d, q);
+    }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / (float)C) + eps);
+  if (!ok) return;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int c = (sub + i * LPR) * 8;
+    float g[8], b[8], o[8];
+    load8(gamma + c, g);
+    load8(beta + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+    store8(y + row * ldy + c, o);
+  }
+}
+
+template <typename T, typename TO>
+static bool layernorm5_launch(const T* x, TO* y, int64_t M, int C, int ldx, int ldy, const float* gamma, const float* beta,
+                              float eps, cudaStream_t st, cudaError_t* err) {
+  const int warps = 8;
+  auto go = [&](auto kernel, int rpw) {
+    const int64_t rows_per_cta = (int64_t)warps * rpw;
+    *err = launch_pdl(kernel, dim3((unsigned)((M + rows_per_cta - 1) / rows_per_cta)), dim3(warps * 32), 0, st, x, y, M, ldx, ldy, gamma, beta, eps);
+    return true;
+  };
+  if (C == 320) return go(layernorm5_kernel<T, TO, 8>, 4);
+  if (C == 640) return go(layernorm5_kernel<T, TO, 16>, 2);
+  if (C == 1280) return go(layernorm5_kernel<T, TO, 32>, 1);
+  return false;
+}
 }  // namespace
 
 extern "C" size_t mkd_groupnorm_workspace_bytes(int N, int groups) {
@@ -590,6 +658,21 @@ extern "C" int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, i
   const int warps = 8;
   int64_t blocks = (M + warps - 1) / warps;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    cudaError_t le = cudaSuccess;
+    bool took = false;
+    if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
+      took = layernorm5_launch((const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps, st, &le);
+    else if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
+      took = layernorm5_launch((const float*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps, st, &le);
+    else if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
+      took = layernorm5_launch((const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps, st, &le);
+    if (took) {
+      MKD_LAUNCH_OK(le);
+      MKD_CHECK_LAUNCH();
+      return MKD_OK;
+    }
+  }
   if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
     MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<bf16, bf16>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps));
   else if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)

@@ -15,8 +15,11 @@ SHAPES = [("self 32x32 d40", 16, 8, 1024, 1024, 40), ("self 16x16 d80", 16, 8, 2
           ("cross 32x32 d40", 16, 8, 1024, 77, 40), ("cross 16x16 d80", 16, 8, 256, 77, 80),
           ("cross 8x8 d160", 16, 8, 64, 77, 160), ("self 64x64 d40 (512^2)", 8, 8, 4096, 4096, 40),
           ("self 32x32 d80 (512^2)", 8, 8, 1024, 1024, 80)]
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
 print("kernel:", os.environ.get("MKD_ATTN", "tcgen05"))
 for name, B, heads, Nq, Nkv, d in SHAPES:
+    if ONLY and ONLY not in name:
+        continue
     C = heads * d
     g = torch.Generator(device=DEV).manual_seed(0)
     if Nq == Nkv:
