@@ -316,6 +316,18 @@ __global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ 
   __shared__ float2 gstat[64];   // (mean, rstd) per group
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int cgs = C / groups, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // the first batch of x loads does not depend on the statistics: issue it before the prologue so that its DRAM / L2
+  // latency overlaps the (dependent, three-barrier) statistics chain
+  const int VX = C / 8, RY = blockDim.x / VX;
+  const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
+  float v[4][8];
+  if (ry < RY) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r0 + ry + u * RY < r1) load8(xb + (int64_t)(r0 + ry + u * RY) * ldx, v[u]);
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float2* p = stats + (int64_t)n * tiles * stats_ld + c;
     float a = 0.f, b = 0.f;
@@ -351,23 +363,20 @@ __global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ 
     shift[c] = beta[c] - ms.x * sc;
   }
   __syncthreads();
-  const int VX = C / 8, RY = blockDim.x / VX;
-  const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
   if (ry >= RY) return;
-  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sc[j] = scale[vx * 8 + j];
     sh[j] = shift[vx * 8 + j];
   }
-  const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
   TO* yb = y + (int64_t)n * HW * ldy + vx * 8;
   for (int r = r0 + ry; r < r1; r += 4 * RY) {
-    float v[4][8];
+    if (r != r0 + ry) {  // (the first batch is already in registers)
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (r + u * RY < r1) load8(xb + (int64_t)(r + u * RY) * ldx, v[u]);
+      for (int u = 0; u < 4; ++u)
+        if (r + u * RY < r1) load8(xb + (int64_t)(r + u * RY) * ldx, v[u]);
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (r + u * RY < r1) {

@@ -438,7 +438,20 @@ class B200ControlNet(_Net):
     def _load_extra(self, g):
         for i in range(8):
             k = f"input_hint_block.{2 * i}"
-            self._put(k + ".w", self._krsc(g(k + ".weight")), True); self._put(k + ".b", g(k + ".bias"))
+            w, b = self._krsc(g(k + ".weight")), g(k + ".bias")
+            self._put(k + ".w", w, True); self._put(k + ".b", b)
+            if self._hi:
+                # bf16 path: the hint block's channel counts (6, 16, 32, 96, 256) are zero-padded to multiples of 64
+                # so that every conv of it runs on the tcgen05 kernel (which wants C % 64 == 0) instead of the
+                # CUDA-core kernel: padded input channels meet zero weights, padded output channels have zero
+                # weights and bias, and SiLU(0) = 0 keeps them zero for the next layer.
+                co, _, _, ci = w.shape
+                cop, cip = -(-co // 64) * 64, -(-ci // 64) * 64
+                wp = torch.zeros(cop, 3, 3, cip, dtype=w.dtype)
+                wp[:co, :, :, :ci] = w
+                bp = torch.zeros(cop, dtype=b.dtype)
+                bp[:co] = b
+                self._put(k + ".wp", wp, True); self._put(k + ".bp", bp)
         for j in range(len(self.input_blocks)):
             k = f"zero_convs.{j}.0"
             self._put(k + ".w", self._krsc(g(k + ".weight")), True); self._put(k + ".b", g(k + ".bias"))
@@ -462,9 +475,12 @@ class B200ControlNet(_Net):
         """input_hint_block(hint): independent of x and t, so computed once per batch of images, not once per step.
         hint: [B, 6, 8h, 8w] fp32 in [0,1] = cat(source, reference) (makeup_diffuse.py:56).  Returns [B*h*w, mc]."""
         B, Cc, H, W = hint.shape
-        cur = self._to_nhwc(hint, "hint_in")
         chans = [c for c, _ in self.HINT] + [self.mc]
         strides = [s for _, s in self.HINT] + [1]
+        pow2 = lambda v: v > 0 and v & (v - 1) == 0  # noqa: E731
+        if self._hi and pow2(H) and pow2(W) and H >= 8 and W >= 8:
+            return self._hint_features_padded(hint, chans, strides)
+        cur = self._to_nhwc(hint, "hint_in")
         for i, (co, s) in enumerate(zip(chans, strides)):
             Ho, Wo = (H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1
             out = self._buf(f"hint_{i}", B * Ho * Wo, co)
@@ -472,6 +488,28 @@ class B200ControlNet(_Net):
                        act=L.ACT_SILU if i < 7 else L.ACT_NONE)
             cur, H, W = out, Ho, Wo
         return cur
+
+    def _hint_features_padded(self, hint, chans, strides):
+        """the hint block on the tensor cores: channel-padded buffers / weights (see _load_extra)"""
+        B, Cc, H, W = hint.shape
+        pad = lambda c: -(-c // 64) * 64  # noqa: E731
+        key = ("hint_in_p", B * H * W, pad(Cc))
+        if key not in self._bufs:
+            self._bufs[key] = torch.zeros(B * H * W, pad(Cc), dtype=self.dtype, device=self._device)  # pad columns stay 0
+        cur = self._bufs[key]
+        ops.nchw_to_nhwc(hint.float().contiguous(), cur[:, :Cc])
+        for i, (co, s) in enumerate(zip(chans, strides)):
+            Ho, Wo = H // s, W // s
+            out = self._buf(f"hint_p{i}", B * Ho * Wo, pad(co))
+            ws = self._ws
+            if s == 2:  # the stride-2 convs run as im2col + GEMM: the im2col matrix lives in the workspace
+                need = B * Ho * Wo * 9 * cur.shape[1] * 2 + (2 << 20)
+                ws = self._buf("hint_ws", 1, -(-need // 4), torch.float32) if need > self._ws.numel() * 4 else self._ws
+            k = f"input_hint_block.{2 * i}"
+            ops.conv2d(cur, self.w[k + ".wp"], out, N=B, H=H, W=W, R=3, S=3, stride=s, pad=1, bias=self.w[k + ".bp"],
+                       workspace=ws, act=L.ACT_SILU if i < 7 else L.ACT_NONE)
+            cur, H, W = out, Ho, Wo
+        return cur[:, :self.mc]
 
     def run_trunk(self, x_nhwc, guided_hint, t, ctx_kv, N, H, W):
         """time embedding + input blocks + middle block.  Returns the 13 pending zero-conv calls

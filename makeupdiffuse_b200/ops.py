@@ -233,7 +233,7 @@ def conv2d(x2d, w, y2d, **kw):
     Hi, Wi = (2 * d.H, 2 * d.W) if d.upsample else (d.H, d.W)
     P, Q = (Hi + 2 * d.pad - d.R) // d.stride + 1, (Wi + 2 * d.pad - d.S) // d.stride + 1
     PROFILE.append({"op": "conv2d", "path": path, "flops": 2.0 * d.N * P * Q * d.K * d.R * d.S * d.C, "M": d.N * P * Q, "K": d.K,
-                    "C": d.C, "R": d.R, "stride": d.stride, "up": d.upsample, "e0": e0, "e1": e1})
+                    "C": d.C, "R": d.R, "stride": d.stride, "up": d.upsample, "e0": e0, "e1": e1, "desc": d})
 
 
 def conv2d_path(x2d, w, y2d, **kw) -> int:
@@ -248,8 +248,18 @@ def run_conv_desc(d: L.ConvDesc):
     L.check(L.load().mkd_conv2d(C.byref(d), _stream()), "conv2d")
 
 
-@_timed("attention", lambda q, k, v, o, **kw: _nb(q, k, v, o))
 def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
+    if PROFILE is None:
+        return _attention(q2d, k2d, v2d, o2d, B=B, heads=heads, Nq=Nq, Nkv=Nkv, d=d, scale=scale)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _attention(q2d, k2d, v2d, o2d, B=B, heads=heads, Nq=Nq, Nkv=Nkv, d=d, scale=scale)
+    e1.record()
+    PROFILE.append({"op": "attention", "bytes": _nb(q2d, k2d, v2d, o2d), "flops": 4.0 * B * heads * Nq * Nkv * d,
+                    "e0": e0, "e1": e1})
+
+
+def _attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
     pq, ldq = _rows(q2d)
     pk, ldk = _rows(k2d)
     pv, ldv = _rows(v2d)

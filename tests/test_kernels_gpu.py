@@ -255,6 +255,10 @@ TC_CASES = [
     dict(N=2, H=16, W=16, C=640, K=640, R=3, residual=True, res32=True, y32="both", ldy_extra=640),  # trunk: slot + fp32
     dict(N=1, H=1, W=300, C=1280, K=320, R=1, residual=True, res32=True),  # ff2: fp32 stream in, bf16 operand out
     dict(N=8, H=4, W=4, C=1280, K=1280, R=3, residual=True, res32=True, y32="both", workspace=True),  # split-K + fp32
+    dict(N=1, H=256, W=256, C=64, K=64, R=3, act=L.ACT_SILU),              # hint block (channel-padded) @256^2: box = half a row
+    dict(N=2, H=256, W=256, C=64, K=64, R=3, stride=2, act=L.ACT_SILU, workspace=True),  # hint stride-2 @256^2
+    dict(N=2, H=64, W=64, C=64, K=128, R=3, stride=2, act=L.ACT_SILU, workspace=True),   # hint 32(+pad) -> 96(+pad)
+    dict(N=2, H=32, W=32, C=256, K=320, R=3),                              # last hint conv
 ]
 
 
