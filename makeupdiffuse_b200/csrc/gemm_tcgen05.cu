@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < 8; ++k) res[u][k] = 0.f;
           const int m = m_base + rr + u * RPI;
-          if (full8 && rr + u * RPI < BM && m < ep.M) {
+          if (full8 && rr + u * RPI < BM && m < ep.M && !(mp.debug & 8)) {
             if (ep.res) {
               if (ep.res_f32) load8(static_cast<const float*>(ep.res) + (int64_t)m * ep.ldr + o, res[u]);
               else load8(static_cast<const bf16*>(ep.res) + (int64_t)m * ep.ldr + o, res[u]);
@@ -711,8 +711,12 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
                     st_q[k] = fmaf(r[k], r[k], st_q[k]);
                   }
                 }
-                if (ep.y32) store8(ep.y32 + (int64_t)m * ep.ldy32 + o, r);
-                if (ep.y) store8(ep.y + (int64_t)m * ep.ldy + o, r);
+                if (!(mp.debug & 4)) {
+                  if (ep.y32) store8(ep.y32 + (int64_t)m * ep.ldy32 + o, r);
+                  if (ep.y) store8(ep.y + (int64_t)m * ep.ldy + o, r);
+                } else if (r[0] == 1234.5f) {  // (debug timing run: keep the math alive without the stores)
+                  ep.y32[0] = r[1];
+                }
               } else {  // ragged channel tail (e.g. the 4-channel `out` conv): scalar, statically indexed
                 const int nimg = ep.emb ? m / ep.pix_per_img : 0;
 #pragma unroll
@@ -1063,7 +1067,8 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     mp.commit_every = ge > 0 ? ge : 1;  // measured: G = 1, 2, 3 give identical k-block times
   }
   {
-    const char* e = g_trace ? getenv("MKD_DEBUG") : nullptr;  // only honoured together with the trace hook
+    // timing experiments (RESULTS INVALID): 1 skip B loads, 2 skip MMA issue, 4 skip epilogue stores, 8 skip residual loads
+    const char* e = getenv("MKD_DEBUG_TIMING");
     mp.debug = e ? atoi(e) : 0;
   }
   mp.num_units = g.m_tiles * n_groups * splits;  // cluster-level work units

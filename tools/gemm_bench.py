@@ -1,5 +1,5 @@
 """Micro-benchmark of the tcgen05 conv/GEMM kernel on the shapes that dominate one UNet+ControlNet eval.
-Back-to-back launches between two CUDA events (no host gaps), L2 kept warm or flushed (--flush)."""
+Back-to-back launches replayed from a CUDA graph between two events (no host gaps), L2 warm or flushed (--flush)."""
 import argparse
 import math
 import sys
@@ -66,23 +66,31 @@ for name, (N, H, W, C, K, R, epi) in SHAPES.items():
     for _ in range(3):
         ops.run_conv_desc(d)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if a.flush:
-        tot = 0.0
-        for _ in range(a.iters):
-            flush.zero_()
-            e0.record()
-            ops.run_conv_desc(d)
-            e1.record()
-            torch.cuda.synchronize()
-            tot += e0.elapsed_time(e1)
-        us = 1e3 * tot / a.iters
-    else:
+    # launches are replayed from a CUDA graph: a Python/ctypes launch costs ~12 us of host time, which would hide every
+    # kernel shorter than that; --flush interleaves a 256 MB memset whose own time is measured and subtracted
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g, gf = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(a.iters):
+                if a.flush:
+                    flush.zero_()
+                ops.run_conv_desc(d)
+        with torch.cuda.graph(gf, stream=side):
+            for _ in range(a.iters):
+                flush.zero_()
+    torch.cuda.current_stream().wait_stream(side)
+
+    def run(graph):
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(a.iters):
-            ops.run_conv_desc(d)
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
-        us = 1e3 * e0.elapsed_time(e1) / a.iters
+        return e0.elapsed_time(e1)
+    us = 1e3 * (run(g) - (run(gf) if a.flush else 0.0)) / a.iters
     fl = 2.0 * M * K * C * R * R
     print(f"{name:14s} M={M:6d} N={K:5d} K={C * R * R:6d} {epi:6s}: {us:8.1f} us  {fl / us / 1e6:8.1f} TFLOP/s", flush=True)
