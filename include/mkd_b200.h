@@ -151,7 +151,8 @@ int mkd_conv2d_path(const mkd_conv_desc* d); /* MKD_PATH_GENERIC or MKD_PATH_TCG
 /* ---- attention (SpatialTransformer attn1 self / attn2 cross; upstream CrossAttention.forward) -------------
  *   O[b, i, h*d:(h+1)*d] = softmax_j( scale * <Q[b,i,h], K[b,j,h]> ) V[b,j,h]      softmax in fp32
  * Q rows: q + (b*Nq + i)*ldq + h*d ; K/V rows: k + (b*Nkv + j)*ldk + h*d (so q/k/v may be column slices of one
- * fused projection buffer).  d % 8 == 0, d <= 160. */
+ * fused projection buffer).  d % 8 == 0, d <= 512: head dims up to 160 (the SpatialTransformer's) run on the tensor
+ * cores in bf16, wider single heads (the VAE decoder's 512-wide mid.attn_1) on the one-warp-per-query SIMT kernel. */
 int mkd_attention(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads, int Nq,
                   int Nkv, int d, int ldq, int ldk, int ldv, int ldo, float scale, mkd_stream_t stream);
 

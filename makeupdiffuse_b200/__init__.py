@@ -5,10 +5,12 @@ Public surface (mirrors the reference's):
     B200ControlLDM       <->  the ControlLDM object the sampler calls apply_model(x_t, t, cond) on
     B200ControlNet       <->  cldm.cldm.ControlNet            (yaml control_stage_config target)
     B200ControlledUnet   <->  cldm.cldm.ControlledUnetModel   (yaml unet_config target)
+    B200FirstStageDecoder <-> first_stage_model.decode of ldm AutoencoderKL (yaml first_stage_config)
 Everything computes through libmkd_b200.so (include/mkd_b200.h); there is no CPU or PyTorch-compute fallback.
 """
 from .ldm import B200ControlLDM  # noqa: F401
 from .nets import B200ControlNet, B200ControlledUnet  # noqa: F401
 from .sampler import B200DDIMSampler  # noqa: F401
+from .vae import B200FirstStageDecoder  # noqa: F401
 
-__all__ = ["B200DDIMSampler", "B200ControlLDM", "B200ControlNet", "B200ControlledUnet"]
+__all__ = ["B200DDIMSampler", "B200ControlLDM", "B200ControlNet", "B200ControlledUnet", "B200FirstStageDecoder"]

@@ -280,13 +280,15 @@ bool attn_force_mma() {
 extern "C" int mkd_attention(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads, int Nq,
                              int Nkv, int d, int ldq, int ldk, int ldv, int ldo, float scale, mkd_stream_t stream) {
   MKD_REQUIRE(q && k && v && o && B > 0 && heads > 0 && Nq > 0 && Nkv > 0 && d > 0, MKD_E_INVALID, "attention: bad args");
-  MKD_REQUIRE(d % 8 == 0 && d <= 160, MKD_E_INVALID, "attention: head dim %d must be a multiple of 8, <= 160", d);
+  // head dims up to 160 (the SpatialTransformer's 40 / 80 / 160) run on the tensor cores; wider single heads (the VAE
+  // decoder's 512-wide mid.attn_1) take the one-warp-per-query SIMT kernel
+  MKD_REQUIRE(d % 8 == 0 && d <= 512, MKD_E_INVALID, "attention: head dim %d must be a multiple of 8, <= 512", d);
   MKD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && aligned16(q) && aligned16(k) &&
                   aligned16(v) && aligned16(o),
               MKD_E_ALIGN, "attention: ld must be multiples of 8 and pointers 16B aligned");
   MKD_REQUIRE(B <= 65535 && heads <= 65535, MKD_E_INVALID, "attention: B/heads too large");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MKD_BF16) {
+  if (dtype == MKD_BF16 && d <= 160) {
     const bf16 *qq = (const bf16*)q, *kk = (const bf16*)k, *vv = (const bf16*)v;
     bf16* oo = (bf16*)o;
     // production path: tcgen05 / TMEM / TMA flash attention (attention_tcgen05.cu); MKD_ATTN=mma selects the older
@@ -306,12 +308,17 @@ extern "C" int mkd_attention(const void* q, const void* k, const void* v, void* 
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   dim3 grid((Nq + warps - 1) / warps, heads, B);
-  MKD_LAUNCH_OK(launch_pdl(attn_simt_kernel<float>, dim3(grid), dim3(warps * 32), smem, st, (const float*)q, (const float*)k, (const float*)v, (float*)o, Nq,
-                                                          Nkv, d, ldq, ldk, ldv, ldo, scale));
+  if (dtype == MKD_BF16)
+    MKD_LAUNCH_OK(launch_pdl(attn_simt_kernel<bf16>, dim3(grid), dim3(warps * 32), smem, st, (const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, Nq,
+                             Nkv, d, ldq, ldk, ldv, ldo, scale));
+  else
+    MKD_LAUNCH_OK(launch_pdl(attn_simt_kernel<float>, dim3(grid), dim3(warps * 32), smem, st, (const float*)q, (const float*)k, (const float*)v, (float*)o, Nq,
+                             Nkv, d, ldq, ldk, ldv, ldo, scale));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }

@@ -159,6 +159,20 @@ class B200ControlLDM:
             return eps
         return eps, self.predict_start_from_noise(x_noisy, t, eps)
 
+    # ---- first stage: diffmk/makeups.py:260-262, diffusion_makeup.py:389,396,409 --------------
+    def attach_first_stage_decoder(self, decoder):
+        """decoder: a loaded ``B200FirstStageDecoder`` (the reference's ``first_stage_model``, decode side only)"""
+        self.first_stage_model = decoder
+        return self
+
+    def decode_first_stage(self, z):
+        """``first_stage_model.decode(1 / scale_factor * z)`` -> NCHW fp32 images in (about) [-1, 1]"""
+        if getattr(self, "first_stage_model", None) is None:
+            raise RuntimeError("no first-stage decoder attached (attach_first_stage_decoder)")
+        return self.first_stage_model.decode(1.0 / self.scale_factor * z)
+
+    decode_latent_code = decode_first_stage  # the reference's other name for it (makeups.py:260)
+
     # ---- x_p entry helpers (diffusion_makeup.py:384-389); latent-sized, outside the 50-step loop ---------------
     @staticmethod
     def _extract(a, t, x):

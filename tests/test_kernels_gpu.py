@@ -363,7 +363,7 @@ def test_conv_stats_rejected_on_generic_path():
                                                (2, 8, 16, 16, 160), (2, 8, 1024, 77, 40), (2, 8, 64, 77, 160),
                                                (1, 4, 100, 77, 16), (1, 4, 64, 64, 32), (2, 2, 200, 130, 64),
                                                (1, 8, 4096, 4096, 40), (2, 8, 300, 300, 8), (1, 3, 513, 257, 96),
-                                               (1, 2, 129, 128, 128)])
+                                               (1, 2, 129, 128, 128), (2, 1, 256, 256, 512)])  # last: the VAE decoder's single 512-wide head (SIMT kernel)
 def test_attention(dt, B, heads, Nq, Nkv, d):
     C = heads * d
     self_attn = Nq == Nkv

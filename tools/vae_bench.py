@@ -1,0 +1,34 @@
+"""Times B200FirstStageDecoder.decode on a batch of 256^2 images (yaml-sized decoder, synthetic seeded weights)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from makeupdiffuse_b200 import B200FirstStageDecoder  # noqa: E402
+from makeupdiffuse_b200.synth import synthetic_state_dict  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+dev = torch.device("cuda", 0)
+m = B200FirstStageDecoder(dtype=torch.bfloat16)
+shapes = m.upstream_shapes()
+from oracle.init import hash_uniform, init_rule  # noqa: E402  (bench tooling only: same seeded init as the tests)
+import zlib  # noqa: E402
+sd = {}
+for k, shp in shapes.items():
+    full = "first_stage_model." + k
+    c, h = init_rule(full, shp)
+    sd[full] = hash_uniform(shp, 0, zlib.crc32(full.encode()), device=dev) * h + c
+m.load_state_dict(sd)
+z = torch.randn(B, 4, 32, 32, device=dev)
+for _ in range(2):
+    out = m.decode(z)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3):
+    out = m.decode(z)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 3
+fl = 1.24e12 * B  # ~1.24 TFLOP per 256^2 image (enumerated from the module tree)
+print(f"decode batch {B} x 256^2: {ms:.2f} ms  ({ms / B:.2f} ms / image), out {tuple(out.shape)} finite={bool(torch.isfinite(out).all())}")
