@@ -117,7 +117,8 @@ def workload_config(args, world):
     B, S, size = args.batch, args.ddim_steps, args.size
     return {"workload": f"{size}x{size}, DDIM-{S} eta 0, ControlNet (6-ch hint) conditioning, no CFG, "
                         f"batch {B} per GPU (global {B * world}), random-init (seeded non-zero) weights of "
-                        "base_diffusion_makeup.yaml = BASELINE.json configs[1]",
+                        "base_diffusion_makeup.yaml = BASELINE.json configs[1]"
+                        + (" + first-stage (VAE) decode of the samples to images" if getattr(args, "decode", False) else ""),
             "parallelism": f"batch-sharded x{world}, one all-gather of final latents",
             "cuda_graph": not args.no_graph,
             "l2": "per-step working set (2.44 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush"}
@@ -156,6 +157,9 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode", action="store_true",
+                    help="also run the first-stage (VAE) decoder on the sampled latents inside every pass (SURVEY 8(f) rank 1; "
+                         "not part of BASELINE.json's metric, so off by default and named in config.workload when on)")
     ap.add_argument("--profile-out", default=None, help="write the per-layer kernel timing table to this file")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -185,6 +189,11 @@ def main():
     model = B200ControlLDM(dtype=torch.bfloat16, device=dev)
     model.load_state_dict(synthetic_state_dict(model, 0, dev))
     sampler = B200DDIMSampler(model, use_cuda_graph=not args.no_graph)
+    if args.decode:
+        from makeupdiffuse_b200 import B200FirstStageDecoder
+        from makeupdiffuse_b200.synth import synthetic_first_stage_state_dict
+        vae = B200FirstStageDecoder(dtype=torch.bfloat16)
+        model.attach_first_stage_decoder(vae.load_state_dict(synthetic_first_stage_state_dict(vae, 0, dev), device=dev))
     data = synthetic_batch(Bg, size, 768, seed=1234, device=dev)  # whole-job batch from one generator, then sliced
     lo, hi = shard_bounds(Bg, rank, world)
     loc = {k: v[lo:hi].contiguous() for k, v in data.items()}
@@ -195,7 +204,10 @@ def main():
     def one_pass_device():
         hint_dev.add_(0.0)  # bump the version: a new batch of images -> hint block + K/V are recomputed every pass
         cond = {"c_crossattn": [ctx_dev], "c_concat": [hint_dev]}
-        return sample_sharded(sampler, S, Bg, (4, h, h), cond, loc["x_T"], rank, world)
+        lat = sample_sharded(sampler, S, Bg, (4, h, h), cond, loc["x_T"], rank, world)
+        if args.decode:  # each rank decodes its own images
+            return model.decode_first_stage(lat[lo:hi])
+        return lat
 
     # host-side (pinned) copies for the end-to-end arm
     pin = {k: loc[k].cpu().pin_memory() for k in ("src", "ref", "ctx", "x_T")}
@@ -204,6 +216,9 @@ def main():
     out_host = torch.empty(B, 4, h, h, dtype=torch.float32).pin_memory()
     h2d = sum(pin[k].numel() * 4 for k in pin)
     d2h = out_host.numel() * 4
+    if args.decode:
+        img_host = torch.empty(B, 3, size, size, dtype=torch.float32).pin_memory()
+        d2h += img_host.numel() * 4
 
     def one_pass_e2e():
         dsrc.copy_(pin["src"], non_blocking=True)
@@ -213,6 +228,8 @@ def main():
         torch.cat([dsrc, dref], 1, out=dhint)
         cond = {"c_crossattn": [dctx], "c_concat": [dhint]}
         out, _ = sampler.sample(S, B, (4, h, h), cond, eta=0.0, x_T=dxt, verbose=False)  # the public API call
+        if args.decode:
+            img_host.copy_(model.decode_first_stage(out), non_blocking=True)
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host

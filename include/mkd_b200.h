@@ -97,6 +97,12 @@ int mkd_groupnorm_apply(const void* x, void* y, int x_dtype, int y_dtype, int N,
 int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,
                   const float* gamma, const float* beta, float eps, mkd_stream_t stream);
 
+/* ---- row softmax y = softmax(scale * x) over the last dim (fp32 statistics) ----------------------------------------
+ * The VAE decoder's mid.attn_1 (upstream AttnBlock: one 512-wide head over all pixels, reached from decode_first_stage,
+ * diffmk/makeups.py:260-262) runs as  S = Q K^T (mkd_conv2d) -> mkd_softmax_rows -> P V (mkd_conv2d).  C <= 2048. */
+int mkd_softmax_rows(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy, float scale,
+                     mkd_stream_t stream);
+
 /* ---- convolution / GEMM family --------------------------------------------------------------------------
  * One descriptor covers every contraction of the path: ResBlock 3x3 convs, Down (stride 2) / Up (nearest x2
  * then 3x3) convs, hint-block convs, 1x1 convs, Linear layers (H=1, W=M, R=S=1) and ControlNet zero-convs:

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "mkd_groupnorm_workspace_bytes": (_sz, [_i, _i]),
     "mkd_groupnorm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _sz, _vp]),
     "mkd_groupnorm_apply": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _i, _vp]),
+    "mkd_softmax_rows": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _f, _vp]),
     "mkd_layernorm": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _vp, _vp, _f, _vp]),
     "mkd_conv2d": (_i, [C.POINTER(ConvDesc), _vp]),
     "mkd_conv2d_path": (_i, [C.POINTER(ConvDesc)]),

@@ -933,10 +933,14 @@ bool geometry(const mkd_conv_desc* d, Geometry& g) {
   return true;
 }
 
-int pick_bn(const mkd_conv_desc* d) {
+int pick_bn(const mkd_conv_desc* d, const Geometry& g) {
   if (d->act == MKD_ACT_GEGLU) return 160;
   if (d->K % 160 == 0) return 160;
   if (d->K % 80 == 0) return 80;
+  // power-of-two widths (the VAE decoder's 128 / 256 / 512 channels): the widest tile that still leaves at least one
+  // work unit per SM — every doubling of the N tile halves the A-tile traffic per FLOP
+  if (d->K % 256 == 0 && (int64_t)g.m_tiles * (d->K / 256) >= 148) return 256;
+  if (d->K % 128 == 0 && (int64_t)g.m_tiles * (d->K / 128) >= 148) return 128;
   if (d->K % 64 == 0) return 64;
   if (d->K <= 32) return 32;
   return 64;  // ragged last tile: B rows beyond K are zero-filled by TMA, stores are masked
@@ -1117,8 +1121,10 @@ int conv2d_tcgen05(const mkd_conv_desc* d, cudaStream_t stream) {
   Geometry g;
   MKD_REQUIRE(geometry(d, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
   const int cl = (d->K > 160) ? cluster_pref() : 1;  // a pair needs two N tiles to share an A tile
-  switch (pick_bn(d)) {
+  switch (pick_bn(d, g)) {
     case 160: return (cl == 2) ? launch<160, 2>(d, g, stream) : launch<160, 1>(d, g, stream);
+    case 256: return launch<256, 1>(d, g, stream);
+    case 128: return launch<128, 1>(d, g, stream);
     case 80: return launch<80, 1>(d, g, stream);
     case 64: return launch<64, 1>(d, g, stream);
     default: return launch<32, 1>(d, g, stream);

@@ -328,15 +328,32 @@ __global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ 
     for (int u = 0; u < 4; ++u)
       if (r0 + ry + u * RY < r1) load8(xb + (int64_t)(r0 + ry + u * RY) * ldx, v[u]);
   }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  // per-channel totals of this sample's tile partials.  When the CTA has more threads than channels, G thread groups
+  // split the tiles (a 256^2 map has 512 of them); fixed partition and fixed summation order: deterministic.
+  const int G = blockDim.x >= 2 * C ? blockDim.x / C : 1;
+  for (int idx = threadIdx.x; idx < G * C; idx += blockDim.x) {
+    const int gq = idx / C, c = idx - gq * C;
     const float2* p = stats + (int64_t)n * tiles * stats_ld + c;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < tiles; ++k) {
+#pragma unroll 4
+    for (int k = gq; k < tiles; k += G) {
       const float2 v = p[(int64_t)k * stats_ld];
       a += v.x;
       b += v.y;
     }
-    csum[c] = make_float2(a, b);
+    csum[idx] = make_float2(a, b);
+  }
+  if (G > 1) {
+    __syncthreads();
+    float a = 0.f, b = 0.f;
+    if (threadIdx.x < C) {
+      for (int gq = 0; gq < G; ++gq) {
+        a += csum[gq * C + threadIdx.x].x;
+        b += csum[gq * C + threadIdx.x].y;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < C) csum[threadIdx.x] = make_float2(a, b);
   }
   __syncthreads();
   const float inv_cnt = 1.0f / ((float)cgs * (float)HW);
@@ -494,6 +511,51 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(const T* __restrict__ x
   }
 }
 
+// Row softmax y = softmax(scale * x) over the last dim, one warp per row (the VAE decoder's single-head attention runs
+// as S = Q K^T (GEMM) -> this -> P V (GEMM); statistics in fp32, exp2 with the scale folded in).
+template <typename T, typename TO>
+__global__ void softmax_rows_kernel(const T* __restrict__ x, TO* __restrict__ y, int64_t M, int C, int ldx, int ldy,
+                                    float scale_log2e) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nv = C / 8;
+  float v[LN_VPL][8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < LN_VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nv) {
+      load8(x + row * ldx + vi * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, v[i][j]);
+    }
+  }
+  mx = warp_max(mx) * scale_log2e;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_VPL; ++i) {
+    if (lane + i * 32 < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] = exp2f(fmaf(v[i][j], scale_log2e, -mx));
+        s += v[i][j];
+      }
+    }
+  }
+  const float inv = 1.0f / warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < LN_VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] *= inv;
+      store8(y + row * ldy + vi * 8, v[i]);
+    }
+  }
+}
+
 template <typename T, typename TO>
 static bool layernorm5_launch(const T* x, TO* y, int64_t M, int C, int ldx, int ldy, const float* gamma, const float* beta,
                               float eps, cudaStream_t st, cudaError_t* err) {
@@ -621,7 +683,7 @@ static int gn_apply_launch(const T* x, TO* y, int N, int HW, int C, int groups, 
   if (nchunks < 1) nchunks = 1;
   const int rows = (HW + nchunks - 1) / nchunks;
   nchunks = (HW + rows - 1) / rows;
-  const size_t smem = (size_t)4 * C * sizeof(float);
+  const size_t smem = (size_t)(2 * C + 2 * (C > threads ? C : threads)) * sizeof(float);  // scale, shift, csum[G][C]
   MKD_REQUIRE(smem <= 48 * 1024, MKD_E_INVALID, "groupnorm_apply: C=%d too large", C);
   dim3 grid(nchunks, N);
   if (silu)
@@ -655,6 +717,29 @@ extern "C" int mkd_groupnorm_apply(const void* x, void* y, int x_dtype, int y_dt
   if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
     return gn_apply_launch<float, float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, st);
   MKD_REQUIRE(false, MKD_E_INVALID, "groupnorm_apply: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
+}
+
+extern "C" int mkd_softmax_rows(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,
+                                float scale, mkd_stream_t stream) {
+  MKD_REQUIRE(x && y && M > 0 && C > 0, MKD_E_INVALID, "softmax_rows: bad args");
+  MKD_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_VPL && scale > 0.f, MKD_E_INVALID,
+              "softmax_rows: C=%d must be a multiple of 8, <= %d; scale must be positive", C, 8 * 32 * LN_VPL);
+  MKD_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), MKD_E_ALIGN,
+              "softmax_rows: ld must be a multiple of 8 and pointers 16B aligned");
+  const int warps = 8;
+  const dim3 grid((unsigned)((M + warps - 1) / warps)), block(warps * 32);
+  const float sl2 = scale * 1.4426950408889634f;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
+    MKD_LAUNCH_OK(launch_pdl(softmax_rows_kernel<float, bf16>, grid, block, 0, st, (const float*)x, (bf16*)y, M, C, ldx, ldy, sl2));
+  else if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
+    MKD_LAUNCH_OK(launch_pdl(softmax_rows_kernel<float, float>, grid, block, 0, st, (const float*)x, (float*)y, M, C, ldx, ldy, sl2));
+  else if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
+    MKD_LAUNCH_OK(launch_pdl(softmax_rows_kernel<bf16, bf16>, grid, block, 0, st, (const bf16*)x, (bf16*)y, M, C, ldx, ldy, sl2));
+  else
+    MKD_REQUIRE(false, MKD_E_INVALID, "softmax_rows: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
 }
 
 extern "C" int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,

@@ -173,6 +173,16 @@ def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
                                    _stream()), "layernorm")
 
 
+@_timed("softmax_rows", lambda x, y, *a, **k: _nb(x, y))
+def softmax_rows(x2d, y2d, scale=1.0):
+    """y = softmax(scale * x) over the last dim (fp32 statistics)"""
+    px, ldx = _rows(x2d)
+    py, ldy = _rows(y2d)
+    M, Cc = x2d.shape
+    assert y2d.shape == x2d.shape
+    L.check(L.load().mkd_softmax_rows(px, py, _dt(x2d), _dt(y2d), M, Cc, ldx, ldy, float(scale), _stream()), "softmax_rows")
+
+
 def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None,
                    residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None,
                    y32=None, stats=None) -> L.ConvDesc:

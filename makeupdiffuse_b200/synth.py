@@ -58,6 +58,12 @@ def synthetic_state_dict(ldm, seed: int = 0, device="cuda") -> dict:
     return sd
 
 
+def synthetic_first_stage_state_dict(decoder, seed: int = 0, device="cuda") -> dict:
+    """upstream-keyed fp32 state dict (``first_stage_model.*``) for a B200FirstStageDecoder"""
+    return {"first_stage_model." + k: synthetic_tensor("first_stage_model." + k, shape, seed, device)
+            for k, shape in decoder.upstream_shapes().items()}
+
+
 def synthetic_batch(B_global: int, image_hw: int = 256, context_dim: int = 768, seed: int = 1234, device="cuda"):
     """Synthetic source / reference pairs, text context and start noise for the WHOLE job, drawn from one seeded
     generator so that results do not depend on how many GPUs share the batch.

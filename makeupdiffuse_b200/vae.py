@@ -8,8 +8,8 @@ Reference surface: ``decode_first_stage(z)`` = ``first_stage_model.decode(1 / sc
 
 Everything runs through the same C-ABI kernels as the denoiser: 3x3 / 1x1 convolutions on the tcgen05 implicit-GEMM
 kernel (the 4 latent channels are zero-padded to 64 for ``conv_in``; nearest x2 upsampling is materialised by the
-library ahead of the conv), GroupNorm(+swish) from statistics fused into the producing epilogue where a sample has at
-most 64 row tiles and the two-phase kernel above that, the residual trunk in fp32 (``nets.Act``).  The single-head
+library ahead of the conv), GroupNorm(+swish) as one streaming pass from statistics fused into the producing epilogue
+(up to 512 row tiles per sample, i.e. 256^2 maps; the two-phase kernel above that), the residual trunk in fp32 (``nets.Act``).  The single-head
 512-wide attention of ``mid.attn_1`` exceeds the tensor-core attention kernel's head-dim range and runs on the SIMT
 kernel.  No PyTorch compute fallback.
 """
@@ -22,7 +22,7 @@ from . import _lib as L
 from . import ops
 from .nets import Act
 
-_MAX_STAT_TILES = 64  # groupnorm_apply sums a sample's tile partials in its prologue: keep that short
+_MAX_STAT_TILES = 512  # groupnorm_apply sums a sample's tile partials in its prologue (512 tiles = a 256^2 map)
 
 
 class B200FirstStageDecoder(nn.Module):
@@ -189,11 +189,36 @@ class B200FirstStageDecoder(nn.Module):
         M = N * H * W
         n = self._buf("at_n", M, c)
         self._gn(x, n, N, self.w[key + ".norm.g"], self.w[key + ".norm.b"], False)
-        qkv = self._buf("at_qkv", M, 3 * c)
-        self._conv(n, key + ".qkv", qkv, N, H, W, 1)
+        HW = H * W
         att = self._buf("at_o", M, c)
-        ops.attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], att, B=N, heads=1, Nq=H * W, Nkv=H * W, d=c,
-                      scale=float(c) ** -0.5)
+        if self._hi and c % 64 == 0 and HW % 64 == 0 and HW <= 2048:
+            # One 512-wide head is outside the flash kernel's head-dim range, but per image it is just two GEMMs around
+            # a row softmax, all on the tensor-core kernel with the projections' outputs used in place as operands:
+            #   S = Q K^T      x = q_b [HW, C],  "weights" = k_b [HW, C]             -> fp32 [HW, HW]
+            #   P = softmax(S / sqrt C)                                               -> bf16 [HW, HW]
+            #   O = P V + b_v  x = P,            "weights" = V^T_b = W_v n_b^T [C, HW] (the v projection with the roles of
+            #                                    activation and weight swapped, so no transpose pass exists; the v bias
+            #                                    is added after P V, exact because the rows of P sum to 1)
+            q, k = self._buf("at_q", M, c), self._buf("at_k", M, c)
+            wq, wk, wv = (self.w[key + ".qkv.w"][i * c:(i + 1) * c] for i in range(3))
+            bq, bk, bv = (self.w[key + ".qkv.b"][i * c:(i + 1) * c] for i in range(3))
+            ops.conv2d(n, wq, q, N=1, H=1, W=M, bias=bq, workspace=self._ws)
+            ops.conv2d(n, wk, k, N=1, H=1, W=M, bias=bk, workspace=self._ws)
+            vt = self._buf("at_vt", c, HW)
+            s32 = self._buf("at_s", HW, HW, torch.float32)
+            p = self._buf("at_p", HW, HW)
+            wv2d = wv.reshape(c, c)
+            for b in range(N):
+                rows = slice(b * HW, (b + 1) * HW)
+                ops.conv2d(wv2d, n[rows], vt, N=1, H=1, W=c, workspace=self._ws)
+                ops.conv2d(q[rows], k[rows], None, N=1, H=1, W=HW, y32=s32, workspace=self._ws)
+                ops.softmax_rows(s32, p, scale=float(c) ** -0.5)
+                ops.conv2d(p, vt, att[rows], N=1, H=1, W=HW, bias=bv, workspace=self._ws)
+        else:
+            qkv = self._buf("at_qkv", M, 3 * c)
+            self._conv(n, key + ".qkv", qkv, N, H, W, 1)
+            ops.attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], att, B=N, heads=1, Nq=HW, Nkv=HW, d=c,
+                          scale=float(c) ** -0.5)
         self._conv(att, key + ".po", y.lo, N, H, W, 1, residual=x.src(), y32=y.hi, stats=y.st)
 
     # ---- first_stage_model.decode -------------------------------------------------------------------------------------

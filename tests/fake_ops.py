@@ -93,6 +93,10 @@ def groupnorm_apply(x2d, y2d, N, gamma, beta, eps, silu, stats, groups=32):
     y2d.copy_(r.reshape(M, C))
 
 
+def softmax_rows(x2d, y2d, scale=1.0):
+    y2d.copy_(torch.softmax(x2d.float() * scale, -1))
+
+
 def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
     y2d.copy_(F.layer_norm(x2d.float(), (x2d.shape[1],), gamma, beta, eps))
 
@@ -140,4 +144,4 @@ def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
 
 
 ALL = ["device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
-       "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "conv2d", "attention"]
+       "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "softmax_rows", "conv2d", "attention"]

@@ -121,6 +121,18 @@ def test_groupnorm(dt, N, HW, C, ld, silu, eps):
     assert rel(y, ref) < tol(dto)
 
 
+@pytest.mark.parametrize("dt", [(F32, BF), F32, BF])
+@pytest.mark.parametrize("M,C,scale", [(1024, 1024, 512 ** -0.5), (77, 256, 0.125), (5, 2048, 1.0), (300, 64, 3.0)])
+def test_softmax_rows(dt, M, C, scale):
+    dt, dto = dt if isinstance(dt, tuple) else (dt, dt)
+    x = rnd(M, C, dt=dt, seed=1) * 4
+    y = torch.empty(M, C, device=DEV, dtype=dto)
+    ops.softmax_rows(x, y, scale)
+    ref = torch.softmax(x.float() * scale, -1)
+    assert rel(y, ref) < tol(dto)
+    assert float((y.float().sum(-1) - 1).abs().max()) < (2e-2 if dto == BF else 1e-5)
+
+
 @pytest.mark.parametrize("dt", [BF, F32, (F32, BF)])
 @pytest.mark.parametrize("M,C", [(1024, 320), (77, 640), (300, 1280), (5, 64)])
 def test_layernorm(dt, M, C):
@@ -259,6 +271,10 @@ TC_CASES = [
     dict(N=2, H=256, W=256, C=64, K=64, R=3, stride=2, act=L.ACT_SILU, workspace=True),  # hint stride-2 @256^2
     dict(N=2, H=64, W=64, C=64, K=128, R=3, stride=2, act=L.ACT_SILU, workspace=True),   # hint 32(+pad) -> 96(+pad)
     dict(N=2, H=32, W=32, C=256, K=320, R=3),                              # last hint conv
+    dict(N=4, H=64, W=64, C=128, K=256, R=3, residual=True, res32=True, y32="both"),  # VAE widths: N tile 128
+    dict(N=8, H=64, W=64, C=64, K=512, R=1),                               # N tile 256
+    dict(N=8, H=64, W=64, C=128, K=256, R=3, emb=True, y32="only"),        # N tile 256, 3x3
+    dict(N=1, H=1, W=1024, C=512, K=1024, R=1, bias=False, y32="only"),    # VAE attention S = Q K^T (weights = keys)
 ]
 
 
@@ -303,6 +319,9 @@ STATS_CASES = [
     dict(N=2, H=16, W=16, C=1280, K=640, R=3, upsample=False, emb=True),     # C_in != C_out
     dict(N=2, H=32, W=32, C=320, K=320, R=3, stride=2),                      # Downsample (im2col + GEMM), 16x16 out
     dict(N=2, H=8, W=8, C=640, K=640, R=3, up=True),                         # Upsample 8 -> 16
+    dict(N=8, H=64, W=64, C=128, K=256, R=3, residual=True),                 # N tile 256 (VAE decoder widths)
+    dict(N=4, H=64, W=64, C=256, K=128, R=3),                                # N tile 128
+    dict(N=1, H=256, W=256, C=128, K=128, R=3),                              # 512 row tiles per sample
 ]
 
 

@@ -5,19 +5,12 @@ import torch
 
 sys.path.insert(0, ".")
 from makeupdiffuse_b200 import B200FirstStageDecoder  # noqa: E402
-from makeupdiffuse_b200.synth import synthetic_state_dict  # noqa: E402
+from makeupdiffuse_b200.synth import synthetic_first_stage_state_dict  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 dev = torch.device("cuda", 0)
 m = B200FirstStageDecoder(dtype=torch.bfloat16)
-shapes = m.upstream_shapes()
-from oracle.init import hash_uniform, init_rule  # noqa: E402  (bench tooling only: same seeded init as the tests)
-import zlib  # noqa: E402
-sd = {}
-for k, shp in shapes.items():
-    full = "first_stage_model." + k
-    c, h = init_rule(full, shp)
-    sd[full] = hash_uniform(shp, 0, zlib.crc32(full.encode()), device=dev) * h + c
+sd = synthetic_first_stage_state_dict(m, 0, dev)
 m.load_state_dict(sd)
 z = torch.randn(B, 4, 32, 32, device=dev)
 for _ in range(2):
