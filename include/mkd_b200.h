@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 3
+#define MKD_ABI_VERSION 4
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmkd_b200.so")
 MKD_BF16, MKD_F32 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class ConvDesc(C.Structure):

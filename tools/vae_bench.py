@@ -23,5 +23,6 @@ for _ in range(3):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
-fl = 1.24e12 * B  # ~1.24 TFLOP per 256^2 image (enumerated from the module tree)
-print(f"decode batch {B} x 256^2: {ms:.2f} ms  ({ms / B:.2f} ms / image), out {tuple(out.shape)} finite={bool(torch.isfinite(out).all())}")
+fl = 0.6222e12 * B  # 0.622 TFLOP per 256^2 image (convs + mid attention, enumerated from the module tree)
+print(f"decode batch {B} x 256^2: {ms:.2f} ms  ({ms / B:.2f} ms / image, {fl / ms / 1e9:.0f} TFLOP/s over the whole decode), "
+      f"out {tuple(out.shape)} finite={bool(torch.isfinite(out).all())}")
