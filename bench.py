@@ -119,7 +119,9 @@ def workload_config(args, world):
                         f"batch {B} per GPU (global {B * world}), random-init (seeded non-zero) weights of "
                         "base_diffusion_makeup.yaml = BASELINE.json configs[1]"
                         + (" + first-stage (VAE) decode of the samples to images" if getattr(args, "decode", False) else ""),
-            "parallelism": f"batch-sharded x{world}, one all-gather of final latents",
+            "parallelism": f"batch-sharded x{world}, one all-gather of final latents"
+                           + (" fused into the last DDIM-update kernel (peer stores)" if getattr(args, "fused_gather", False)
+                              and world > 1 else " (NCCL)" if world > 1 else ""),
             "cuda_graph": not args.no_graph,
             "l2": "per-step working set (2.44 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush"}
 
@@ -157,6 +159,9 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-gather", action="store_true",
+                    help="N > 1: all-gather the final latents with the last DDIM-update kernel's own peer stores "
+                         "(symmetric memory over NVLink) instead of the NCCL collective")
     ap.add_argument("--decode", action="store_true",
                     help="also run the first-stage (VAE) decoder on the sampled latents inside every pass (SURVEY 8(f) rank 1; "
                          "not part of BASELINE.json's metric, so off by default and named in config.workload when on)")
@@ -204,7 +209,7 @@ def main():
     def one_pass_device():
         hint_dev.add_(0.0)  # bump the version: a new batch of images -> hint block + K/V are recomputed every pass
         cond = {"c_crossattn": [ctx_dev], "c_concat": [hint_dev]}
-        lat = sample_sharded(sampler, S, Bg, (4, h, h), cond, loc["x_T"], rank, world)
+        lat = sample_sharded(sampler, S, Bg, (4, h, h), cond, loc["x_T"], rank, world, fused_gather=args.fused_gather)
         if args.decode:  # each rank decodes its own images
             return model.decode_first_stage(lat[lo:hi])
         return lat

@@ -58,6 +58,16 @@ int mkd_ddim_update(const float* x, const float* eps, int cfg, float cfg_scale, 
                     float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef, float sigma_t,
                     float temperature, float* x_prev, float* pred_x0, int64_t n, mkd_stream_t stream);
 
+/* The same update with x_prev written to n_peers (1..8) destinations: x_prev_peers is a HOST array of device pointers,
+ * one per rank of the box, each pointing at this rank's slice inside that rank's gather buffer (peer memory mapped over
+ * NVLink, e.g. torch symmetric memory).  The last step of a batch-sharded run thereby performs the path's only
+ * collective — the all-gather of the final latents — with its own stores; the caller follows it with
+ * a rank barrier.  Values are bit-identical to mkd_ddim_update. */
+int mkd_ddim_update_peers(const float* x, const float* eps, int cfg, float cfg_scale, const float* noise,
+                          float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef, float sigma_t,
+                          float temperature, float* const* x_prev_peers, int n_peers, float* pred_x0, int64_t n,
+                          mkd_stream_t stream);
+
 /* ---- layout / small elementwise ---------------------------------------------------------------------------
  * NCHW fp32 (the reference boundary layout, makeup_diffuse.py:152) <-> NHWC working layout. */
 int mkd_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int C, int H, int W, int ld_dst,

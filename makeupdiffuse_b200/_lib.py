@@ -46,6 +46,7 @@ PROTOTYPES = {
     "mkd_last_error": (C.c_char_p, []),
     "mkd_launch_count": (C.c_longlong, []),
     "mkd_ddim_update": (_i, [_vp, _vp, _i, _f, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp, _i64, _vp]),
+    "mkd_ddim_update_peers": (_i, [_vp, _vp, _i, _f, _vp, _f, _f, _f, _f, _f, _f, _vp, _i, _vp, _i64, _vp]),
     "mkd_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mkd_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mkd_timestep_embedding": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),

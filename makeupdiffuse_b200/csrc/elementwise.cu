@@ -67,6 +67,63 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
+// The same update writing x_prev into the gather buffers of up to 8 ranks (peer memory mapped over NVLink): the final
+// step of a batch-sharded run produces its slice of the all-gathered result directly in every rank's buffer, so the
+// path's only collective needs no separate launch (a signal barrier between the ranks follows on the host side).
+struct PeerPtrs {
+  float* p[8];
+};
+template <int NP>
+__global__ void ddim_update_peers_kernel(const float* __restrict__ x, const float* __restrict__ eps, int cfg,
+                                         float cfg_scale, const float* __restrict__ noise, float s1m, float sqrt_at,
+                                         float sqrt_ap, float dirc, float sigma, float temp, PeerPtrs out,
+                                         float* __restrict__ pred_x0, int64_t n) {
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float e = eps[i];
+    if (cfg) {
+      float ec = eps[n + i];
+      e = __fadd_rn(e, __fmul_rn(cfg_scale, __fsub_rn(ec, e)));
+    }
+    float xv = x[i];
+    float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(s1m, e)), sqrt_at);
+    float xp = __fadd_rn(__fmul_rn(sqrt_ap, p0), __fmul_rn(dirc, e));
+    if (noise) xp = __fadd_rn(xp, __fmul_rn(__fmul_rn(sigma, noise[i]), temp));
+    if (pred_x0) pred_x0[i] = p0;
+#pragma unroll
+    for (int r = 0; r < NP; ++r) out.p[r][i] = xp;
+  }
+}
+
+extern "C" int mkd_ddim_update_peers(const float* x, const float* eps, int cfg, float cfg_scale, const float* noise,
+                                     float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef,
+                                     float sigma_t, float temperature, float* const* x_prev_peers, int n_peers,
+                                     float* pred_x0, int64_t n, mkd_stream_t stream) {
+  MKD_REQUIRE(x && eps && x_prev_peers && n >= 0, MKD_E_INVALID, "ddim_update_peers: null pointer or negative n");
+  MKD_REQUIRE(n_peers >= 1 && n_peers <= 8, MKD_E_INVALID, "ddim_update_peers: n_peers=%d must be 1..8 (one box)", n_peers);
+  PeerPtrs pp;
+  for (int r = 0; r < 8; ++r) pp.p[r] = r < n_peers ? x_prev_peers[r] : nullptr;  // host array of device pointers
+  for (int r = 0; r < n_peers; ++r) MKD_REQUIRE(pp.p[r] != nullptr, MKD_E_INVALID, "ddim_update_peers: null peer pointer %d", r);
+  if (n == 0) return MKD_OK;
+  int threads = 256;
+  int blocks = (int)((n + threads - 1) / threads);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MKD_PEERS_CASE(NP)                                                                                              \
+  case NP:                                                                                                              \
+    MKD_LAUNCH_OK(launch_pdl(ddim_update_peers_kernel<NP>, dim3(blocks), dim3(threads), 0, st, x, eps, cfg, cfg_scale,  \
+                             noise, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_t, temperature, pp,        \
+                             pred_x0, n));                                                                              \
+    break;
+  switch (n_peers) {
+    MKD_PEERS_CASE(1) MKD_PEERS_CASE(2) MKD_PEERS_CASE(3) MKD_PEERS_CASE(4)
+    MKD_PEERS_CASE(5) MKD_PEERS_CASE(6) MKD_PEERS_CASE(7) MKD_PEERS_CASE(8)
+  }
+#undef MKD_PEERS_CASE
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
 extern "C" int mkd_ddim_update(const float* x, const float* eps, int cfg, float cfg_scale, const float* noise,
                                float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef,
                                float sigma_t, float temperature, float* x_prev, float* pred_x0, int64_t n,

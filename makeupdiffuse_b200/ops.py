@@ -66,7 +66,7 @@ def device_ok(device: int = 0):
 
 
 def ddim_update(x, eps, x_prev, *, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_t=0.0, temperature=1.0,
-                noise=None, pred_x0=None, cfg_scale=None):
+                noise=None, pred_x0=None, cfg_scale=None, peer_ptrs=None):
     """eps holds n values, or 2n ([uncond; cond]) when cfg_scale is given  (diffmk/cddim.py:39-40,56-78)."""
     n = x.numel()
     for t in (x, eps, x_prev, noise, pred_x0):
@@ -75,6 +75,13 @@ def ddim_update(x, eps, x_prev, *, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_
     cfg = cfg_scale is not None
     if eps.numel() != (2 * n if cfg else n):
         raise ValueError("eps has the wrong number of elements")
+    if peer_ptrs is not None:  # x_prev goes to every rank's gather buffer (mkd_ddim_update_peers); x_prev = own slice
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        L.check(L.load().mkd_ddim_update_peers(x.data_ptr(), eps.data_ptr(), int(cfg), float(cfg_scale or 0.0), _p(noise),
+                                               float(sqrt_one_minus_at), float(sqrt_at), float(sqrt_a_prev), float(dir_coef),
+                                               float(sigma_t), float(temperature), arr, len(peer_ptrs), _p(pred_x0), n,
+                                               _stream()), "ddim_update_peers")
+        return
     L.check(L.load().mkd_ddim_update(x.data_ptr(), eps.data_ptr(), int(cfg), float(cfg_scale or 0.0), _p(noise),
                                      float(sqrt_one_minus_at), float(sqrt_at), float(sqrt_a_prev), float(dir_coef),
                                      float(sigma_t), float(temperature), x_prev.data_ptr(), _p(pred_x0), n, _stream()),

@@ -176,9 +176,11 @@ class B200DDIMSampler:
     def denoising_step(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
                        temperature=1.0, noise_dropout=0.0, score_corrector=None, corrector_kwargs=None,
                        unconditional_guidance_scale=1.0, unconditional_conditioning=None, dynamic_threshold=None,
-                       out=None):
+                       out=None, peer_ptrs=None):
         """``out`` (extension, optional): tensor that receives x_prev — e.g. this rank's slice of an all-gather
-        buffer, so the last update of a sharded run lands directly where the collective reads it."""
+        buffer, so the last update of a sharded run lands directly where the collective reads it.
+        ``peer_ptrs`` (extension, optional): device pointers of that same slice inside EVERY rank's gather buffer (peer
+        memory); the update kernel then stores x_prev to all of them — the all-gather fused into the kernel."""
         m = self.model
         if m.parameterization != "eps":
             raise NotImplementedError("B200 path implements the yaml's parameterization: eps (yaml:50)")
@@ -217,7 +219,7 @@ class B200DDIMSampler:
         x_prev, pred_x0 = (torch.empty_like(x) if out is None else out), torch.empty_like(x)
         ops.ddim_update(x, e.contiguous(), x_prev, sqrt_one_minus_at=s1m, sqrt_at=sq_at, sqrt_a_prev=sq_ap, dir_coef=dirc,
                         sigma_t=sigma, temperature=temperature, noise=noise, pred_x0=pred_x0,
-                        cfg_scale=float(unconditional_guidance_scale) if cfg else None)
+                        cfg_scale=float(unconditional_guidance_scale) if cfg else None, peer_ptrs=peer_ptrs)
         return x_prev, pred_x0
 
     # ---- truncated reverse loop from a caller-supplied x_t: diffmk/cddim.py:81-100 -------------------------------

@@ -18,7 +18,8 @@ def groupnorm_workspace_bytes(N, groups=32):
 
 
 def ddim_update(x, eps, x_prev, *, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_t=0.0, temperature=1.0,
-                noise=None, pred_x0=None, cfg_scale=None):
+                noise=None, pred_x0=None, cfg_scale=None, peer_ptrs=None):
+    assert peer_ptrs is None, "peer stores need real GPUs"
     f = lambda v: torch.tensor(v, dtype=torch.float32)  # noqa: E731
     e = eps
     if cfg_scale is not None:

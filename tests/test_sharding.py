@@ -68,3 +68,47 @@ def test_two_rank_gloo_equals_single_process(tmp_path):
     with torch.no_grad():
         ref, _ = s.sample(S, BG, (4, H, H), cond, eta=0.0, x_T=d["x_T"], verbose=False)
     assert float((r0 - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+
+
+# ---- 2 x B200: NCCL all-gather vs the gather fused into the last DDIM-update kernel (peer stores) -------------------
+def _gpu_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from makeupdiffuse_b200 import B200ControlLDM, B200DDIMSampler
+    from makeupdiffuse_b200.dist import sample_sharded
+    from makeupdiffuse_b200.synth import synthetic_state_dict
+    params = dict(model_channels=64, num_heads=4, context_dim=64)
+    m = B200ControlLDM(params, params, dtype=torch.bfloat16, device=dev)
+    m.load_state_dict(synthetic_state_dict(m, 0, dev))
+    s = B200DDIMSampler(m)
+    g = torch.Generator(device=dev).manual_seed(7)
+    bg, h = 4, 16
+    ctx = torch.randn(bg, 77, 64, device=dev, generator=g)
+    hint = torch.rand(bg, 6, 8 * h, 8 * h, device=dev, generator=g)
+    xT = torch.randn(bg, 4, h, h, device=dev, generator=g)
+    lo, hi = shard_bounds(bg, rank, world)
+    cond = {"c_crossattn": [ctx[lo:hi].contiguous()], "c_concat": [hint[lo:hi].contiguous()]}
+    res = {}
+    for name, fused in (("nccl", False), ("fused", True), ("fused_again", True)):
+        res[name] = sample_sharded(s, 4, bg, (4, h, h), cond, xT[lo:hi].contiguous(), rank, world, fused_gather=fused).cpu()
+    full_cond = {"c_crossattn": [ctx], "c_concat": [hint]}
+    res["single"], _ = s.sample(4, bg, (4, h, h), full_cond, eta=0.0, x_T=xT, verbose=False)
+    res["single"] = res["single"].cpu()
+    torch.save(res, os.path.join(out_dir, f"g{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs of one box")
+def test_two_gpu_fused_gather_equals_nccl(tmp_path):
+    port = 29600 + os.getpid() % 2000
+    mp.spawn(_gpu_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
+    for r in (r0, r1):
+        assert torch.equal(r["nccl"], r["fused"]) and torch.equal(r["fused"], r["fused_again"])
+    assert torch.equal(r0["fused"], r1["fused"])
+    # batch rows are independent but a rank's kernels see a different batch size than the single-process run
+    # (tile / split-K choices differ), so this comparison is numerical, not bitwise
+    assert float((r0["fused"] - r0["single"]).abs().max()) < 0.05 * float(r0["single"].abs().max())
