@@ -66,10 +66,15 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 // slot layout per CTA (16 x u64): 0 entry, 1 prologue done, 2 first TMA issued, 3 first full barrier, 4 unit-0 MMAs
 // committed, 5 unit-0 accumulator ready (epilogue), 6 unit-0 epilogue done, 7 last unit epilogue done, 8 exit
+// (compiled in only with -DMKD_ENABLE_TRACE, i.e. `MKD_TRACE=1 python -m makeupdiffuse_b200.build --force`)
+#ifdef MKD_ENABLE_TRACE
 #define MKD_TRACE(slot)                                                     \
   do {                                                                      \
     if (mp.trace) mp.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer();    \
   } while (0)
+#else
+#define MKD_TRACE(slot) do { } while (0)
+#endif
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -1,4 +1,5 @@
-"""Per-role %globaltimer timeline of one tcgen05 GEMM launch (debug hook mkd_debug_set_trace)."""
+"""Per-role %globaltimer timeline of one tcgen05 GEMM launch (debug hook mkd_debug_set_trace).
+Needs a library built with the stamps compiled in:  MKD_TRACE=1 python -m makeupdiffuse_b200.build --force"""
 import ctypes
 import math
 import sys
