@@ -72,8 +72,10 @@ __device__ __forceinline__ unsigned long long gtimer() {
   do {                                                                      \
     if (mp.trace) mp.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer();    \
   } while (0)
+#define MKD_DEBUG_BIT(bit) (mp.debug & (bit))  // timing experiments (tools/dbg_epilogue.sh), same build flag
 #else
 #define MKD_TRACE(slot) do { } while (0)
+#define MKD_DEBUG_BIT(bit) false
 #endif
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
               }
               if (first) MKD_TRACE(2);
             } else {
-              if (mp.debug & 1) mbar_arrive(full_bar + s);
+              if (MKD_DEBUG_BIT(1)) mbar_arrive(full_bar + s);
               else {
                 mbar_expect_tx(full_bar + s, STAGE_BYTES - A_BYTES);
                 tma_load_2d(&bmap, full_bar + s, sa + A_BYTES, kb * BK, nb);
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
             if (first) MKD_TRACE(3);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              if (mp.debug & 2) break;
+              if (MKD_DEBUG_BIT(2)) break;
               // advance K inside the 128-byte swizzle atom: +32 bytes per UMMA_K (encoded >> 4)
               umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > kb0 || k) ? 1u : 0u);
             }
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < 8; ++k) res[u][k] = 0.f;
           const int m = m_base + rr + u * RPI;
-          if (full8 && rr + u * RPI < BM && m < ep.M && !(mp.debug & 8)) {
+          if (full8 && rr + u * RPI < BM && m < ep.M && !MKD_DEBUG_BIT(8)) {
             if (ep.res) {
               if (ep.res_f32) load8(static_cast<const float*>(ep.res) + (int64_t)m * ep.ldr + o, res[u]);
               else load8(static_cast<const bf16*>(ep.res) + (int64_t)m * ep.ldr + o, res[u]);
@@ -716,13 +718,16 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
                     st_q[k] = fmaf(r[k], r[k], st_q[k]);
                   }
                 }
-                if (!(mp.debug & 4)) {
+                if (!MKD_DEBUG_BIT(4)) {
                   if (ep.y32) store8(ep.y32 + (int64_t)m * ep.ldy32 + o, r);
                   if (ep.y) store8(ep.y + (int64_t)m * ep.ldy + o, r);
                 } else if (r[0] == 1234.5f) {  // (debug timing run: keep the math alive without the stores)
                   ep.y32[0] = r[1];
                 }
-              } else {  // ragged channel tail (e.g. the 4-channel `out` conv): scalar, statically indexed
+              } else if constexpr (BN == 32) {
+                // ragged channel tail (the 4-channel `out` conv, the VAE's 3-channel conv_out): scalar, statically
+                // indexed.  Only K < 16 can leave a partial 8-channel group and such filters always take the N = 32
+                // tile, so the wider instantiations do not carry this block (the epilogue is sensitive to code size).
                 const int nimg = ep.emb ? m / ep.pix_per_img : 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {

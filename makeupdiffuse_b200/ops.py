@@ -49,7 +49,8 @@ def _timed(name, nbytes_fn=None):
             e0.record()
             r = fn(*a, **kw)
             e1.record()
-            PROFILE.append({"op": name, "bytes": nbytes_fn(*a, **kw) if nbytes_fn else 0, "e0": e0, "e1": e1})
+            PROFILE.append({"op": name, "bytes": nbytes_fn(*a, **kw) if nbytes_fn else 0, "e0": e0, "e1": e1,
+                            "replay": (fn, a, kw)})
             return r
         wrapper.__name__ = fn.__name__
         wrapper.__doc__ = fn.__doc__
@@ -273,7 +274,8 @@ def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
     _attention(q2d, k2d, v2d, o2d, B=B, heads=heads, Nq=Nq, Nkv=Nkv, d=d, scale=scale)
     e1.record()
     PROFILE.append({"op": "attention", "bytes": _nb(q2d, k2d, v2d, o2d), "flops": 4.0 * B * heads * Nq * Nkv * d,
-                    "e0": e0, "e1": e1})
+                    "e0": e0, "e1": e1,
+                    "replay": (_attention, (q2d, k2d, v2d, o2d), dict(B=B, heads=heads, Nq=Nq, Nkv=Nkv, d=d, scale=scale))})
 
 
 def _attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
