@@ -114,9 +114,9 @@ class B200ControlLDM:
             fork.record(main)
             self._side.wait_event(fork)
             with torch.cuda.stream(self._side):
-                pending = cn.run_trunk(cn._to_nhwc(x_noisy, "x_in"), prep["hint"], t, prep["kv_cn"], N, H, W)
+                pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W)
                 join.record(self._side)
-        xin = un._to_nhwc(x_noisy, "x_in")
+        xin = un._x_in(x_noisy)
         slots = un.encode(xin, t, prep["kv_unet"], N, H, W)
         before_block = None
         if use_cn:
@@ -149,7 +149,7 @@ class B200ControlLDM:
                     if i == nb - 1:
                         main.wait_event(tail)  # joins the side stream whatever was injected
             else:
-                pending = cn.run_trunk(cn._to_nhwc(x_noisy, "x_in"), prep["hint"], t, prep["kv_cn"], N, H, W)
+                pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W)
                 cn.zero_convs(pending, N, inject=inject, scales=self.control_scales, inject_st=inject_st)
             un.note_slots_rewritten([j for j, s in enumerate(inject) if s is not None], with_stats=True)
         e = un.decode(prep["kv_unet"], N, H, W, before_block=before_block)

@@ -129,7 +129,14 @@ class _Net(nn.Module):
         emb_w, emb_b = [], []
         for layer in self._all_layers():
             kind, key = layer[0], layer[1]
-            if kind in ("conv_in", "down", "up"):
+            if kind == "conv_in" and self._hi:
+                # bf16 path: the 4 latent channels are zero-padded to 64 so that conv_in runs on the tensor-core kernel
+                # (which wants C % 64 == 0) and emits GroupNorm statistics like every other trunk producer
+                w = self._krsc(g(key + ".weight"))
+                wp = torch.zeros(w.shape[0], 3, 3, 64, dtype=w.dtype)
+                wp[..., :w.shape[3]] = w
+                self._put(key + ".w", wp, True); self._put(key + ".b", g(key + ".bias"))
+            elif kind in ("conv_in", "down", "up"):
                 self._put(key + ".w", self._krsc(g(key + ".weight")), True); self._put(key + ".b", g(key + ".bias"))
             elif kind == "res":
                 self._put(key + ".gn1.g", g(key + ".in_layers.0.weight")); self._put(key + ".gn1.b", g(key + ".in_layers.0.bias"))
@@ -274,8 +281,7 @@ class _Net(nn.Module):
         e1 = self._buf("te1", B, self.ted)
         self._linear(te, "te0", e1, act=L.ACT_SILU)
         e2 = self._buf("te2", B, self.ted)
-        self._linear(e1, "te2", e2)
-        ops.silu(e2, e2)  # every consumer (ResBlock.emb_layers) starts with SiLU
+        self._linear(e1, "te2", e2, act=L.ACT_SILU)  # every consumer (ResBlock.emb_layers) starts with SiLU: fused here
         ea = self._buf("emb_all", B, self._emb_total)
         self._linear(e2, "emb_all", ea)
         return ea
@@ -369,6 +375,18 @@ class _Net(nn.Module):
                 out[layer[1]] = kv
         return out
 
+    def _x_in(self, x):
+        """the latent x_t as conv_in's NHWC operand: [B*H*W, 64] with zero pad channels (bf16 path) or [.., 4] (check mode)"""
+        if not self._hi:
+            return self._to_nhwc(x, "x_in")
+        B, Cc, H, W = x.shape
+        key = ("x_in_p", B * H * W, 64)
+        if key not in self._bufs:
+            self._bufs[key] = torch.zeros(B * H * W, 64, dtype=self.dtype, device=self._device)  # pad columns stay 0
+        buf = self._bufs[key]
+        ops.nchw_to_nhwc(x.float().contiguous(), buf[:, :Cc])
+        return buf
+
     def _to_nhwc(self, x, name):
         B, Cc, H, W = x.shape
         buf = self._buf(name, B * H * W, (Cc + 7) // 8 * 8)
@@ -401,8 +419,10 @@ class _Net(nn.Module):
             else:
                 out = y
             if kind == "conv_in":
-                out.st = None  # C = 4 runs on the generic kernel, which emits no statistics
-                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, residual=conv_in_residual, y32=out.hi)
+                pow2 = H & (H - 1) == 0 and W & (W - 1) == 0
+                if not (self._hi and pow2):
+                    out.st = None  # the generic kernel (check mode / odd sizes) emits no statistics
+                self._conv(cur.lo, layer[1], out.lo, N, H, W, R=3, residual=conv_in_residual, y32=out.hi, stats=out.st)
             elif kind == "res":
                 self._res(layer, cur, out, emb_all, N, H, W)
             elif kind == "st":
@@ -559,7 +579,7 @@ class B200ControlNet(_Net):
         """Reference call form (makeup_diffuse.py:164): returns the 13 control residuals as NCHW fp32 tensors."""
         assert self._loaded, "load_state_dict() first"
         N, _, H, W = x.shape
-        xin = self._to_nhwc(x, "x_in")
+        xin = self._x_in(x)
         outs = self.run(xin, self.hint_features(hint), timesteps.to(torch.int64).contiguous(),
                         self.context_kv(context), N, H, W)
         res = []
@@ -705,7 +725,7 @@ class B200ControlledUnet(_Net):
         assert self._loaded, "load_state_dict() first"
         N, _, H, W = x.shape
         ctx_kv = self.context_kv(context)
-        xin = self._to_nhwc(x, "x_in")
+        xin = self._x_in(x)
         slots = self.encode(xin, timesteps.to(torch.int64).contiguous(), ctx_kv, N, H, W)
         if control is not None:
             idx = [len(slots) - 1] if only_mid_control else range(len(slots))
