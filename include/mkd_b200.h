@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 4
+#define MKD_ABI_VERSION 5
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 
@@ -159,6 +159,9 @@ typedef struct mkd_conv_desc {
    * row (stats_ld > K) the same way `y` may point into a concat buffer.  Not available on the generic path. */
   float* stats;
   int stats_ld;
+  /* extra zero padding on the bottom / right edge only (0 or 1).  The VAE encoder's Downsample is
+   * F.pad(x, (0,1,0,1)) followed by a 3x3 stride-2 conv without padding: pad = 0, pad_hi_extra = 1. */
+  int pad_hi_extra;
 } mkd_conv_desc;
 
 int mkd_conv2d(const mkd_conv_desc* d, mkd_stream_t stream);

@@ -11,6 +11,6 @@ Everything computes through libmkd_b200.so (include/mkd_b200.h); there is no CPU
 from .ldm import B200ControlLDM  # noqa: F401
 from .nets import B200ControlNet, B200ControlledUnet  # noqa: F401
 from .sampler import B200DDIMSampler  # noqa: F401
-from .vae import B200FirstStageDecoder  # noqa: F401
+from .vae import B200FirstStageDecoder, B200FirstStageEncoder  # noqa: F401
 
-__all__ = ["B200DDIMSampler", "B200ControlLDM", "B200ControlNet", "B200ControlledUnet", "B200FirstStageDecoder"]
+__all__ = ["B200DDIMSampler", "B200ControlLDM", "B200ControlNet", "B200ControlledUnet", "B200FirstStageDecoder", "B200FirstStageEncoder"]

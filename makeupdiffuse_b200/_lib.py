@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmkd_b200.so")
 MKD_BF16, MKD_F32 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class ConvDesc(C.Structure):
@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ("residual_dtype", C.c_int), ("ldy32", C.c_int), ("y32", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("stats", C.c_void_p), ("stats_ld", C.c_int),
+        ("pad_hi_extra", C.c_int),
     ]
 
 

@@ -155,8 +155,8 @@ int conv2d_generic(const mkd_conv_desc* d, cudaStream_t stream) {
   p.stride = d->stride; p.pad = d->pad; p.up = d->upsample ? 1 : 0;
   p.Hin = p.up ? 2 * d->H : d->H;
   p.Win = p.up ? 2 * d->W : d->W;
-  p.P = (p.Hin + 2 * p.pad - p.R) / p.stride + 1;
-  p.Q = (p.Win + 2 * p.pad - p.S) / p.stride + 1;
+  p.P = (p.Hin + 2 * p.pad + d->pad_hi_extra - p.R) / p.stride + 1;  // (the kernel bounds-checks every tap)
+  p.Q = (p.Win + 2 * p.pad + d->pad_hi_extra - p.S) / p.stride + 1;
   p.ldx = d->ldx; p.ldy = d->ldy; p.ldr = d->ldr; p.lde = d->lde;
   p.Ktot = p.R * p.S * p.C;
   p.M = p.N * p.P * p.Q;
@@ -198,7 +198,7 @@ static int validate(const mkd_conv_desc* d) {
   MKD_REQUIRE(d->x && d->w && (d->y || d->y32), MKD_E_INVALID, "conv2d: null x/w/y");
   MKD_REQUIRE(d->residual_dtype == MKD_BF16 || d->residual_dtype == MKD_F32, MKD_E_INVALID, "conv2d: bad residual_dtype");
   MKD_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0 && d->stride > 0 &&
-                  d->pad >= 0,
+                  d->pad >= 0 && d->pad_hi_extra >= 0 && d->pad_hi_extra <= 1,
               MKD_E_INVALID, "conv2d: non-positive dimension");
   MKD_REQUIRE(d->ldx >= d->C, MKD_E_INVALID, "conv2d: ldx %d < C %d", d->ldx, d->C);
   const int kout = d->act == MKD_ACT_GEGLU ? d->K / 2 : d->K;
@@ -213,7 +213,8 @@ static int validate(const mkd_conv_desc* d) {
     MKD_REQUIRE(!d->emb && !d->residual && d->alpha == 1.0f, MKD_E_INVALID, "conv2d: GEGLU excludes emb/residual/alpha");
   }
   const int Hin = d->upsample ? 2 * d->H : d->H, Win = d->upsample ? 2 * d->W : d->W;
-  MKD_REQUIRE(Hin + 2 * d->pad >= d->R && Win + 2 * d->pad >= d->S, MKD_E_INVALID, "conv2d: filter larger than input");
+  MKD_REQUIRE(Hin + 2 * d->pad + d->pad_hi_extra >= d->R && Win + 2 * d->pad + d->pad_hi_extra >= d->S, MKD_E_INVALID,
+              "conv2d: filter larger than input");
   MKD_REQUIRE((int64_t)d->N * Hin * Win < (1ll << 31), MKD_E_INVALID, "conv2d: too many pixels");
   MKD_REQUIRE(d->path >= MKD_PATH_AUTO && d->path <= MKD_PATH_TCGEN05, MKD_E_INVALID, "conv2d: bad path");
   return MKD_OK;

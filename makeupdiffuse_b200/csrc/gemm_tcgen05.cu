@@ -840,7 +840,8 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__
 }
 // im2col for the three stride-2 Downsample convs: out[m, (r*3+s)*C + c] = in[n, 2p-1+r, 2q-1+s, c] (0 outside).
 // The outputs are 4x smaller than the inputs, so the 9x expansion costs little and the conv becomes a plain GEMM.
-__global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int ldx) {
+__global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int ldx,
+                                 int pad) {
   pdl_wait();
   const int vpr = C / 8, P = H / 2, Q = W / 2;
   const int64_t total = (int64_t)N * P * Q * 9 * vpr;
@@ -852,7 +853,7 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
     const int q = (int)(t % Q);
     t /= Q;
     const int p = (int)(t % P), n = (int)(t / P);
-    const int ih = 2 * p - 1 + tap / 3, iw = 2 * q - 1 + tap % 3;
+    const int ih = 2 * p - pad + tap / 3, iw = 2 * q - pad + tap % 3;  // pad 1: UNet Downsample; pad 0: VAE (pad at the far edge)
     uint4 val = make_uint4(0, 0, 0, 0);
     if (ih >= 0 && ih < H && iw >= 0 && iw < W)
       val = *reinterpret_cast<const uint4*>(x + ((int64_t)(n * H + ih) * W + iw) * ldx + v * 8);
@@ -898,11 +899,16 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 bool geometry(const mkd_conv_desc* d, Geometry& g) {
   if (d->dtype != MKD_BF16) { set_error("dtype is not bf16"); return false; }
   if (d->C % BK != 0) { set_error("C=%d is not a multiple of 64", d->C); return false; }
-  if (d->R != d->S || (d->R != 1 && d->R != 3) || d->pad != d->R / 2) { set_error("filter is not 1x1/p0 or 3x3/p1"); return false; }
+  const bool vae_down = d->R == 3 && d->S == 3 && d->stride == 2 && d->pad == 0 && d->pad_hi_extra == 1;
+  if (!vae_down && (d->R != d->S || (d->R != 1 && d->R != 3) || d->pad != d->R / 2 || d->pad_hi_extra != 0)) {
+    set_error("filter is not 1x1/p0, 3x3/p1 or 3x3/s2 with far-edge padding");
+    return false;
+  }
   if (d->stride != 1 || d->upsample) {
     // Downsample (3x3 stride 2) and Upsample (nearest x2 + 3x3) run as: materialise (im2col / upsampled copy) into the
     // workspace, then the ordinary tensor-core kernel.  Needs the workspace and even, power-of-two sizes.
-    const bool down = d->stride == 2 && !d->upsample && d->R == 3 && d->H % 2 == 0 && d->W % 2 == 0;
+    const bool down = d->stride == 2 && !d->upsample && d->R == 3 && d->H % 2 == 0 && d->W % 2 == 0 &&
+                      d->pad + d->pad_hi_extra == 1;  // p1 (UNet) or p0 + one far-edge row/column (VAE encoder)
     const bool up = d->stride == 1 && d->upsample && d->R == 3;
     if (!down && !up) { set_error("stride %d / upsample %d conv is not a Downsample/Upsample shape", d->stride, d->upsample); return false; }
     const size_t need = down ? (size_t)d->N * (d->H / 2) * (d->W / 2) * 9 * d->C * 2 : (size_t)d->N * 4 * d->H * d->W * d->C * 2;
@@ -979,7 +985,7 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     int blocks = (int)((vecs + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (down)
-      MKD_LAUNCH_OK(launch_pdl(im2col_s2_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx));
+      MKD_LAUNCH_OK(launch_pdl(im2col_s2_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx, d_in->pad));
     else
       MKD_LAUNCH_OK(launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx));
     MKD_CHECK_LAUNCH();

@@ -173,6 +173,29 @@ class B200ControlLDM:
 
     decode_latent_code = decode_first_stage  # the reference's other name for it (makeups.py:260)
 
+    # ---- x_p entry: diffmk/makeup_diffuse.py:37-40, diffusion_makeup.py:384-387 -------------
+    def attach_first_stage_encoder(self, encoder):
+        """encoder: a loaded ``B200FirstStageEncoder`` (the reference's ``first_stage_model``, encode side only)"""
+        self.first_stage_encoder = encoder
+        return self
+
+    def encode_first_stage(self, x):
+        """posterior moments (mean, logvar) of ``first_stage_model.encode(x)``; x: [B, 3, H, W] in [-1, 1]"""
+        if getattr(self, "first_stage_encoder", None) is None:
+            raise RuntimeError("no first-stage encoder attached (attach_first_stage_encoder)")
+        return self.first_stage_encoder.encode(x)
+
+    def get_first_stage_encoding(self, posterior, noise=None):
+        """``scale_factor * posterior.sample()`` with sample = mean + exp(logvar / 2) * randn (upstream
+        DiagonalGaussianDistribution.sample); latent-sized, outside the loop"""
+        mean, logvar = posterior
+        noise = torch.randn_like(mean) if noise is None else noise
+        return self.scale_factor * (mean + torch.exp(0.5 * logvar) * noise)
+
+    def get_z(self, x, noise=None):
+        """diffmk/makeup_diffuse.py:37-40"""
+        return self.get_first_stage_encoding(self.encode_first_stage(x), noise)
+
     # ---- x_p entry helpers (diffusion_makeup.py:384-389); latent-sized, outside the 50-step loop ---------------
     @staticmethod
     def _extract(a, t, x):

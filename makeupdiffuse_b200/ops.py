@@ -193,7 +193,7 @@ def softmax_rows(x2d, y2d, scale=1.0):
 
 def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None,
                    residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None,
-                   y32=None, stats=None) -> L.ConvDesc:
+                   y32=None, stats=None, pad_hi_extra=0) -> L.ConvDesc:
     """y2d: output in the activation dtype (or None); y32: optional fp32 copy of the same result."""
     px, ldx = _rows(x2d)
     Cc = x2d.shape[1]
@@ -215,7 +215,7 @@ def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=
         assert y32.dtype == torch.float32
         d.y32, d.ldy32 = _rows(y32)
     d.N, d.H, d.W, d.C, d.K, d.R, d.S = N, H, W, Cc, K, R, S
-    d.stride, d.pad, d.upsample = stride, pad, int(bool(upsample))
+    d.stride, d.pad, d.upsample, d.pad_hi_extra = stride, pad, int(bool(upsample)), int(pad_hi_extra)
     d.ldx = ldx
     d.act, d.geglu_block, d.path, d.alpha = act, geglu_block, path, float(alpha)
     d.x, d.w = px, w.data_ptr()
@@ -249,7 +249,8 @@ def conv2d(x2d, w, y2d, **kw):
     L.check(L.load().mkd_conv2d(C.byref(d), _stream()), "conv2d")
     e1.record()
     Hi, Wi = (2 * d.H, 2 * d.W) if d.upsample else (d.H, d.W)
-    P, Q = (Hi + 2 * d.pad - d.R) // d.stride + 1, (Wi + 2 * d.pad - d.S) // d.stride + 1
+    P = (Hi + 2 * d.pad + d.pad_hi_extra - d.R) // d.stride + 1
+    Q = (Wi + 2 * d.pad + d.pad_hi_extra - d.S) // d.stride + 1
     PROFILE.append({"op": "conv2d", "path": path, "flops": 2.0 * d.N * P * Q * d.K * d.R * d.S * d.C, "M": d.N * P * Q, "K": d.K,
                     "C": d.C, "R": d.R, "stride": d.stride, "up": d.upsample, "e0": e0, "e1": e1, "desc": d})
 

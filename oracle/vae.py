@@ -127,3 +127,75 @@ class OracleFirstStageDecoder(nn.Module):
 def decode_first_stage(first_stage: OracleFirstStageDecoder, z, scale_factor=0.18215):
     """upstream LatentDiffusion.decode_first_stage / diffmk/makeups.py:260-262 (scale_factor: yaml:47)"""
     return first_stage.decode(1.0 / scale_factor * z)
+
+
+# ---- encode side: SURVEY.md §8(f) rank 2 (x_p entry) -------------------------------------------------------------------
+class Downsample(nn.Module):
+    """upstream Downsample(with_conv=True): zero-pad the bottom / right edge by one, then 3x3 stride-2 conv without padding"""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+
+
+class Encoder(nn.Module):
+    """upstream ldm.modules.diffusionmodules.model.Encoder for yaml:88-105 (double_z: 2 * z_channels output channels)"""
+
+    def __init__(self, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, z_channels=4, double_z=True, **unused):
+        super().__init__()
+        self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, padding=1)
+        in_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block_in, block_out = ch * in_mult[i_level], ch * ch_mult[i_level]
+            down = nn.Module()
+            down.block = nn.ModuleList()
+            for _ in range(num_res_blocks):
+                down.block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in)
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        self.norm_out = _norm(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, 3, padding=1)
+
+    def forward(self, x):
+        h = self.conv_in(x)
+        for i_level in range(self.num_resolutions):
+            for blk in self.down[i_level].block:
+                h = blk(h)
+            if i_level != self.num_resolutions - 1:
+                h = self.down[i_level].downsample(h)
+        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
+        return self.conv_out(_swish(self.norm_out(h)))
+
+
+class OracleFirstStageEncoder(nn.Module):
+    """``first_stage_model`` restricted to what encoding needs (``encoder.*`` + ``quant_conv``).  ``encode`` returns the
+    moments (mean, logvar clamped to [-30, 20]) of upstream's DiagonalGaussianDistribution."""
+
+    def __init__(self, embed_dim=4, ddconfig=None):
+        super().__init__()
+        dd = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, z_channels=4, double_z=True)
+        dd.update(ddconfig or {})
+        self.encoder = Encoder(**dd)
+        self.quant_conv = nn.Conv2d(2 * dd["z_channels"], 2 * embed_dim, 1)
+
+    def encode(self, x):
+        mean, logvar = torch.chunk(self.quant_conv(self.encoder(x)), 2, dim=1)
+        return mean, torch.clamp(logvar, -30.0, 20.0)
+
+
+def get_z(first_stage: OracleFirstStageEncoder, x, noise, scale_factor=0.18215):
+    """diffmk/makeup_diffuse.py:37-40: z = scale_factor * posterior.sample(), sample = mean + exp(logvar / 2) * noise"""
+    mean, logvar = first_stage.encode(x)
+    return scale_factor * (mean + torch.exp(0.5 * logvar) * noise)

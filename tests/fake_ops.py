@@ -103,13 +103,16 @@ def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
 
 
 def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None, residual=None,
-           alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None, y32=None, stats=None):
+           alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None, y32=None, stats=None,
+           pad_hi_extra=0):
     C = x2d.shape[1]
     K = w.shape[0]
     assert x2d.shape[0] == N * H * W and w.numel() == K * R * S * C
     xr = x2d.float().reshape(N, H, W, C).permute(0, 3, 1, 2)
     if upsample:
         xr = F.interpolate(xr, scale_factor=2, mode="nearest")
+    if pad_hi_extra:
+        xr = F.pad(xr, (0, pad_hi_extra, 0, pad_hi_extra))
     acc = F.conv2d(xr, w.float().reshape(K, R, S, C).permute(0, 3, 1, 2), None if bias is None else bias.float(),
                    stride=stride, padding=pad)
     Mo = acc.shape[0] * acc.shape[2] * acc.shape[3]
