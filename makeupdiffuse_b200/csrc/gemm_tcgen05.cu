@@ -24,6 +24,9 @@ using namespace mkd;
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
+#ifndef MKD_EPI_PIPE
+#define MKD_EPI_PIPE 1  // 0 = lock-step epilogue everywhere (A/B builds)
+#endif
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 
 struct EpiP {
@@ -323,12 +326,21 @@ enum { EPI_PLAIN = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_PARTIAL = 3, EPI_STATS = 
 // under load + MMA + two barrier wake-ups ~ 1800+ cycles), so the staging panel is kept narrow (40 columns, 22 KB) and
 // every remaining byte of the 227 KB goes to pipeline stages.
 template <int BN, int CL, int EPI> struct Cfg {
+  // PIPE: the epilogue is split into 4 DRAIN warps (TMEM -> registers -> staging panel) and 8 STORE warps (staging
+  // panel -> fused epilogue math -> global), handing double-buffered panels over with named barriers, so that the TMEM
+  // read of panel q + 1 (64 B/clk per SM) runs under the shared/global traffic of panel q.  The lock-step version
+  // (every thread does both phases, two CTA-wide barriers per panel) overlaps nothing.  EPI_STATS keeps the lock-step
+  // epilogue (its column-sum scratch plus a second staging panel would cost the 3x3 convs a pipeline stage), and so does
+  // EPI_GEGLU (two 80-column panels per tile; with 32-column panels the FF1 GEMM measured 3 % slower).
+  static constexpr bool PIPE = EPI != 4 /*EPI_STATS*/ && EPI != 2 /*EPI_GEGLU*/ && MKD_EPI_PIPE;
+  static constexpr int THREADS = PIPE ? 512 : 352;
   // staging panel width (columns); GEGLU needs value + gate groups side by side (even group count)
-  static constexpr int PW = (BN % 80 == 0) ? (EPI == EPI_GEGLU ? 80 : 40) : (BN >= 64 ? 64 : 32);
+  static constexpr int PW = (BN % 80 == 0) ? (EPI == 2 /*EPI_GEGLU*/ ? (PIPE ? 32 : 80) : 40) : (BN >= 64 ? 64 : 32);
   static constexpr int NP = BN / PW;
   static constexpr int LDT = PW + 4;                                      // +4 floats: conflict-free phase-1 writes
   static constexpr int STAGE_BYTES = A_BYTES + BN * BK * 2;
-  static constexpr int STAGING_BYTES = BM * LDT * 4;
+  static constexpr int PANEL_BYTES = BM * LDT * 4;
+  static constexpr int STAGING_BYTES = PANEL_BYTES * (PIPE ? 2 : 1);
   // EPI_STATS: 16 planes (8 channels x {sum, sumsq}) of per-thread column partials, pitch 257 floats
   static constexpr int STATS_PITCH = 257;
   static constexpr int SCRATCH_BYTES = EPI == 4 /*EPI_STATS*/ ? 16 * STATS_PITCH * 4 : 0;
@@ -336,6 +348,7 @@ template <int BN, int CL, int EPI> struct Cfg {
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + SCRATCH_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(STAGES >= 3 && SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(BN % PW == 0, "panels tile the N tile");
 };
 __host__ __device__ constexpr int tmem_cols2(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -355,13 +368,24 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
 // tiles are private to an M tile.  (Sharing B instead — by multicast or by cta_group::2 — measured no gain.)
 // EPI selects the ONE epilogue variant an instantiation carries (a single body holding all of them was ~10^4 SASS
 // instructions and instruction-fetch bound in phase 2).
-template <int BN, int CL, int EPI>
-__global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
+// SPEC != 0 fixes the epilogue's operand set at compile time (bit 0: fp32 residual, bit 1: fp32 output y32, bit 2: bf16
+// output y; no timestep embedding): the run-time dispatch on ep.res / ep.y32 / ep.y / ep.emb cost ~115 SASS instructions
+// per 8-channel piece where ~30 do the work, and with two store warps per scheduler the epilogue is issue-bound.
+template <int BN, int CL, int EPI, int SPEC = 0>
+__global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
                                                               const __grid_constant__ CUtensorMap bmap, MainP mp, EpiP ep) {
   using C = Cfg<BN, CL, EPI>;
   const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
   const int cl_id = blockIdx.x / CL, cl_num = gridDim.x / CL;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, PW = C::PW, NP = C::NP, LDT = C::LDT;
+  constexpr bool PIPE = C::PIPE;
+  const bool has_res = SPEC ? (SPEC & 1) != 0 : ep.res != nullptr, res_f32 = SPEC ? true : ep.res_f32 != 0;
+  const bool has_y32 = SPEC ? (SPEC & 2) != 0 : ep.y32 != nullptr, has_y = SPEC ? (SPEC & 4) != 0 : ep.y != nullptr;
+  const bool has_emb = SPEC ? false : ep.emb != nullptr;
+  // warp roles.  lock-step: 0 A producer, 1 MMA, 2-9 epilogue, 10 B producer.  PIPE: 0 A producer, 1 MMA, 2 B producer,
+  // 3 idle, 4-7 drain (TMEM lane quadrant = warp % 4), 8-15 store.
+  constexpr int B_WARP = PIPE ? 2 : 10, EPI_WARP0 = PIPE ? 8 : 2;
+  constexpr int BAR_FULL = 2, BAR_EMPTY = 4, BAR_N = 384;  // named barriers of the panel hand-over (+ buffer index)
   constexpr int TCOLS = tmem_cols2(2 * BN);
   constexpr int NG = PW / 8;  // 8-column groups per panel
   extern __shared__ unsigned char smem_raw[];
@@ -376,7 +400,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 11 warps: 0 A-producer, 1 MMA, 2-9 epilogue, 10 B-producer
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) MKD_TRACE(0);
 
   if (warp == 0 && lane == 0) {
@@ -390,7 +414,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full_bar + i, 1);
-      mbar_init(tmem_empty_bar + i, 8);  // one arrival per epilogue warp
+      mbar_init(tmem_empty_bar + i, PIPE ? 4 : 8);  // one arrival per warp that reads TMEM
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -408,8 +432,8 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
   pdl_wait();
   if (threadIdx.x == 0) MKD_TRACE(1);
 
-  if (warp == 0 || warp == 10) {
-    // ===== TMA producers: warp 0 streams A, warp 10 streams B.  The whole warp walks the loop (warp-uniform ->
+  if (warp == 0 || warp == B_WARP) {
+    // ===== TMA producers: warp 0 streams A, warp B_WARP streams B.  The whole warp walks the loop (warp-uniform ->
     // operands stay in uniform registers), one elected lane issues. =====
     const bool do_a = warp == 0;
     {
@@ -541,16 +565,58 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
         __syncwarp();
       }
     }
-  } else if (warp < 10) {
-    // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4 =====
+  } else if (PIPE && warp >= 4 && warp < 8) {
+    // ===== drain warps (PIPE): accumulator rows of TMEM lane quadrant `warp % 4`, panel by panel, into the staging
+    // buffer q & 1; full/empty hand-over with the store warps through named barriers =====
+    constexpr bool geglu = EPI == EPI_GEGLU;
+    const int quad = warp & 3, trow_idx = quad * 32 + lane;
+    int j = 0, q = 0;
+#pragma unroll 1
+    for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
+      const int ab = j & 1, use = j >> 1;
+      mbar_wait(tmem_full_bar + ab, use & 1);
+      tcgen05_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
+#pragma unroll 1
+      for (int p = 0; p < NP; ++p, ++q) {
+        const int b = q & 1;
+        uint32_t r[NG][8];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          // GEGLU panels interleave NG/2 value groups with their NG/2 gate groups (gate columns start at BN/2)
+          const int col = geglu ? (g < NG / 2 ? p * (PW / 2) + g * 8 : BN / 2 + p * (PW / 2) + (g - NG / 2) * 8)
+                                : p * PW + g * 8;
+          tmem_ld8_nowait(trow + col, r[g]);
+        }
+        // the store warps have consumed panel q - 2 (same buffer); waited for while the TMEM read is in flight
+        if (q >= 2) asm volatile("bar.sync %0, %1;\n" ::"r"(BAR_EMPTY + b), "n"(BAR_N) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        float* dst = staging + b * (BM * LDT) + trow_idx * LDT;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(r[g][0], r[g][1], r[g][2], r[g][3]);
+          *reinterpret_cast<uint4*>(dst + g * 8 + 4) = make_uint4(r[g][4], r[g][5], r[g][6], r[g][7]);
+        }
+        if (p == NP - 1) {  // every TMEM read of this unit is done: hand the accumulator buffer back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar + ab);
+        }
+        __threadfence_block();
+        asm volatile("bar.arrive %0, %1;\n" ::"r"(BAR_FULL + b), "n"(BAR_N) : "memory");  // panel staged
+      }
+    }
+  } else if (PIPE ? warp >= 8 : warp < 10) {
+    // ===== epilogue warps.  lock-step (warps 2..9): TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4,
+    // every thread drains (phase 1) and stores (phase 2).  PIPE (warps 8..15): phase 2 only. =====
     // Phase-2 work split: thread -> ONE 8-channel column group g (so its bias vector is loaded once per panel) and
     // rows rr, rr + RPI, ... of the tile.  Consecutive threads own consecutive groups of the same row: every global
     // access of a warp is a run of consecutive 16 / 32-byte pieces.
     constexpr int RPI = 256 / NG;                 // rows covered per iteration (25 when NG = 10: 6 threads idle)
     constexpr int P2_ITERS = (BM + RPI - 1) / RPI;
-    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
-    const int et = threadIdx.x - 64;  // 0..255
-    const int trow_idx = quad * 32 + lane;
+    [[maybe_unused]] const int ew = warp - EPI_WARP0, quad = warp & 3, half = ew >> 2;
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
+    [[maybe_unused]] const int trow_idx = quad * 32 + lane;
     const int g2 = et % NG, rr = et / NG;         // phase-2 column group / first row
     const bool p2_active = et < RPI * NG;
     // EPI_STATS: column sums of a panel are reduced one barrier LATER (after the next panel's first barrier), out of a
@@ -571,37 +637,92 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
         if ((et & 3) == 0 && ch < ep.N_out) ep.stats[(int64_t)pend_mtile * ep.stats_ld + ch] = make_float2(acc, sq);
       }
     };
+    constexpr bool geglu = EPI == EPI_GEGLU;
+    constexpr bool plain = EPI == EPI_PLAIN || EPI == EPI_SILU || EPI == EPI_STATS;
+    // ---- software-pipelined global loads: bias / timestep-embedding / residual of panel q + 1 are requested while
+    // panel q is processed (raw registers, unpacked at use), so no panel waits for an L2 / DRAM round trip.  Loading
+    // them at the top of their own panel put that latency (~1000+ clk under load) on every panel's critical path:
+    // 3 us per 128 x 160 tile, whatever the drain and the stores cost. ----
+    struct Pre {
+      float bias[8];              // plain: bias of this thread's 8 channels; GEGLU: bias of its value channels
+      float bias2[8];             // GEGLU: bias of its gate channels
+      uint4 res[P2_ITERS][2];     // residual, raw: 8 fp32 (both) or 8 bf16 ([0])
+      uint4 emb[P2_ITERS];        // timestep-embedding row slice, raw bf16
+    };
+    auto prefetch = [&](int n_tile_, int m_base_, int p_, Pre& L) {
+      if constexpr (geglu) {
+        constexpr int NV = NG / 2, RPG = 256 / NV;
+        const int rowv = n_tile_ * BN + p_ * (PW / 2) + (et % NV) * 8;  // weight/bias row of the value channels
+#pragma unroll
+        for (int k = 0; k < 8; ++k) L.bias[k] = L.bias2[k] = 0.f;
+        if (et < RPG * NV && ep.bias) {
+          load8(ep.bias + rowv, L.bias);
+          load8(ep.bias + rowv + BN / 2, L.bias2);
+        }
+      } else if constexpr (plain) {
+        const int o_ = n_tile_ * BN + p_ * PW + g2 * 8;
+        const bool full8_ = p2_active && o_ + 8 <= ep.N_out;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) L.bias[k] = 0.f;
+        if (full8_ && ep.bias) load8(ep.bias + o_, L.bias);
+#pragma unroll
+        for (int u = 0; u < P2_ITERS; ++u) {
+          const int row = rr + u * RPI, m = m_base_ + row;
+          if (full8_ && row < BM && m < ep.M) {
+            if (has_res && !MKD_DEBUG_BIT(8)) {
+              if (res_f32) {
+                const uint4* src = reinterpret_cast<const uint4*>(static_cast<const float*>(ep.res) + (int64_t)m * ep.ldr + o_);
+                L.res[u][0] = src[0];
+                L.res[u][1] = src[1];
+              } else {
+                L.res[u][0] = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(ep.res) + (int64_t)m * ep.ldr + o_);
+              }
+            }
+            if (has_emb) L.emb[u] = *reinterpret_cast<const uint4*>(ep.emb + (int64_t)(m / ep.pix_per_img) * ep.lde + o_);
+          }
+        }
+      }
+    };
+    auto unpack8 = [](const uint4& u, float (&v)[8]) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+      }
+    };
+    Pre cur, nxt;
+    if (cl_id < mp.num_units) {
+      const int n_tile0 = (cl_id % mp.n_tiles) * CL + (int)cta_rank, m_tile0 = (cl_id / mp.n_tiles) % mp.m_tiles;
+      prefetch(n_tile0, m_tile0 * BM, 0, cur);
+    }
     int j = 0;
     for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
       const int n_tile = (unit % mp.n_tiles) * CL + (int)cta_rank, rest = unit / mp.n_tiles;
       const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
       const int ab = j & 1, use = j >> 1;
       const int m_base = m_tile * BM;
-      constexpr bool geglu = EPI == EPI_GEGLU;
-      constexpr bool plain = EPI == EPI_PLAIN || EPI == EPI_SILU || EPI == EPI_STATS;
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
-      bool acc_ready = false;
+      [[maybe_unused]] const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
+      [[maybe_unused]] bool acc_ready = false;
 #pragma unroll 1
       for (int p = 0; p < NP; ++p) {
-        // ---- prefetch: every long-latency global load of this panel is issued before the TMEM drain ----
         const int o = n_tile * BN + p * PW + g2 * 8;  // first output channel of this thread's group (plain path)
         const bool full8 = plain && p2_active && o + 8 <= ep.N_out;
-        float bias8[8], res[P2_ITERS][8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) bias8[k] = 0.f;
-        if (full8 && ep.bias) load8(ep.bias + o, bias8);
-#pragma unroll
-        for (int u = 0; u < P2_ITERS; ++u) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) res[u][k] = 0.f;
-          const int m = m_base + rr + u * RPI;
-          if (full8 && rr + u * RPI < BM && m < ep.M && !MKD_DEBUG_BIT(8)) {
-            if (ep.res) {
-              if (ep.res_f32) load8(static_cast<const float*>(ep.res) + (int64_t)m * ep.ldr + o, res[u]);
-              else load8(static_cast<const bf16*>(ep.res) + (int64_t)m * ep.ldr + o, res[u]);
-            }
-          }
+        // ---- request the NEXT panel's global operands (this panel's were requested one panel ago) ----
+        if (p + 1 < NP) {
+          prefetch(n_tile, m_base, p + 1, nxt);
+        } else if (unit + cl_num < mp.num_units) {
+          const int nu = unit + cl_num;
+          prefetch((nu % mp.n_tiles) * CL + (int)cta_rank, ((nu / mp.n_tiles) % mp.m_tiles) * BM, 0, nxt);
         }
+        const float* stg = staging;  // the panel phase 2 reads
+        if constexpr (PIPE) {
+          const int b = (j * NP + p) & 1;
+          stg = staging + b * (BM * LDT);
+          asm volatile("bar.sync %0, %1;\n" ::"r"(BAR_FULL + b), "n"(BAR_N) : "memory");  // the drain warps staged it
+          if (j == 0 && et == 0 && p == 0) MKD_TRACE(5);
+        } else {
         if (!acc_ready) {
           mbar_wait(tmem_full_bar + ab, use & 1);
           if (j == 0 && et == 0) MKD_TRACE(5);
@@ -644,6 +765,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
           if (lane == 0) mbar_arrive(tmem_empty_bar + ab);
         }
         asm volatile("bar.sync 1, 256;\n" ::: "memory");  // panel staged (RAW)
+        }  // !PIPE
         if (j == 0 && et == 0) MKD_TRACE(p == 0 ? 11 : 13);
         // ---- phase 2: coalesced walk over the panel ----
         [[maybe_unused]] float st_s[8], st_q[8];  // EPI_STATS: this thread's column partials over its rows
@@ -659,7 +781,7 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
               const int row = rr + u * RPI, m = m_base + row;
               if (row < BM && m < ep.M && n < ep.n_rows) {
                 float* dst = ep.partial + ((int64_t)split * ep.M + m) * ep.n_rows + n;
-                const float* src = staging + row * LDT + g2 * 8;
+                const float* src = stg + row * LDT + g2 * 8;
                 *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
                 *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(src + 4);
               }
@@ -670,21 +792,15 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
           const int gv = et % NV, rv0 = et / NV;
           constexpr int RPG = 256 / NV, G_ITERS = (BM + RPG - 1) / RPG;
           if (et < RPG * NV) {
-            const int rowv = n_tile * BN + p * (PW / 2) + gv * 8;  // weight/bias row of the value channels
-            float bv[8], bg[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) bv[k] = bg[k] = 0.f;
-            if (ep.bias) {
-              load8(ep.bias + rowv, bv);
-              load8(ep.bias + rowv + BN / 2, bg);
-            }
+            const float(&bv)[8] = cur.bias;
+            const float(&bg)[8] = cur.bias2;
 #pragma unroll
             for (int u = 0; u < G_ITERS; ++u) {
               const int row = rv0 + u * RPG, m = m_base + row;
               if (row < BM && m < ep.M) {
                 float a[8], gt[8], r[8];
-                load8(staging + row * LDT + gv * 8, a);
-                load8(staging + row * LDT + (NV + gv) * 8, gt);
+                load8(stg + row * LDT + gv * 8, a);
+                load8(stg + row * LDT + (NV + gv) * 8, gt);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) r[k] = (a[k] + bv[k]) * gelu_erf_fast(gt[k] + bg[k]);
                 store8(ep.y + (int64_t)m * ep.ldy + n_tile * (BN / 2) + p * (PW / 2) + gv * 8, r);
@@ -697,16 +813,28 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
             const int row = rr + u * RPI, m = m_base + row;
             if (row < BM && m < ep.M && o < ep.N_out) {
               float r[8];
-              load8(staging + row * LDT + g2 * 8, r);
+              load8(stg + row * LDT + g2 * 8, r);
               if (full8) {
-                if (ep.emb) {  // per-sample timestep embedding (ResBlock conv1 only): small, L1/L2 resident
+                if (has_emb) {  // per-sample timestep embedding (ResBlock conv1 only)
                   float t[8];
-                  load8(ep.emb + (int64_t)(m / ep.pix_per_img) * ep.lde + o, t);
+                  unpack8(cur.emb[u], t);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) r[k] += t[k];
                 }
+                float rs[8];
+                if (!has_res || MKD_DEBUG_BIT(8)) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) r[k] = (r[k] + bias8[k]) * ep.alpha + res[u][k];
+                  for (int k = 0; k < 8; ++k) rs[k] = 0.f;
+                } else if (res_f32) {
+                  rs[0] = __uint_as_float(cur.res[u][0].x); rs[1] = __uint_as_float(cur.res[u][0].y);
+                  rs[2] = __uint_as_float(cur.res[u][0].z); rs[3] = __uint_as_float(cur.res[u][0].w);
+                  rs[4] = __uint_as_float(cur.res[u][1].x); rs[5] = __uint_as_float(cur.res[u][1].y);
+                  rs[6] = __uint_as_float(cur.res[u][1].z); rs[7] = __uint_as_float(cur.res[u][1].w);
+                } else {
+                  unpack8(cur.res[u][0], rs);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = (r[k] + cur.bias[k]) * ep.alpha + rs[k];
                 if constexpr (EPI == EPI_SILU) {
 #pragma unroll
                   for (int k = 0; k < 8; ++k) r[k] = silu_f(r[k]);
@@ -719,8 +847,8 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
                   }
                 }
                 if (!MKD_DEBUG_BIT(4)) {
-                  if (ep.y32) store8(ep.y32 + (int64_t)m * ep.ldy32 + o, r);
-                  if (ep.y) store8(ep.y + (int64_t)m * ep.ldy + o, r);
+                  if (has_y32) store8(ep.y32 + (int64_t)m * ep.ldy32 + o, r);
+                  if (has_y) store8(ep.y + (int64_t)m * ep.ldy + o, r);
                 } else if (r[0] == 1234.5f) {  // (debug timing run: keep the math alive without the stores)
                   ep.y32[0] = r[1];
                 }
@@ -761,7 +889,11 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
           pend_mtile = m_tile;
           pend_ch0 = n_tile * BN + p * PW;
         }
+        if constexpr (PIPE) {  // this thread's reads of the panel are done: the drain warps may refill the buffer
+          asm volatile("bar.arrive %0, %1;\n" ::"r"(BAR_EMPTY + ((j * NP + p) & 1)), "n"(BAR_N) : "memory");
+        }
         if (j == 0 && et == 0 && p == 0) MKD_TRACE(12);
+        cur = nxt;
       }
       if (et == 0) {
         if (j == 0) MKD_TRACE(6);
@@ -787,10 +919,11 @@ __global__ void __launch_bounds__(352, 1) gemm_tcgen05_kernel(const __grid_const
 template <int BN>
 __global__ void splitk_epilogue_kernel(EpiP ep, int splits) {
   pdl_wait();
-  const int groups = ep.n_rows / 16;
+  const int gw = ep.act == MKD_ACT_GEGLU ? 16 : 8;  // channels per thread
+  const int groups = ep.n_rows / gw;
   const int64_t total = (int64_t)ep.M * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / groups), n = (int)(i % groups) * 16;
+    const int m = (int)(i / groups), n = (int)(i % groups) * gw;
     auto gather = [&](int col, float (&v)[16]) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -815,9 +948,34 @@ __global__ void splitk_epilogue_kernel(EpiP ep, int splits) {
       epilogue_geglu8(ep, m, n, n + BN / 2, tile * (BN / 2) + c, a0, g0);
       epilogue_geglu8(ep, m, n + 8, n + BN / 2 + 8, tile * (BN / 2) + c + 8, a1, g1);
     } else {
-      float v[16];
-      gather(n, v);
-      epilogue_store16(ep, m, n, v);
+      // 8 channels per thread; every partial of a batch of <= 8 splits is requested before the first add (the serial
+      // split loop above costs one L2 round trip per split: ~8 us for 9 splits of a 256 x 1280 tile set).
+      // The adds keep the order s = 0, 1, ...: bit-identical to the serial loop.
+      {
+        constexpr int h = 0;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        for (int s0 = 0; s0 < splits; s0 += 8) {
+          float4 t[8][2];
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            if (s0 + s < splits) {
+              const float4* p = reinterpret_cast<const float4*>(ep.partial + ((int64_t)(s0 + s) * ep.M + m) * ep.n_rows + n + 8 * h);
+              t[s][0] = p[0];
+              t[s][1] = p[1];
+            }
+          }
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            if (s0 + s < splits) {
+              v[0] += t[s][0].x; v[1] += t[s][0].y; v[2] += t[s][0].z; v[3] += t[s][0].w;
+              v[4] += t[s][1].x; v[5] += t[s][1].y; v[6] += t[s][1].z; v[7] += t[s][1].w;
+            }
+          }
+        }
+        epilogue_vec8(ep, m, n + 8 * h, v);
+      }
     }
   }
 }
@@ -999,12 +1157,24 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     else { dd.H = g.P; dd.W = g.Q; dd.ldx = d_in->C; }
   }
   constexpr int EG = (BN == 160 ? EPI_GEGLU : EPI_PLAIN);
-  constexpr int NV = 5;
+  // 0-4: the epilogue variants with run-time operand dispatch; 5-9: compile-time operand sets (SPEC) of the shapes that
+  // dominate a UNet step (N tile 160): y32 | res32 + y32 | y | res32 + y (plain), res32 + y32 + y (statistics)
+  constexpr bool SP = BN == 160 && CL == 1;
+  constexpr int NV = 10;
   const KernelFn all[NV] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
                             gemm_tcgen05_kernel<BN, CL, EG>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>,
-                            gemm_tcgen05_kernel<BN, CL, EPI_STATS>};
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS>,
+                            gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 2 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 3 : 0>,
+                            gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 4 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 5 : 0>,
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0>};
   const size_t smems[NV] = {Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_SILU>::SMEM, Cfg<BN, CL, EG>::SMEM,
-                            Cfg<BN, CL, EPI_PARTIAL>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM};
+                            Cfg<BN, CL, EPI_PARTIAL>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM,
+                            Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_PLAIN>::SMEM,
+                            Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM};
+  const int threads[NV] = {Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_SILU>::THREADS, Cfg<BN, CL, EG>::THREADS,
+                           Cfg<BN, CL, EPI_PARTIAL>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS,
+                           Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_PLAIN>::THREADS,
+                           Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS};
   static bool configured = false;
   if (!configured) {
     for (int i = 0; i < NV; ++i) {
@@ -1096,9 +1266,14 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   const int grid = CL * (mp.num_units < max_clusters ? mp.num_units : max_clusters);
   {
     cudaLaunchConfig_t cfg = {};
+    int variant = ep.partial ? 3 : ep.stats ? 4 : (ep.act == MKD_ACT_GEGLU ? 2 : (ep.act == MKD_ACT_SILU ? 1 : 0));
+    if (SP && (variant == 0 || variant == 4) && !ep.emb && (!ep.res || ep.res_f32) && !mp.debug) {
+      const int spec = (ep.res ? 1 : 0) | (ep.y32 ? 2 : 0) | (ep.y ? 4 : 0);
+      if (variant == 0 && spec >= 2 && spec <= 5) variant = 3 + spec;
+      else if (variant == 4 && spec == 7) variant = 9;
+    }
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(352);
-    const int variant = ep.partial ? 3 : ep.stats ? 4 : (ep.act == MKD_ACT_GEGLU ? 2 : (ep.act == MKD_ACT_SILU ? 1 : 0));
+    cfg.blockDim = dim3(threads[variant]);
     cfg.dynamicSmemBytes = smems[variant];
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -1114,10 +1289,10 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   }
   MKD_CHECK_LAUNCH();
   if (splits > 1) {
-    int64_t total = (int64_t)g.M * (d->K / 16);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    MKD_LAUNCH_OK(launch_pdl(splitk_epilogue_kernel<BN>, dim3(blocks), dim3(256), 0, stream, ep, splits));
+    int64_t total = (int64_t)g.M * (d->K / (d->act == MKD_ACT_GEGLU ? 16 : 8));
+    int blocks = (int)((total + 127) / 128);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    MKD_LAUNCH_OK(launch_pdl(splitk_epilogue_kernel<BN>, dim3(blocks), dim3(128), 0, stream, ep, splits));
     MKD_CHECK_LAUNCH();
   }
   return MKD_OK;
