@@ -200,9 +200,11 @@ class B200DDIMSampler:
             e = self._eps(torch.cat([x] * 2), torch.cat([t] * 2), cc[2])
         if use_original_steps:
             if self._coef_orig is None:
+                # cddim.py:54 reads the sigma table off the MODEL; without that attribute the reference raises
+                # AttributeError, and so does this
                 self._coef_orig = self._coefficients(m.alphas_cumprod, m.alphas_cumprod_prev,
                                                      m.sqrt_one_minus_alphas_cumprod,
-                                                     self.ddim_sigmas_for_original_num_steps)
+                                                     m.ddim_sigmas_for_original_num_steps)
             s1m, sq_at, sq_ap, dirc, sigma = self._coef_orig[index]
         else:
             s1m, sq_at, sq_ap, dirc, sigma = self._coef_ddim[index]

@@ -6,9 +6,14 @@ It is the *checker*: only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_
 ``--impl reference`` legs of ``bench.py`` may import it.  The product package ``makeupdiffuse_b200``
 never imports it and has no CPU fallback.
 
-PARITY UNPINNED: the reference ships no tests, fixtures or golden vectors for this path (SURVEY.md §4,
-§8(c)), and the arithmetic lives in the un-vendored, un-pinned third-party lllyasviel/ControlNet packages
-``ldm`` / ``cldm`` which are not importable here.  The oracle therefore follows
+PARITY PINNED FOR THE SAMPLER, UNPINNED FOR THE NETWORKS.  The reference ships no tests, fixtures or golden
+vectors for this path, and the network arithmetic lives in the un-vendored, un-pinned
+third-party lllyasviel/ControlNet packages ``ldm`` / ``cldm`` which are not importable here.  What CAN run here is
+the reference's own ``diffmk/cddim.py``: ``tests/golden/make_golden_ref_sampler.py`` executes that file unmodified
+(with a stand-in for the one upstream module it star-imports) over a closed-form toy denoiser, and
+``tests/test_ref_sampler_golden.py`` holds ``oracle.MKDDIMSampler.{denoising_step, reconstruct}`` to those outputs:
+bit-identical on all 11 cases (CFG on dict / list / tensor conditioning, eta > 0 with its RNG consumption,
+repeat_noise, truncated loops, use_original_steps).  For everything else the oracle follows
 
   * in-repo, cite-able code: ``diffmk/cddim.py:9-100`` (per-step DDIM math, CFG batching order, loop/index
     convention), ``diffmk/makeup_diffuse.py:152-170`` (ControlNet -> x control_scales -> UNet dataflow),

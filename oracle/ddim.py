@@ -153,8 +153,10 @@ class DDIMSampler:
             e_t = score_corrector.modify_score(m, e_t, x, t, c, **corrector_kwargs)
 
         if use_original_steps:
+            # cddim.py:54 reads this table off the MODEL (upstream registers it on the sampler): a model without the
+            # attribute raises AttributeError in the reference, and so does this restatement
             A, AP, S1, SG = (m.alphas_cumprod, m.alphas_cumprod_prev, m.sqrt_one_minus_alphas_cumprod,
-                             self.ddim_sigmas_for_original_num_steps)
+                             m.ddim_sigmas_for_original_num_steps)
         else:
             A, AP, S1, SG = (self.ddim_alphas, self.ddim_alphas_prev, self.ddim_sqrt_one_minus_alphas,
                              self.ddim_sigmas)
