@@ -207,16 +207,16 @@ __global__ void __launch_bounds__(ACfg<DN, NWG_, KST_, VST_>::THREADS, ACfg<DN, 
           for (int i = 0; i < 32; ++i) v[c][i] = (c * 32 + i >= kvalid) ? 0xff800000u : v[c][i];
         }
       }
-      // ---- row max (8 independent chains) ----
+      // ---- row max: 3-input max (FMNMX3), two keys per instruction, 8 independent chains ----
       float mx8[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx8[i] = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[c][i]));
+        for (int i = 0; i < 32; i += 2) mx8[(i >> 1) & 7] = max3(mx8[(i >> 1) & 7], __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
       }
-      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      const float mx = fmaxf(max3(mx8[0], mx8[1], mx8[2]), max3(mx8[3], mx8[4], fmaxf(max3(mx8[5], mx8[6], mx8[7]), -INFINITY)));
       if (t > 0) {  // PV(t-1) has retired: O(t-1) is complete and the P tile may be rewritten
         mbar_wait(o_full + wg, (t - 1) & 1);
         fence_after();
@@ -242,16 +242,20 @@ __global__ void __launch_bounds__(ACfg<DN, NWG_, KST_, VST_>::THREADS, ACfg<DN, 
         }
       }
       // ---- p = exp2((s - max) * scale * log2 e) -> bf16 -> swizzled smem; fp32 row sum (4 chains) ----
+      // (packed fp32 pipe: one FFMA2 scales-and-shifts two keys, one FADD2 adds two p to two running sums: 3
+      //  instructions per key instead of 4.5 — the loop is issue-bound, MUFU sits at ~40 %)
       const float mb = m_used * sl2;
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint64_t sl2x2 = pack2(sl2, sl2), nmbx2 = pack2(-mb, -mb);
+      uint64_t sum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(v[c][i]), sl2, -mb));
-          const float p1 = ex2(fmaf(__uint_as_float(v[c][i + 1]), sl2, -mb));
-          sum4[(i >> 1) & 3] += p0 + p1;
+          float a0, a1;
+          unpack2(ffma2(pack2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sl2x2, nmbx2), a0, a1);
+          const float p0 = ex2(a0), p1 = ex2(a1);
+          sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], pack2(p0, p1));
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
         }
@@ -262,7 +266,12 @@ __global__ void __launch_bounds__(ACfg<DN, NWG_, KST_, VST_>::THREADS, ACfg<DN, 
           *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
         }
       }
-      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      {
+        float s0, s1, s2, s3;
+        unpack2(fadd2(sum2[0], sum2[1]), s0, s1);
+        unpack2(fadd2(sum2[2], sum2[3]), s2, s3);
+        l += (s0 + s1) + (s2 + s3);
+      }
       fence_before();            // TMEM accesses above ordered before the MMA warp's PV(t)
       fence_proxy_async_smem();  // P visible to the tensor core's operand fetch
       __syncwarp();
