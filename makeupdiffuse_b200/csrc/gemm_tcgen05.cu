@@ -333,7 +333,10 @@ template <int BN, int CL, int EPI> struct Cfg {
   // epilogue (its column-sum scratch plus a second staging panel would cost the 3x3 convs a pipeline stage), and so does
   // EPI_GEGLU (two 80-column panels per tile; with 32-column panels the FF1 GEMM measured 3 % slower).
   static constexpr bool PIPE = EPI != 4 /*EPI_STATS*/ && EPI != 2 /*EPI_GEGLU*/ && MKD_EPI_PIPE;
-  static constexpr int THREADS = PIPE ? 512 : 352;
+  // lock-step epilogue threads: 8 warps.  (16 warps for GEGLU — ncu shows 11 300 warp-instructions per 128 x 160 tile at
+  // 1.6 IPC per SM — measured 7 % SLOWER on the FF1 GEMM: 578 -> 541 TFLOP/s; the parametrisation stays for experiments.)
+  static constexpr int ET = 256;
+  static constexpr int THREADS = PIPE ? 512 : 64 + ET + 32;
   // staging panel width (columns); GEGLU needs value + gate groups side by side (even group count)
   static constexpr int PW = (BN % 80 == 0) ? (EPI == 2 /*EPI_GEGLU*/ ? (PIPE ? 32 : 80) : 40) : (BN >= 64 ? 64 : 32);
   static constexpr int NP = BN / PW;
@@ -384,7 +387,8 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
   const bool has_emb = SPEC ? false : ep.emb != nullptr;
   // warp roles.  lock-step: 0 A producer, 1 MMA, 2-9 epilogue, 10 B producer.  PIPE: 0 A producer, 1 MMA, 2 B producer,
   // 3 idle, 4-7 drain (TMEM lane quadrant = warp % 4), 8-15 store.
-  constexpr int B_WARP = PIPE ? 2 : 10, EPI_WARP0 = PIPE ? 8 : 2;
+  constexpr int ET = C::ET;  // epilogue (lock-step) / store (PIPE) threads
+  constexpr int B_WARP = PIPE ? 2 : 2 + ET / 32, EPI_WARP0 = PIPE ? 8 : 2;
   constexpr int BAR_FULL = 2, BAR_EMPTY = 4, BAR_N = 384;  // named barriers of the panel hand-over (+ buffer index)
   constexpr int TCOLS = tmem_cols2(2 * BN);
   constexpr int NG = PW / 8;  // 8-column groups per panel
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full_bar + i, 1);
-      mbar_init(tmem_empty_bar + i, PIPE ? 4 : 8);  // one arrival per warp that reads TMEM
+      mbar_init(tmem_empty_bar + i, PIPE ? 4 : ET / 32);  // one arrival per warp that reads TMEM
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -606,16 +610,16 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
         asm volatile("bar.arrive %0, %1;\n" ::"r"(BAR_FULL + b), "n"(BAR_N) : "memory");  // panel staged
       }
     }
-  } else if (PIPE ? warp >= 8 : warp < 10) {
+  } else if (PIPE ? warp >= 8 : warp < 2 + ET / 32) {
     // ===== epilogue warps.  lock-step (warps 2..9): TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4,
     // every thread drains (phase 1) and stores (phase 2).  PIPE (warps 8..15): phase 2 only. =====
     // Phase-2 work split: thread -> ONE 8-channel column group g (so its bias vector is loaded once per panel) and
     // rows rr, rr + RPI, ... of the tile.  Consecutive threads own consecutive groups of the same row: every global
     // access of a warp is a run of consecutive 16 / 32-byte pieces.
-    constexpr int RPI = 256 / NG;                 // rows covered per iteration (25 when NG = 10: 6 threads idle)
+    constexpr int RPI = ET / NG;                  // rows covered per iteration (25 when NG = 10: 6 threads idle)
     constexpr int P2_ITERS = (BM + RPI - 1) / RPI;
     [[maybe_unused]] const int ew = warp - EPI_WARP0, quad = warp & 3, half = ew >> 2;
-    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..ET-1
     [[maybe_unused]] const int trow_idx = quad * 32 + lane;
     const int g2 = et % NG, rr = et / NG;         // phase-2 column group / first row
     const bool p2_active = et < RPI * NG;
@@ -651,7 +655,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
     };
     auto prefetch = [&](int n_tile_, int m_base_, int p_, Pre& L) {
       if constexpr (geglu) {
-        constexpr int NV = NG / 2, RPG = 256 / NV;
+        constexpr int NV = NG / 2, RPG = ET / NV;
         const int rowv = n_tile_ * BN + p_ * (PW / 2) + (et % NV) * 8;  // weight/bias row of the value channels
 #pragma unroll
         for (int k = 0; k < 8; ++k) L.bias[k] = L.bias2[k] = 0.f;
@@ -729,17 +733,18 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
           tcgen05_fence_after();
           acc_ready = true;
         }
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // previous panel fully consumed (WAR on the staging panel)
+        asm volatile("bar.sync 1, %0;\n" ::"n"(ET) : "memory");  // previous panel fully consumed (WAR on the staging panel)
         if (j == 0 && et == 0 && p == 0) MKD_TRACE(9);
         if constexpr (EPI == EPI_STATS) {
           if (pend_mtile >= 0) reduce_pending();  // every thread's partials of the previous panel are in `scratch`
         }
         // ---- phase 1: this thread's accumulator row, column groups g = half, half + 2, ... of the panel ----
         {
-          uint32_t r[(NG + 1) / 2][8];
+          constexpr int HS = ET / 128;  // warps per TMEM lane quadrant: column groups g = half, half + HS, ...
+          uint32_t r[(NG + HS - 1) / HS][8];
 #pragma unroll
-          for (int gi = 0; gi < (NG + 1) / 2; ++gi) {
-            const int g = half + 2 * gi;
+          for (int gi = 0; gi < (NG + HS - 1) / HS; ++gi) {
+            const int g = half + HS * gi;
             if (g < NG) {
               // GEGLU panels interleave NG/2 value groups with their NG/2 gate groups (gate columns start at BN/2)
               const int col = geglu ? (g < NG / 2 ? p * (PW / 2) + g * 8 : BN / 2 + p * (PW / 2) + (g - NG / 2) * 8)
@@ -750,8 +755,8 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
           if (j == 0 && et == 0 && p == 0) MKD_TRACE(10);
 #pragma unroll
-          for (int gi = 0; gi < (NG + 1) / 2; ++gi) {
-            const int g = half + 2 * gi;
+          for (int gi = 0; gi < (NG + HS - 1) / HS; ++gi) {
+            const int g = half + HS * gi;
             if (g < NG) {
               float* dst = staging + trow_idx * LDT + g * 8;
               *reinterpret_cast<uint4*>(dst) = make_uint4(r[gi][0], r[gi][1], r[gi][2], r[gi][3]);
@@ -764,7 +769,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar + ab);
         }
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // panel staged (RAW)
+        asm volatile("bar.sync 1, %0;\n" ::"n"(ET) : "memory");  // panel staged (RAW)
         }  // !PIPE
         if (j == 0 && et == 0) MKD_TRACE(p == 0 ? 11 : 13);
         // ---- phase 2: coalesced walk over the panel ----
@@ -790,7 +795,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
         } else if constexpr (geglu) {
           constexpr int NV = NG / 2;  // value groups of the panel; their gate groups follow in the staging row
           const int gv = et % NV, rv0 = et / NV;
-          constexpr int RPG = 256 / NV, G_ITERS = (BM + RPG - 1) / RPG;
+          constexpr int RPG = ET / NV, G_ITERS = (BM + RPG - 1) / RPG;
           if (et < RPG * NV) {
             const float(&bv)[8] = cur.bias;
             const float(&bg)[8] = cur.bias2;
@@ -901,7 +906,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
       }
     }
     if constexpr (EPI == EPI_STATS) {  // statistics of the very last panel
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      asm volatile("bar.sync 1, %0;\n" ::"n"(ET) : "memory");
       if (pend_mtile >= 0) reduce_pending();
     }
   }
