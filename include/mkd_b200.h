@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 5
+#define MKD_ABI_VERSION 6
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 
@@ -174,6 +174,17 @@ int mkd_conv2d_path(const mkd_conv_desc* d); /* MKD_PATH_GENERIC or MKD_PATH_TCG
  * cores in bf16, wider single heads (the VAE decoder's 512-wide mid.attn_1) on the one-warp-per-query SIMT kernel. */
 int mkd_attention(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads, int Nq,
                   int Nkv, int d, int ldq, int ldk, int ldv, int ldo, float scale, mkd_stream_t stream);
+
+/* ---- conditioning producer: FrozenCLIPEmbedder (yaml:109-110; makeup_controlnet.py:20) ----
+ * Runs once per prompt, not per step.  (ABI v6)
+ * mkd_embed_tokens: out[b*T + t, :] = tok_emb[ids[b*T + t], :] + pos_emb[t, :]  — CLIPTextEmbeddings.forward; fp32
+ *   tables and output, C % 4 == 0, ids must lie in [0, vocab).
+ * mkd_attention_causal: mkd_attention with Nq == Nkv == N and key j visible to query i iff j <= i — the causal mask of
+ *   CLIPTextTransformer; N short (77), one warp per query row. */
+int mkd_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_emb, float* out, int B, int T, int C,
+                     int vocab, int ld_out, mkd_stream_t stream);
+int mkd_attention_causal(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads, int N, int d,
+                         int ldq, int ldk, int ldv, int ldo, float scale, mkd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmkd_b200.so")
 MKD_BF16, MKD_F32 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class ConvDesc(C.Structure):
@@ -62,6 +62,8 @@ PROTOTYPES = {
     "mkd_conv2d": (_i, [C.POINTER(ConvDesc), _vp]),
     "mkd_conv2d_path": (_i, [C.POINTER(ConvDesc)]),
     "mkd_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "mkd_attention_causal": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "mkd_embed_tokens": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

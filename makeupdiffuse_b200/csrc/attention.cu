@@ -15,13 +15,15 @@ namespace {
 // -------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
-                                 T* __restrict__ o, int Nq, int Nkv, int d, int ldq, int ldk, int ldv, int ldo,
-                                 float scale) {
+                                 T* __restrict__ o, int Nq, int Nkv_all, int d, int ldq, int ldk, int ldv, int ldo,
+                                 float scale, int causal) {
   pdl_wait();
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, i = blockIdx.x * warps + warp;
-  float* qs = sm + (size_t)warp * (d + Nkv);
+  float* qs = sm + (size_t)warp * (d + Nkv_all);
+  // causal (the CLIP text encoder): query i sees keys 0..i, i.e. the row simply has fewer keys
+  const int Nkv = causal ? min(Nkv_all, i + 1) : Nkv_all;
   float* ps = qs + d;
   if (i >= Nq) return;
   const T* qrow = q + ((int64_t)b * Nq + i) * ldq + h * d;
@@ -29,7 +31,7 @@ __global__ void attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ 
   __syncwarp();
   float mx = -INFINITY;
   for (int j = lane; j < Nkv; j += 32) {
-    const T* krow = k + ((int64_t)b * Nkv + j) * ldk + h * d;
+    const T* krow = k + ((int64_t)b * Nkv_all + j) * ldk + h * d;
     float acc = 0.f;
     for (int c = 0; c < d; c += 8) {
       float kv[8];
@@ -53,7 +55,7 @@ __global__ void attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ 
   T* orow = o + ((int64_t)b * Nq + i) * ldo + h * d;
   for (int c = lane; c < d; c += 32) {
     float acc = 0.f;
-    const T* vcol = v + (int64_t)b * Nkv * ldv + h * d + c;
+    const T* vcol = v + (int64_t)b * Nkv_all * ldv + h * d + c;
     for (int j = 0; j < Nkv; ++j) acc = fmaf(ps[j], to_f(vcol[(int64_t)j * ldv]), acc);
     orow[c] = from_f<T>(acc * inv);
   }
@@ -315,10 +317,34 @@ extern "C" int mkd_attention(const void* q, const void* k, const void* v, void* 
   dim3 grid((Nq + warps - 1) / warps, heads, B);
   if (dtype == MKD_BF16)
     MKD_LAUNCH_OK(launch_pdl(attn_simt_kernel<bf16>, dim3(grid), dim3(warps * 32), smem, st, (const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, Nq,
-                             Nkv, d, ldq, ldk, ldv, ldo, scale));
+                             Nkv, d, ldq, ldk, ldv, ldo, scale, 0));
   else
     MKD_LAUNCH_OK(launch_pdl(attn_simt_kernel<float>, dim3(grid), dim3(warps * 32), smem, st, (const float*)q, (const float*)k, (const float*)v, (float*)o, Nq,
-                             Nkv, d, ldq, ldk, ldv, ldo, scale));
+                             Nkv, d, ldq, ldk, ldv, ldo, scale, 0));
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+// Causal self-attention of short sequences (the 77-token CLIP text encoder, makeup_controlnet.py:20 / yaml:109-110):
+// one warp per query row on the SIMT kernel, key j visible to query i iff j <= i.  Runs once per prompt, not per step.
+extern "C" int mkd_attention_causal(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads,
+                                    int N, int d, int ldq, int ldk, int ldv, int ldo, float scale, mkd_stream_t stream) {
+  MKD_REQUIRE(q && k && v && o && B > 0 && heads > 0 && N > 0 && d > 0, MKD_E_INVALID, "attention_causal: bad args");
+  MKD_REQUIRE(d % 8 == 0 && d <= 512 && B <= 65535 && heads <= 65535, MKD_E_INVALID, "attention_causal: head dim %d / batch", d);
+  MKD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && aligned16(q) && aligned16(k) &&
+                  aligned16(v) && aligned16(o),
+              MKD_E_ALIGN, "attention_causal: ld must be multiples of 8 and pointers 16B aligned");
+  const int warps = 4;
+  const size_t smem = (size_t)warps * (d + N) * sizeof(float);
+  MKD_REQUIRE(smem <= 48 * 1024, MKD_E_INVALID, "attention_causal: N=%d too long for this kernel", N);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((N + warps - 1) / warps, heads, B);
+  if (dtype == MKD_BF16)
+    MKD_LAUNCH_OK(launch_pdl(attn_simt_kernel<bf16>, dim3(grid), dim3(warps * 32), smem, st, (const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, N,
+                             N, d, ldq, ldk, ldv, ldo, scale, 1));
+  else
+    MKD_LAUNCH_OK(launch_pdl(attn_simt_kernel<float>, dim3(grid), dim3(warps * 32), smem, st, (const float*)q, (const float*)k, (const float*)v, (float*)o, N,
+                             N, d, ldq, ldk, ldv, ldo, scale, 1));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }

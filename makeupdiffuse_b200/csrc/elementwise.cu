@@ -312,3 +312,35 @@ extern "C" int mkd_add(const void* a, const void* b, void* y, int dtype, int64_t
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
+
+// ---- token + position embedding of the CLIP text encoder (once per prompt) ------------------------------------------
+// out[b * T + t, :] = tok_emb[ids[b * T + t], :] + pos_emb[t, :]   (fp32 tables, fp32 out; C % 4 == 0)
+namespace {
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                    float* __restrict__ out, int rows, int T, int C, int vocab, int ld_out) {
+  pdl_wait();
+  const int vpr = C / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)rows * vpr; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vpr), c = (int)(i % vpr) * 4;
+    int64_t id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);  // (the host wrapper rejects out-of-range ids; never read out of bounds)
+    const float4 a = *reinterpret_cast<const float4*>(tok + id * C + c);
+    const float4 b = *reinterpret_cast<const float4*>(pos + (int64_t)(r % T) * C + c);
+    *reinterpret_cast<float4*>(out + (int64_t)r * ld_out + c) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+}  // namespace
+
+extern "C" int mkd_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_emb, float* out, int B, int T,
+                                int C, int vocab, int ld_out, mkd_stream_t stream) {
+  MKD_REQUIRE(ids && tok_emb && pos_emb && out && B > 0 && T > 0 && C > 0 && vocab > 0, MKD_E_INVALID, "embed_tokens: bad args");
+  MKD_REQUIRE(C % 4 == 0 && ld_out % 4 == 0 && ld_out >= C && aligned16(tok_emb) && aligned16(pos_emb) && aligned16(out), MKD_E_ALIGN,
+              "embed_tokens: C / ld_out must be multiples of 4, pointers 16B aligned");
+  const int64_t n = (int64_t)B * T * (C / 4);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  MKD_LAUNCH_OK(launch_pdl(embed_tokens_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, ids, tok_emb, pos_emb, out, B * T, T, C,
+                           vocab, ld_out));
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}

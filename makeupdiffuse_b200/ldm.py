@@ -174,6 +174,37 @@ class B200ControlLDM:
     decode_latent_code = decode_first_stage  # the reference's other name for it (makeups.py:260)
 
     # ---- x_p entry: diffmk/makeup_diffuse.py:37-40, diffusion_makeup.py:384-387 -------------
+    # ---- conditioning producer ----------------------------------------------------------
+    def attach_cond_stage_model(self, encoder):
+        """encoder: a loaded ``B200FrozenCLIPEmbedder`` (the reference's ``cond_stage_model``, yaml:109-110)"""
+        self.cond_stage_model = encoder
+        self._prompt_cache = {}
+        return self
+
+    def get_learned_conditioning(self, c):
+        """``cond_stage_model.encode(c)``: prompts (list of str) or token ids [B, 77] -> c_crossattn [B, 77, 768].
+        The reference's prompt is the constant 'makeup transfer' (datasets.py:772): string prompts are encoded once and
+        the result is reused for every later batch (the encoder is frozen)."""
+        if getattr(self, "cond_stage_model", None) is None:
+            raise RuntimeError("no cond-stage model attached (attach_cond_stage_model)")
+        if torch.is_tensor(c):
+            return self.cond_stage_model(c)
+        key = tuple([c] if isinstance(c, str) else c)
+        if key not in self._prompt_cache:
+            uniq = sorted(set(key))
+            z = self.cond_stage_model.encode(uniq)
+            self._prompt_cache[key] = torch.stack([z[uniq.index(p)] for p in key])
+        return self._prompt_cache[key]
+
+    def get_unconditional_conditioning(self, N):
+        """CLIP encoding of the empty prompt, N times (diffusion_makeup.py:399-402)"""
+        return self.get_learned_conditioning([""] * N)
+
+    @staticmethod
+    def assemble_hint(src_img, ref_img):
+        """c_concat[0] = cat((src_img, ref_img), 1): source first (makeup_diffuse.py:56; images in [0, 1])"""
+        return torch.cat((src_img, ref_img), 1)
+
     def attach_first_stage_encoder(self, encoder):
         """encoder: a loaded ``B200FirstStageEncoder`` (the reference's ``first_stage_model``, encode side only)"""
         self.first_stage_encoder = encoder

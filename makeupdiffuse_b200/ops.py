@@ -286,3 +286,26 @@ def _attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
     po, ldo = _rows(o2d)
     L.check(L.load().mkd_attention(pq, pk, pv, po, _dt(q2d), B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, float(scale),
                                    _stream()), "attention")
+
+
+def attention_causal(q2d, k2d, v2d, o2d, *, B, heads, N, d, scale):
+    """causal self-attention over N tokens per sample (CLIP text encoder); q/k/v may be column slices of one buffer"""
+    pq, ldq = _rows(q2d)
+    pk, ldk = _rows(k2d)
+    pv, ldv = _rows(v2d)
+    po, ldo = _rows(o2d)
+    L.check(L.load().mkd_attention_causal(pq, pk, pv, po, _dt(q2d), B, heads, N, d, ldq, ldk, ldv, ldo, float(scale),
+                                          _stream()), "attention_causal")
+
+
+def embed_tokens(ids, tok_emb, pos_emb, out2d):
+    """out[b*T + t] = tok_emb[ids[b, t]] + pos_emb[t]   (fp32)"""
+    B, T = ids.shape
+    vocab, Cc = tok_emb.shape
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and tok_emb.dtype == pos_emb.dtype == out2d.dtype == torch.float32
+    assert pos_emb.shape[0] >= T and pos_emb.shape[1] == Cc and tok_emb.is_contiguous() and pos_emb.is_contiguous()
+    if int(ids.min()) < 0 or int(ids.max()) >= vocab:
+        raise IndexError(f"token id outside [0, {vocab})")  # nn.Embedding raises IndexError as well
+    po, ldo = _rows(out2d)
+    L.check(L.load().mkd_embed_tokens(ids.data_ptr(), tok_emb.data_ptr(), pos_emb.data_ptr(), po, B, T, Cc, vocab, ldo,
+                                      _stream()), "embed_tokens")

@@ -147,5 +147,16 @@ def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
     o2d.copy_(o.permute(0, 2, 1, 3).reshape(B * Nq, heads * d))
 
 
-ALL = ["device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
+def attention_causal(q2d, k2d, v2d, o2d, *, B, heads, N, d, scale):
+    sp = lambda t: t.float().reshape(B, N, heads, d).permute(0, 2, 1, 3)  # noqa: E731
+    o = F.scaled_dot_product_attention(sp(q2d), sp(k2d), sp(v2d), scale=scale, is_causal=True)
+    o2d.copy_(o.permute(0, 2, 1, 3).reshape(B * N, heads * d))
+
+
+def embed_tokens(ids, tok_emb, pos_emb, out2d):
+    B, T = ids.shape
+    out2d.copy_((tok_emb[ids] + pos_emb[:T]).reshape(B * T, -1))
+
+
+ALL = ["attention_causal", "embed_tokens", "device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
        "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "softmax_rows", "conv2d", "attention"]
