@@ -186,6 +186,14 @@ int mkd_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_
 int mkd_attention_causal(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads, int N, int d,
                          int ldq, int ldk, int ldv, int ldo, float scale, mkd_stream_t stream);
 
+/* ---- test-harness output: `save_local`, diffusion_makeup.py:344-358 (ABI v6) -----------------
+ * images: N x C x H x W fp32 (C = 1 or 3) -> grid: GH x GW x 3 uint8, GH = (H + padding) * ceil(N / min(nrow, N)) + padding,
+ * GW = (W + padding) * min(nrow, N) + padding: torchvision make_grid (pad_value 0), optional clamp to [-1, 1], optional
+ * (x + 1) / 2, x * 255 truncated to uint8 — byte-identical to the reference's torch / numpy sequence (N == 1: no padding
+ * frame, as make_grid returns a single image unchanged). */
+int mkd_image_grid_u8(const float* images, unsigned char* grid, int N, int C, int H, int W, int nrow, int padding, int clamp,
+                      int rescale, mkd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -344,3 +344,48 @@ extern "C" int mkd_embed_tokens(const int64_t* ids, const float* tok_emb, const 
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
+
+// ---- test-harness output: diffusion_makeup.py:344-358 `save_local` -------------------------
+// torchvision.utils.make_grid(images, nrow, padding = 2, pad_value = 0) -> optional clamp to [-1, 1] (test_step,
+// :340-341) -> (x + 1) / 2 -> CHW to HWC -> (x * 255).astype(uint8) (truncation), as ONE pass writing the uint8 grid the
+// PNG encoder takes: the device -> host copy shrinks 4x and no fp32 grid exists.  The fp32 operations are the
+// reference's, in its order, so the bytes are identical.  C == 1 images are replicated to 3 channels like make_grid.
+namespace {
+__global__ void image_grid_u8_kernel(const float* __restrict__ src, unsigned char* __restrict__ dst, int N, int C, int H, int W,
+                                     int xmaps, int pad, int GH, int GW, int clamp, int rescale) {
+  pdl_wait();
+  const int64_t total = (int64_t)GH * GW * 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 3), gx = (int)((i / 3) % GW), gy = (int)(i / (3 * (int64_t)GW));
+    const int cy = gy / (H + pad), cx = gx / (W + pad);
+    const int y = gy - cy * (H + pad) - pad, x = gx - cx * (W + pad) - pad;
+    const int k = cy * xmaps + cx;
+    float v = 0.f;  // pad_value
+    if (y >= 0 && x >= 0 && cx < xmaps && k < N && y < H && x < W) {
+      v = src[(((int64_t)k * C + (C == 1 ? 0 : c)) * H + y) * W + x];
+      if (clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
+    }
+    if (rescale) v = (v + 1.0f) / 2.0f;
+    v = v * 255.0f;
+    // numpy's float32 -> uint8 cast of in-range values truncates toward zero; out-of-range input (no clamp) wraps
+    // through int on the reference's platform, which this mirrors for the representable range
+    dst[i] = (unsigned char)(int)v;
+  }
+}
+}  // namespace
+
+extern "C" int mkd_image_grid_u8(const float* images, unsigned char* grid, int N, int C, int H, int W, int nrow, int padding,
+                                 int clamp, int rescale, mkd_stream_t stream) {
+  MKD_REQUIRE(images && grid && N > 0 && (C == 1 || C == 3) && H > 0 && W > 0 && nrow > 0 && padding >= 0, MKD_E_INVALID,
+              "image_grid_u8: bad args (C must be 1 or 3)");
+  if (N == 1) padding = 0;  // make_grid returns a single image as it is, without the padding frame
+  const int xmaps = nrow < N ? nrow : N, ymaps = (N + xmaps - 1) / xmaps;
+  const int GH = (H + padding) * ymaps + padding, GW = (W + padding) * xmaps + padding;
+  const int64_t total = (int64_t)GH * GW * 3;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  MKD_LAUNCH_OK(launch_pdl(image_grid_u8_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, images, grid, N, C, H, W, xmaps, padding,
+                           GH, GW, clamp, rescale));
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}

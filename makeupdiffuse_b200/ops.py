@@ -309,3 +309,23 @@ def embed_tokens(ids, tok_emb, pos_emb, out2d):
     po, ldo = _rows(out2d)
     L.check(L.load().mkd_embed_tokens(ids.data_ptr(), tok_emb.data_ptr(), pos_emb.data_ptr(), po, B, T, Cc, vocab, ldo,
                                       _stream()), "embed_tokens")
+
+
+def image_grid_shape(N, H, W, nrow, padding=2):
+    if N == 1:
+        padding = 0  # torchvision's make_grid returns a single image without the padding frame
+    xmaps = min(nrow, N)
+    ymaps = (N + xmaps - 1) // xmaps
+    return (H + padding) * ymaps + padding, (W + padding) * xmaps + padding
+
+
+def image_grid_u8(images, nrow, padding=2, clamp=True, rescale=True):
+    """images [N, C, H, W] fp32 (C = 1 or 3) -> uint8 [GH, GW, 3] grid (make_grid + rescale + HWC + uint8 in one pass)"""
+    assert images.dtype == torch.float32 and images.dim() == 4
+    images = images.contiguous()
+    N, Cc, H, W = images.shape
+    GH, GW = image_grid_shape(N, H, W, nrow, padding)
+    out = torch.empty(GH, GW, 3, dtype=torch.uint8, device=images.device)
+    L.check(L.load().mkd_image_grid_u8(images.data_ptr(), out.data_ptr(), N, Cc, H, W, int(nrow), int(padding), int(clamp),
+                                       int(rescale), _stream()), "image_grid_u8")
+    return out

@@ -158,5 +158,19 @@ def embed_tokens(ids, tok_emb, pos_emb, out2d):
     out2d.copy_((tok_emb[ids] + pos_emb[:T]).reshape(B * T, -1))
 
 
-ALL = ["attention_causal", "embed_tokens", "device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
+def image_grid_u8(images, nrow, padding=2, clamp=True, rescale=True):
+    """the reference's sequence itself (diffusion_makeup.py:340-355)"""
+    import numpy as np
+    import torchvision
+    x = images.detach().cpu()
+    if clamp:
+        x = torch.clamp(x, -1.0, 1.0)
+    grid = torchvision.utils.make_grid(x, nrow=nrow, padding=padding)
+    if rescale:
+        grid = (grid + 1.0) / 2.0
+    grid = grid.transpose(0, 1).transpose(1, 2).squeeze(-1).numpy()
+    return torch.from_numpy((grid * 255).astype(np.uint8))
+
+
+ALL = ["image_grid_u8", "attention_causal", "embed_tokens", "device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
        "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "softmax_rows", "conv2d", "attention"]
