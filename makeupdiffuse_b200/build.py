@@ -17,6 +17,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          *(["-DMKD_ENABLE_TRACE"] if os.environ.get("MKD_TRACE") == "1" else []),  # %globaltimer stamps + timing switches (tools/gemm_trace.py, tools/dbg_epilogue.sh)
          *([f"-DMKD_EPI_PIPE={os.environ['MKD_EPI_PIPE']}"] if os.environ.get("MKD_EPI_PIPE") else []),  # A/B builds of the GEMM epilogue
+         *([f"-DMKD_MAX_STAGES={os.environ['MKD_MAX_STAGES']}"] if os.environ.get("MKD_MAX_STAGES") else []),  # pipeline-depth experiments
          "-Xptxas", "-v"]
 
 

@@ -24,6 +24,9 @@ using namespace mkd;
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
+#ifndef MKD_MAX_STAGES
+#define MKD_MAX_STAGES 8  // -DMKD_MAX_STAGES=3: shallower TMA ring (profiles/r01_gemm_stage_sweep.txt)
+#endif
 #ifndef MKD_EPI_PIPE
 #define MKD_EPI_PIPE 1  // 0 = lock-step epilogue everywhere (A/B builds)
 #endif
@@ -325,7 +328,7 @@ enum { EPI_PLAIN = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_PARTIAL = 3, EPI_STATS = 
 // Shared-memory budget: the main loop is bound by how many bytes are in flight per SM (slot round trip = TMA latency
 // under load + MMA + two barrier wake-ups ~ 1800+ cycles), so the staging panel is kept narrow (40 columns, 22 KB) and
 // every remaining byte of the 227 KB goes to pipeline stages.
-template <int BN, int CL, int EPI> struct Cfg {
+template <int BN, int CL, int EPI, int DUAL = 0> struct Cfg {
   // PIPE: the epilogue is split into 4 DRAIN warps (TMEM -> registers -> staging panel) and 8 STORE warps (staging
   // panel -> fused epilogue math -> global), handing double-buffered panels over with named barriers, so that the TMEM
   // read of panel q + 1 (64 B/clk per SM) runs under the shared/global traffic of panel q.  The lock-step version
@@ -341,17 +344,22 @@ template <int BN, int CL, int EPI> struct Cfg {
   static constexpr int PW = (BN % 80 == 0) ? (EPI == 2 /*EPI_GEGLU*/ ? (PIPE ? 32 : 80) : 40) : (BN >= 64 ? 64 : 32);
   static constexpr int NP = BN / PW;
   static constexpr int LDT = PW + 4;                                      // +4 floats: conflict-free phase-1 writes
-  static constexpr int STAGE_BYTES = A_BYTES + BN * BK * 2;
+  // DUAL (experiment, off by default — see launch()): one work unit = one A tile against TWO adjacent B tiles (both TMEM
+  // accumulator buffers belong to the same unit): half the A bytes per MMA.  Background: the main loop does not speed up
+  // with a deeper ring (3, 4 and 5 stages measure the same, profiles/r01_gemm_stage_sweep.txt) nor with a smaller B tile.
+  static constexpr int STAGE_BYTES = A_BYTES + (1 + DUAL) * BN * BK * 2;
   static constexpr int PANEL_BYTES = BM * LDT * 4;
   static constexpr int STAGING_BYTES = PANEL_BYTES * (PIPE ? 2 : 1);
   // EPI_STATS: 16 planes (8 channels x {sum, sumsq}) of per-thread column partials, pitch 257 floats
   static constexpr int STATS_PITCH = 257;
   static constexpr int SCRATCH_BYTES = EPI == 4 /*EPI_STATS*/ ? 16 * STATS_PITCH * 4 : 0;
   static constexpr int BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - STAGING_BYTES - SCRATCH_BYTES;
-  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+  static constexpr int STAGES_FIT = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > MKD_MAX_STAGES ? MKD_MAX_STAGES : STAGES_FIT;  // (cap: pipeline-depth experiments)
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + SCRATCH_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(STAGES >= 3 && SMEM <= 227 * 1024, "shared memory budget");
   static_assert(BN % PW == 0, "panels tile the N tile");
+  static_assert(!DUAL || (!PIPE && CL == 1 && 2 * BN <= 512), "DUAL: lock-step epilogue, no cluster");
 };
 __host__ __device__ constexpr int tmem_cols2(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -374,10 +382,10 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
 // SPEC != 0 fixes the epilogue's operand set at compile time (bit 0: fp32 residual, bit 1: fp32 output y32, bit 2: bf16
 // output y; no timestep embedding): the run-time dispatch on ep.res / ep.y32 / ep.y / ep.emb cost ~115 SASS instructions
 // per 8-channel piece where ~30 do the work, and with two store warps per scheduler the epilogue is issue-bound.
-template <int BN, int CL, int EPI, int SPEC = 0>
-__global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
+template <int BN, int CL, int EPI, int SPEC = 0, int DUAL = 0>
+__global__ void __launch_bounds__((Cfg<BN, CL, EPI, DUAL>::THREADS), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
                                                               const __grid_constant__ CUtensorMap bmap, MainP mp, EpiP ep) {
-  using C = Cfg<BN, CL, EPI>;
+  using C = Cfg<BN, CL, EPI, DUAL>;
   const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
   const int cl_id = blockIdx.x / CL, cl_num = gridDim.x / CL;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, PW = C::PW, NP = C::NP, LDT = C::LDT;
@@ -448,7 +456,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
 #pragma unroll 1
       for (int unit = cl_id; unit < mp.num_units; unit += cl_num) {
         // unit -> (n group fastest, m_tile, split); a CL == 2 pair shares m_tile and takes n tiles 2*ng, 2*ng + 1
-        const int n_tile = (unit % mp.n_tiles) * CL + (int)cta_rank, rest = unit / mp.n_tiles;
+        const int n_tile = (unit % mp.n_tiles) * (DUAL ? 2 : CL) + (int)cta_rank, rest = unit / mp.n_tiles;
         const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
         const int kb0 = split * mp.kb_per_split, kb1 = min(mp.kblocks, kb0 + mp.kb_per_split);
         int w0 = 0, h0 = 0, n0 = 0;
@@ -498,6 +506,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
               else {
                 mbar_expect_tx(full_bar + s, STAGE_BYTES - A_BYTES);
                 tma_load_2d(&bmap, full_bar + s, sa + A_BYTES, kb * BK, nb);
+                if (DUAL) tma_load_2d(&bmap, full_bar + s, sa + A_BYTES + BN * BK * 2, kb * BK, nb + BN);
               }
             }
           }
@@ -526,8 +535,10 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
       for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
         const int split = (unit / mp.n_tiles) / mp.m_tiles;
         const int kb0 = split * mp.kb_per_split, kb1 = min(mp.kblocks, kb0 + mp.kb_per_split);
-        const int ab = j & 1, use = j >> 1;
+        // DUAL: the unit owns both accumulator buffers (j counts units, each buffer is used once per unit)
+        const int ab = DUAL ? 0 : (j & 1), use = DUAL ? j : (j >> 1);
         mbar_wait(tmem_empty_bar + ab, (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        if (DUAL) mbar_wait(tmem_empty_bar + 1, (use & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
 #pragma unroll 1
@@ -545,6 +556,9 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
               if (MKD_DEBUG_BIT(2)) break;
               // advance K inside the 128-byte swizzle atom: +32 bytes per UMMA_K (encoded >> 4)
               umma_bf16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > kb0 || k) ? 1u : 0u);
+              if (DUAL)  // same A tile, the adjacent B tile, the other accumulator buffer
+                umma_bf16(tacc + (uint32_t)BN, adesc + (uint64_t)(k * 2), make_smem_desc(sa + A_BYTES + BN * BK * 2) + (uint64_t)(k * 2),
+                          idesc, (kb > kb0 || k) ? 1u : 0u);
             }
             // frees the last G smem slots once the MMAs issued so far retire (they retire in order);
             // CL == 2: in both CTAs — each multicasts into the other
@@ -564,6 +578,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
         // accumulator of this unit complete (CL == 2: tell both CTAs' epilogue warps)
         if (elect_one()) {
           tcgen05_commit(tmem_full_bar + ab);
+          if (DUAL) tcgen05_commit(tmem_full_bar + 1);
           if (j == 0) MKD_TRACE(4);
         }
         __syncwarp();
@@ -698,12 +713,13 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
     };
     Pre cur, nxt;
     if (cl_id < mp.num_units) {
-      const int n_tile0 = (cl_id % mp.n_tiles) * CL + (int)cta_rank, m_tile0 = (cl_id / mp.n_tiles) % mp.m_tiles;
+      const int n_tile0 = (cl_id % mp.n_tiles) * (DUAL ? 2 : CL) + (int)cta_rank, m_tile0 = (cl_id / mp.n_tiles) % mp.m_tiles;
       prefetch(n_tile0, m_tile0 * BM, 0, cur);
     }
-    int j = 0;
-    for (int unit = cl_id; unit < mp.num_units; unit += cl_num, ++j) {
-      const int n_tile = (unit % mp.n_tiles) * CL + (int)cta_rank, rest = unit / mp.n_tiles;
+    int j = 0;  // accumulator-buffer uses: one per unit, two (sub = 0, 1: adjacent N tiles) per DUAL unit
+    for (int unit = cl_id; unit < mp.num_units; unit += cl_num)
+    for (int sub = 0; sub <= DUAL; ++sub, ++j) {
+      const int n_tile = DUAL ? (unit % mp.n_tiles) * 2 + sub : (unit % mp.n_tiles) * CL + (int)cta_rank, rest = unit / mp.n_tiles;
       const int m_tile = rest % mp.m_tiles, split = rest / mp.m_tiles;
       const int ab = j & 1, use = j >> 1;
       const int m_base = m_tile * BM;
@@ -716,9 +732,11 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI>::THREADS), 1) gemm_tcgen05_k
         // ---- request the NEXT panel's global operands (this panel's were requested one panel ago) ----
         if (p + 1 < NP) {
           prefetch(n_tile, m_base, p + 1, nxt);
+        } else if (DUAL && sub == 0) {
+          prefetch(n_tile + 1, m_base, 0, nxt);
         } else if (unit + cl_num < mp.num_units) {
           const int nu = unit + cl_num;
-          prefetch((nu % mp.n_tiles) * CL + (int)cta_rank, ((nu / mp.n_tiles) % mp.m_tiles) * BM, 0, nxt);
+          prefetch((nu % mp.n_tiles) * (DUAL ? 2 : CL) + (int)cta_rank, ((nu / mp.n_tiles) % mp.m_tiles) * BM, 0, nxt);
         }
         const float* stg = staging;  // the panel phase 2 reads
         if constexpr (PIPE) {
@@ -1164,22 +1182,27 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   constexpr int EG = (BN == 160 ? EPI_GEGLU : EPI_PLAIN);
   // 0-4: the epilogue variants with run-time operand dispatch; 5-9: compile-time operand sets (SPEC) of the shapes that
   // dominate a UNet step (N tile 160): y32 | res32 + y32 | y | res32 + y (plain), res32 + y32 + y (statistics)
+  // 10-11: the statistics variants as DUAL kernels (one A tile against two adjacent N tiles), for shapes with more than
+  // one 128 x 160 tile per SM and an even number of N tiles (the 3x3 convs of the 32x32 level)
   constexpr bool SP = BN == 160 && CL == 1;
-  constexpr int NV = 10;
+  constexpr int NV = 12;
   const KernelFn all[NV] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
                             gemm_tcgen05_kernel<BN, CL, EG>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>,
                             gemm_tcgen05_kernel<BN, CL, EPI_STATS>,
                             gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 2 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 3 : 0>,
                             gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 4 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 5 : 0>,
-                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0>};
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0>,
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, 0, SP ? 1 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0, SP ? 1 : 0>};
   const size_t smems[NV] = {Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_SILU>::SMEM, Cfg<BN, CL, EG>::SMEM,
                             Cfg<BN, CL, EPI_PARTIAL>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM,
                             Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_PLAIN>::SMEM,
-                            Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM};
+                            Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM,
+                            Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM};
   const int threads[NV] = {Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_SILU>::THREADS, Cfg<BN, CL, EG>::THREADS,
                            Cfg<BN, CL, EPI_PARTIAL>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS,
                            Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_PLAIN>::THREADS,
-                           Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS};
+                           Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS,
+                           Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::THREADS, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::THREADS};
   static bool configured = false;
   if (!configured) {
     for (int i = 0; i < NV; ++i) {
@@ -1266,17 +1289,33 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     const char* e = getenv("MKD_DEBUG_TIMING");
     mp.debug = e ? atoi(e) : 0;
   }
-  mp.num_units = g.m_tiles * n_groups * splits;  // cluster-level work units
+  int variant = ep.partial ? 3 : ep.stats ? 4 : (ep.act == MKD_ACT_GEGLU ? 2 : (ep.act == MKD_ACT_SILU ? 1 : 0));
+  if (SP && (variant == 0 || variant == 4) && !ep.emb && (!ep.res || ep.res_f32) && !mp.debug) {
+    const int spec = (ep.res ? 1 : 0) | (ep.y32 ? 2 : 0) | (ep.y ? 4 : 0);
+    if (variant == 0 && spec >= 2 && spec <= 5) variant = 3 + spec;
+    else if (variant == 4 && spec == 7) variant = 9;
+  }
+  {
+    // DUAL units (opt-in, MKD_DUAL=1): meant for shapes where every SM has more than one 128 x 160 tile to do anyway; needs
+    // an even number of N tiles.  MEASURED: no gain — 16384 x 320 x 2880 conv1 36.8 -> 39.4 us, conv2 38.0 -> 38.1 us, only
+    // K = 8640 gains (82.3 -> 77.3 us); whole step 7.28 -> 7.45 ms.  A dual k-block takes ~2.5x a single one, so the main
+    // loop is NOT paced by the A tile alone: time follows the bytes that cross shared memory per k-block (TMA writes + the
+    // MMA's operand reads), which DUAL does not reduce per FLOP.  Off by default; kept as the experiment it is.
+    static int de = -1;
+    if (de < 0) {
+      const char* e = getenv("MKD_DUAL");
+      de = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (SP && de && (variant == 4 || variant == 9) && splits == 1 && n_tiles % 2 == 0 && g.m_tiles * n_tiles > num_sms() && !mp.debug) {
+      variant = variant == 4 ? 10 : 11;
+      mp.n_tiles = n_tiles / 2;
+    }
+  }
+  mp.num_units = g.m_tiles * mp.n_tiles * splits;  // cluster-level work units
   const int max_clusters = num_sms() / CL;
   const int grid = CL * (mp.num_units < max_clusters ? mp.num_units : max_clusters);
   {
     cudaLaunchConfig_t cfg = {};
-    int variant = ep.partial ? 3 : ep.stats ? 4 : (ep.act == MKD_ACT_GEGLU ? 2 : (ep.act == MKD_ACT_SILU ? 1 : 0));
-    if (SP && (variant == 0 || variant == 4) && !ep.emb && (!ep.res || ep.res_f32) && !mp.debug) {
-      const int spec = (ep.res ? 1 : 0) | (ep.y32 ? 2 : 0) | (ep.y ? 4 : 0);
-      if (variant == 0 && spec >= 2 && spec <= 5) variant = 3 + spec;
-      else if (variant == 4 && spec == 7) variant = 9;
-    }
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads[variant]);
     cfg.dynamicSmemBytes = smems[variant];

@@ -31,6 +31,10 @@ SHAPES = {
     "conv1280": (16, 8, 8, 1280, 1280, 3, "emb32"),
     "conv1280_4x4": (16, 4, 4, 1280, 1280, 3, "emb32"),
     "conv2560_4x4": (16, 4, 4, 2560, 1280, 3, "emb32"),
+    "conv320_c1": (16, 32, 32, 320, 320, 3, "emb32st"),   # ResBlock conv1 as the network runs it: + GroupNorm statistics
+    "conv320_c2": (16, 32, 32, 320, 320, 3, "res32st"),   # ResBlock conv2: fp32 residual, bf16 + fp32 out, statistics
+    "conv960_c1": (16, 32, 32, 960, 320, 3, "emb32st"),
+    "up640": (16, 16, 16, 640, 640, 3, "upst"),           # Upsample conv: 16x16 -> 32x32, N = 640
     "ff1_320": (16, 32, 32, 320, 2560, 1, "geglu"),
     "ff2_320": (16, 32, 32, 1280, 320, 1, "res32"),
     "qkv_320": (16, 32, 32, 320, 960, 1, "plain"),
@@ -57,6 +61,20 @@ for name, (N, H, W, C, K, R, epi) in SHAPES.items():
         y32 = torch.empty(M, K, device=DEV)
         args = (x, w, None)
         kw.update(emb=e, y32=y32)
+    elif epi in ("emb32st", "res32st", "upst"):
+        Mo = M * 4 if epi == "upst" else M
+        st = torch.empty((Mo + 127) // 128, K, 2, device=DEV)
+        y32 = torch.empty(Mo, K, device=DEV)
+        if epi == "emb32st":
+            args = (x, w, None)
+            kw.update(emb=torch.randn(N, K, device=DEV).bfloat16(), y32=y32, stats=st)
+        elif epi == "res32st":
+            args = (x, w, torch.empty(Mo, K, device=DEV, dtype=torch.bfloat16))
+            kw.update(residual=torch.randn(Mo, K, device=DEV), y32=y32, stats=st)
+        else:
+            args = (x, w, torch.empty(Mo, K, device=DEV, dtype=torch.bfloat16))
+            kw.update(upsample=True, y32=y32, stats=st)
+            M = Mo
     elif epi == "geglu":
         Ko = K // 2
         y = torch.empty(M, Ko, device=DEV, dtype=torch.bfloat16)
