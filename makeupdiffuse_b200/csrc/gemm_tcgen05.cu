@@ -335,13 +335,16 @@ template <int BN, int CL, int EPI, int DUAL = 0> struct Cfg {
   // (every thread does both phases, two CTA-wide barriers per panel) overlaps nothing.  EPI_STATS keeps the lock-step
   // epilogue (its column-sum scratch plus a second staging panel would cost the 3x3 convs a pipeline stage), and so does
   // EPI_GEGLU (two 80-column panels per tile; with 32-column panels the FF1 GEMM measured 3 % slower).
-  static constexpr bool PIPE = EPI != 4 /*EPI_STATS*/ && EPI != 2 /*EPI_GEGLU*/ && MKD_EPI_PIPE;
+  // (split-K partials of the 256-wide tile: lock-step on 32-column panels, so that FOUR 48 KB stages fit — the coupled
+  //  ring measures 516 clk per k-block with 4 stages, 593 with 3: profiles/r01_mma_probe.txt)
+  static constexpr bool WIDE_PARTIAL = EPI == 3 /*EPI_PARTIAL*/ && BN == 256;
+  static constexpr bool PIPE = EPI != 4 /*EPI_STATS*/ && EPI != 2 /*EPI_GEGLU*/ && !WIDE_PARTIAL && MKD_EPI_PIPE;
   // lock-step epilogue threads: 8 warps.  (16 warps for GEGLU — ncu shows 11 300 warp-instructions per 128 x 160 tile at
   // 1.6 IPC per SM — measured 7 % SLOWER on the FF1 GEMM: 578 -> 541 TFLOP/s; the parametrisation stays for experiments.)
   static constexpr int ET = 256;
   static constexpr int THREADS = PIPE ? 512 : 64 + ET + 32;
   // staging panel width (columns); GEGLU needs value + gate groups side by side (even group count)
-  static constexpr int PW = (BN % 80 == 0) ? (EPI == 2 /*EPI_GEGLU*/ ? (PIPE ? 32 : 80) : 40) : (BN >= 64 ? 64 : 32);
+  static constexpr int PW = WIDE_PARTIAL ? 32 : (BN % 80 == 0) ? (EPI == 2 /*EPI_GEGLU*/ ? (PIPE ? 32 : 80) : 40) : (BN >= 64 ? 64 : 32);
   static constexpr int NP = BN / PW;
   static constexpr int LDT = PW + 4;                                      // +4 floats: conflict-free phase-1 writes
   // DUAL (experiment, off by default — see launch()): one work unit = one A tile against TWO adjacent B tiles (both TMEM
@@ -1132,6 +1135,23 @@ bool geometry(const mkd_conv_desc* d, Geometry& g) {
 
 int pick_bn(const mkd_conv_desc* d, const Geometry& g) {
   if (d->act == MKD_ACT_GEGLU) return 160;
+  // deep-K convs on small maps (the 8x8 / 4x4 levels, N = 1280): they run as split-K anyway, so the tile count is free —
+  // 5 tiles of 256 instead of 8 of 160 per 128 rows.  The coupled TMA / MMA ring costs ~500 clk per k-block whatever the
+  // N tile (profiles/r01_mma_probe.txt): at N = 256 that is the MMA floor, at N = 160 it is 0.6 of it.  MKD_WIDE_SPLITK=0
+  // disables (A/B runs).
+  {
+    static int we = -1;
+    if (we < 0) {
+      const char* e = getenv("MKD_WIDE_SPLITK");
+      we = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int kblocks = g.Ktot / BK;
+    // measured (tools/gemm_bench.py): 1024 x 1280 x 11520  39.5 -> 34.2 us; at M = 256 (4x4 level, 11 splits) it LOSES
+    // (16.5 -> 17.9 us): only from 4 row tiles up
+    if (we && d->K % 256 == 0 && d->K % 160 == 0 && d->workspace && !d->stats && d->act == MKD_ACT_NONE && kblocks >= 64 &&
+        g.m_tiles >= 4 && g.m_tiles * (d->K / 160) <= 74 && (size_t)6 * g.M * d->K * sizeof(float) <= d->workspace_bytes)
+      return 256;
+  }
   if (d->K % 160 == 0) return 160;
   if (d->K % 80 == 0) return 80;
   // power-of-two widths (the VAE decoder's 128 / 256 / 512 channels): the widest tile that still leaves at least one
