@@ -18,6 +18,8 @@ NAMES = ["entry", "prologue", "tma0 issued", "full0", "mma u0 done", "acc0 ready
 ORDER = [0, 1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 6, 7, 8]
 SHAPES = {"sq320": (16, 32, 32, 320, 320, 1), "conv320": (16, 32, 32, 320, 320, 3),
           "tiny": (1, 1, 128, 64, 160, 1), "sq1280_m256": (16, 4, 4, 1280, 1280, 1)}
+if len(sys.argv) > 1 and sys.argv[1] == "dual":  # statistics-emitting 3x3 convs (DUAL-eligible: run with MKD_DUAL=1 / 0)
+    SHAPES = {"conv320_stats": (16, 32, 32, 320, 320, 3), "conv960_stats": (16, 32, 32, 960, 320, 3)}
 if len(sys.argv) > 1 and sys.argv[1] == "nsweep":  # same A, K = 2880; N-tile = 160 / 80 / 64 / 32 (BN picked from N)
     SHAPES = {"N320_bn160": (16, 32, 32, 320, 320, 3), "N240_bn80": (16, 32, 32, 320, 240, 3),
               "N256_bn64": (16, 32, 32, 320, 256, 3), "N32_bn32": (16, 32, 32, 320, 32, 3)}
@@ -26,7 +28,11 @@ for name, (N, H, W, C, K, R) in SHAPES.items():
     x = torch.randn(M, C, device=DEV).bfloat16()
     w = (torch.randn(K, R, R, C, device=DEV) / math.sqrt(C * R * R)).bfloat16()
     y = torch.empty(M, K, device=DEV, dtype=torch.bfloat16)
-    d = ops.make_conv_desc(x, w, y, N=N, H=H, W=W, R=R, S=R, pad=R // 2, bias=torch.randn(K, device=DEV))
+    extra = {}
+    if name.endswith("_stats"):
+        extra = dict(stats=torch.empty(M // 128, K, 2, device=DEV), y32=torch.empty(M, K, device=DEV),
+                     emb=torch.randn(N, K, device=DEV).bfloat16())
+    d = ops.make_conv_desc(x, w, y, N=N, H=H, W=W, R=R, S=R, pad=R // 2, bias=torch.randn(K, device=DEV), **extra)
     for _ in range(3):
         ops.run_conv_desc(d)
     tr = torch.zeros(148 * 16, dtype=torch.int64, device=DEV)
