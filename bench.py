@@ -118,7 +118,8 @@ def workload_config(args, world):
     return {"workload": f"{size}x{size}, DDIM-{S} eta 0, ControlNet (6-ch hint) conditioning, no CFG, "
                         f"batch {B} per GPU (global {B * world}), random-init (seeded non-zero) weights of "
                         "base_diffusion_makeup.yaml = BASELINE.json configs[1]"
-                        + (" + first-stage (VAE) decode of the samples to images" if getattr(args, "decode", False) else ""),
+                        + (" + first-stage (VAE) decode of the samples to images" if getattr(args, "decode", False) else "")
+                        + (" + CLIP text encoding of the prompt tokens and uint8 image grid in every e2e pass" if getattr(args, "pipeline", False) else ""),
             "parallelism": f"batch-sharded x{world}, one all-gather of final latents"
                            + (" fused into the last DDIM-update kernel (peer stores)" if getattr(args, "fused_gather", False)
                               and world > 1 else " (NCCL)" if world > 1 else ""),
@@ -165,6 +166,10 @@ def main():
     ap.add_argument("--decode", action="store_true",
                     help="also run the first-stage (VAE) decoder on the sampled latents inside every pass (SURVEY 8(f) rank 1; "
                          "not part of BASELINE.json's metric, so off by default and named in config.workload when on)")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="widened flow of SURVEY 8(f) ranks 1, 3, 4 inside every e2e pass: prompt token ids -> CLIP text encoder -> "
+                         "c_crossattn, DDIM, first-stage decode, uint8 image grid (mkd_image_grid_u8) -> host; implies --decode; "
+                         "off by default (not BASELINE.json's metric) and named in config.workload when on")
     ap.add_argument("--profile-out", default=None, help="write the per-layer kernel timing table to this file")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -173,6 +178,8 @@ def main():
         return reference_arm(args, rank)
     if args.warmup < 3:
         args.warmup = 3
+    if args.pipeline:
+        args.decode = True
 
     import torch
     import torch.distributed as dist
@@ -199,6 +206,14 @@ def main():
         from makeupdiffuse_b200.synth import synthetic_first_stage_state_dict
         vae = B200FirstStageDecoder(dtype=torch.bfloat16)
         model.attach_first_stage_decoder(vae.load_state_dict(synthetic_first_stage_state_dict(vae, 0, dev), device=dev))
+    if args.pipeline:
+        from makeupdiffuse_b200 import B200FrozenCLIPEmbedder
+        from makeupdiffuse_b200.synth import synthetic_clip_state_dict
+        clip = B200FrozenCLIPEmbedder(device=dev, dtype=torch.bfloat16)
+        clip.load_state_dict(synthetic_clip_state_dict(clip.cfg, 0, dev))
+        model.attach_cond_stage_model(clip)
+        tok_host = torch.randint(0, 49406, (B, 77), generator=torch.Generator().manual_seed(7)).pin_memory()
+        dtok = torch.empty(B, 77, dtype=torch.long, device=dev)
     data = synthetic_batch(Bg, size, 768, seed=1234, device=dev)  # whole-job batch from one generator, then sliced
     lo, hi = shard_bounds(Bg, rank, world)
     loc = {k: v[lo:hi].contiguous() for k, v in data.items()}
@@ -221,19 +236,31 @@ def main():
     out_host = torch.empty(B, 4, h, h, dtype=torch.float32).pin_memory()
     h2d = sum(pin[k].numel() * 4 for k in pin)
     d2h = out_host.numel() * 4
-    if args.decode:
+    if args.pipeline:
+        gh, gw = ops.image_grid_shape(B, size, size, 8)
+        img_host = torch.empty(gh, gw, 3, dtype=torch.uint8).pin_memory()
+        h2d += tok_host.numel() * 8 - pin["ctx"].numel() * 4  # token ids travel instead of the context
+        d2h += img_host.numel()
+    elif args.decode:
         img_host = torch.empty(B, 3, size, size, dtype=torch.float32).pin_memory()
         d2h += img_host.numel() * 4
 
     def one_pass_e2e():
         dsrc.copy_(pin["src"], non_blocking=True)
         dref.copy_(pin["ref"], non_blocking=True)
-        dctx.copy_(pin["ctx"], non_blocking=True)
+        if args.pipeline:
+            dtok.copy_(tok_host, non_blocking=True)
+            ctx_e2e = model.get_learned_conditioning(dtok)  # token ids: encoded every pass (no prompt cache)
+        else:
+            dctx.copy_(pin["ctx"], non_blocking=True)
+            ctx_e2e = dctx
         dxt.copy_(pin["x_T"], non_blocking=True)
         torch.cat([dsrc, dref], 1, out=dhint)
-        cond = {"c_crossattn": [dctx], "c_concat": [dhint]}
+        cond = {"c_crossattn": [ctx_e2e], "c_concat": [dhint]}
         out, _ = sampler.sample(S, B, (4, h, h), cond, eta=0.0, x_T=dxt, verbose=False)  # the public API call
-        if args.decode:
+        if args.pipeline:
+            img_host.copy_(ops.image_grid_u8(model.decode_first_stage(out), nrow=8), non_blocking=True)
+        elif args.decode:
             img_host.copy_(model.decode_first_stage(out), non_blocking=True)
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -78,3 +78,22 @@ def synthetic_batch(B_global: int, image_hw: int = 256, context_dim: int = 768, 
         "uc_ctx": torch.randn(B_global, 77, context_dim, device=device, generator=g),
         "x_T": torch.randn(B_global, 4, h, h, device=device, generator=g),
     }
+
+
+def synthetic_clip_state_dict(cfg, seed=0, device="cpu"):
+    """random-init weights of the CLIP text tower under HuggingFace's parameter names (benchmarks / smoke runs: no
+    checkpoint is available offline); N(0, 0.02) matrices, small biases, LayerNorm weights around 1"""
+    g = torch.Generator().manual_seed(seed)
+    C, I, V, T = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"], cfg["max_position_embeddings"]
+    n = lambda *shape, std=0.02, mean=0.0: (torch.randn(*shape, generator=g) * std + mean).to(device)  # noqa: E731
+    sd = {"text_model.embeddings.token_embedding.weight": n(V, C), "text_model.embeddings.position_embedding.weight": n(T, C),
+          "text_model.final_layer_norm.weight": n(C, std=0.1, mean=1.0), "text_model.final_layer_norm.bias": n(C, std=0.05)}
+    for i in range(cfg["num_hidden_layers"]):
+        p = f"text_model.encoder.layers.{i}."
+        for name in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[p + f"self_attn.{name}.weight"], sd[p + f"self_attn.{name}.bias"] = n(C, C), n(C, std=0.05)
+        sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"] = n(I, C), n(I, std=0.05)
+        sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"] = n(C, I), n(C, std=0.05)
+        for ln in ("layer_norm1", "layer_norm2"):
+            sd[p + ln + ".weight"], sd[p + ln + ".bias"] = n(C, std=0.1, mean=1.0), n(C, std=0.05)
+    return sd
