@@ -651,8 +651,17 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI, DUAL>::THREADS), 1) gemm_tcg
         const int plane = stat * 8 + (c & 7), gq = c >> 3;
         constexpr int HALF = (RPI + 1) / 2;
         const int r0 = hf * HALF, r1 = hf ? RPI : HALF;
-        float acc = 0.f;
-        for (int r = r0; r < r1; ++r) acc += scratch[plane * RP + r * NG + gq];
+        // fixed trip count + predicate: unrolled, so the <= 26 loads are issued back to back instead of one shared-memory
+        // round trip per row (the dependent loop cost ~800 clk per panel, twice the TMEM drain it runs beside); two
+        // interleaved partial sums, fixed order: deterministic
+        float acc = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < HALF; i += 2) {
+          const int r = r0 + i;
+          if (r < r1) acc += scratch[plane * RP + r * NG + gq];
+          if (r + 1 < r1) acc1 += scratch[plane * RP + (r + 1) * NG + gq];
+        }
+        acc += acc1;
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);             // both row halves
         const float sq = __shfl_down_sync(0xffffffffu, acc, 2);  // lane 4c gets the sum of squares from lane 4c + 2
         const int ch = pend_ch0 + c;
