@@ -383,7 +383,7 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
 // EPI selects the ONE epilogue variant an instantiation carries (a single body holding all of them was ~10^4 SASS
 // instructions and instruction-fetch bound in phase 2).
 // SPEC != 0 fixes the epilogue's operand set at compile time (bit 0: fp32 residual, bit 1: fp32 output y32, bit 2: bf16
-// output y; no timestep embedding): the run-time dispatch on ep.res / ep.y32 / ep.y / ep.emb cost ~115 SASS instructions
+// output y, bit 3: timestep embedding): the run-time dispatch on ep.res / ep.y32 / ep.y / ep.emb cost ~115 SASS instructions
 // per 8-channel piece where ~30 do the work, and with two store warps per scheduler the epilogue is issue-bound.
 template <int BN, int CL, int EPI, int SPEC = 0, int DUAL = 0>
 __global__ void __launch_bounds__((Cfg<BN, CL, EPI, DUAL>::THREADS), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap amap,
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI, DUAL>::THREADS), 1) gemm_tcg
   constexpr bool PIPE = C::PIPE;
   const bool has_res = SPEC ? (SPEC & 1) != 0 : ep.res != nullptr, res_f32 = SPEC ? true : ep.res_f32 != 0;
   const bool has_y32 = SPEC ? (SPEC & 2) != 0 : ep.y32 != nullptr, has_y = SPEC ? (SPEC & 4) != 0 : ep.y != nullptr;
-  const bool has_emb = SPEC ? false : ep.emb != nullptr;
+  const bool has_emb = SPEC ? (SPEC & 8) != 0 : ep.emb != nullptr;  // (bit 3: bf16 timestep-embedding rows, ResBlock conv1)
   // warp roles.  lock-step: 0 A producer, 1 MMA, 2-9 epilogue, 10 B producer.  PIPE: 0 A producer, 1 MMA, 2 B producer,
   // 3 idle, 4-7 drain (TMEM lane quadrant = warp % 4), 8-15 store.
   constexpr int ET = C::ET;  // epilogue (lock-step) / store (PIPE) threads
@@ -1214,24 +1214,26 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   // 10-11: the statistics variants as DUAL kernels (one A tile against two adjacent N tiles), for shapes with more than
   // one 128 x 160 tile per SM and an even number of N tiles (the 3x3 convs of the 32x32 level)
   constexpr bool SP = BN == 160 && CL == 1;
-  constexpr int NV = 12;
+  constexpr int NV = 13;  // 12: statistics + timestep embedding + y32 (ResBlock conv1 of the levels with fused statistics)
   const KernelFn all[NV] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
                             gemm_tcgen05_kernel<BN, CL, EG>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>,
                             gemm_tcgen05_kernel<BN, CL, EPI_STATS>,
                             gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 2 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 3 : 0>,
                             gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 4 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 5 : 0>,
                             gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0>,
-                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, 0, SP ? 1 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0, SP ? 1 : 0>};
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, 0, SP ? 1 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0, SP ? 1 : 0>,
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 10 : 0>};
   const size_t smems[NV] = {Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_SILU>::SMEM, Cfg<BN, CL, EG>::SMEM,
                             Cfg<BN, CL, EPI_PARTIAL>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM,
                             Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_PLAIN>::SMEM,
                             Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM,
-                            Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM};
+                            Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM};
   const int threads[NV] = {Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_SILU>::THREADS, Cfg<BN, CL, EG>::THREADS,
                            Cfg<BN, CL, EPI_PARTIAL>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS,
                            Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_PLAIN>::THREADS,
                            Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS,
-                           Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::THREADS, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::THREADS};
+                           Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::THREADS, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::THREADS,
+                           Cfg<BN, CL, EPI_STATS>::THREADS};
   static bool configured = false;
   if (!configured) {
     for (int i = 0; i < NV; ++i) {
@@ -1323,6 +1325,8 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     const int spec = (ep.res ? 1 : 0) | (ep.y32 ? 2 : 0) | (ep.y ? 4 : 0);
     if (variant == 0 && spec >= 2 && spec <= 5) variant = 3 + spec;
     else if (variant == 4 && spec == 7) variant = 9;
+  } else if (SP && variant == 4 && ep.emb && !ep.res && ep.y32 && !ep.y && !mp.debug) {
+    variant = 12;
   }
   {
     // DUAL units (opt-in, MKD_DUAL=1): meant for shapes where every SM has more than one 128 x 160 tile to do anyway; needs
