@@ -18,6 +18,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          *(["-DMKD_ENABLE_TRACE"] if os.environ.get("MKD_TRACE") == "1" else []),  # %globaltimer stamps + timing switches (tools/gemm_trace.py, tools/dbg_epilogue.sh)
          *([f"-DMKD_EPI_PIPE={os.environ['MKD_EPI_PIPE']}"] if os.environ.get("MKD_EPI_PIPE") else []),  # A/B builds of the GEMM epilogue
          *([f"-DMKD_MAX_STAGES={os.environ['MKD_MAX_STAGES']}"] if os.environ.get("MKD_MAX_STAGES") else []),  # pipeline-depth experiments
+         *([f"-DMKD_GEGLU_PIPE={os.environ['MKD_GEGLU_PIPE']}"] if os.environ.get("MKD_GEGLU_PIPE") else []),  # A/B: GEGLU epilogue
          "-Xptxas", "-v"]
 
 

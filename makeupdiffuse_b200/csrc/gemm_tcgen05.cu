@@ -27,6 +27,9 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16;
 #ifndef MKD_MAX_STAGES
 #define MKD_MAX_STAGES 8  // -DMKD_MAX_STAGES=3: shallower TMA ring (profiles/r01_gemm_stage_sweep.txt)
 #endif
+#ifndef MKD_GEGLU_PIPE
+#define MKD_GEGLU_PIPE 1  // GEGLU on the drain / store split with two 80-column panels in flight (3 ring stages)
+#endif
 #ifndef MKD_EPI_PIPE
 #define MKD_EPI_PIPE 1  // 0 = lock-step epilogue everywhere (A/B builds)
 #endif
@@ -333,18 +336,19 @@ template <int BN, int CL, int EPI, int DUAL = 0> struct Cfg {
   // panel -> fused epilogue math -> global), handing double-buffered panels over with named barriers, so that the TMEM
   // read of panel q + 1 (64 B/clk per SM) runs under the shared/global traffic of panel q.  The lock-step version
   // (every thread does both phases, two CTA-wide barriers per panel) overlaps nothing.  EPI_STATS keeps the lock-step
-  // epilogue (its column-sum scratch plus a second staging panel would cost the 3x3 convs a pipeline stage), and so does
-  // EPI_GEGLU (two 80-column panels per tile; with 32-column panels the FF1 GEMM measured 3 % slower).
+  // epilogue (its column-sum scratch plus a second staging panel would cost the 3x3 convs a pipeline stage).  EPI_GEGLU runs the
+  // split scheme on two double-buffered 80-column panels (3 ring stages: FF1 582 -> 607 TFLOP/s; 32-column panels lost 3 %,
+  // 16 store warps 7 %, the erf polynomial on the packed fp32 pipe 10 %: the store side is not issue-bound).
   // (split-K partials of the 256-wide tile: lock-step on 32-column panels, so that FOUR 48 KB stages fit — the coupled
   //  ring measures 516 clk per k-block with 4 stages, 593 with 3: profiles/r01_mma_probe.txt)
   static constexpr bool WIDE_PARTIAL = EPI == 3 /*EPI_PARTIAL*/ && BN == 256;
-  static constexpr bool PIPE = EPI != 4 /*EPI_STATS*/ && EPI != 2 /*EPI_GEGLU*/ && !WIDE_PARTIAL && MKD_EPI_PIPE;
+  static constexpr bool PIPE = EPI != 4 /*EPI_STATS*/ && (EPI != 2 /*EPI_GEGLU*/ || MKD_GEGLU_PIPE) && !WIDE_PARTIAL && MKD_EPI_PIPE;
   // lock-step epilogue threads: 8 warps.  (16 warps for GEGLU — ncu shows 11 300 warp-instructions per 128 x 160 tile at
   // 1.6 IPC per SM — measured 7 % SLOWER on the FF1 GEMM: 578 -> 541 TFLOP/s; the parametrisation stays for experiments.)
   static constexpr int ET = 256;
   static constexpr int THREADS = PIPE ? 512 : 64 + ET + 32;
   // staging panel width (columns); GEGLU needs value + gate groups side by side (even group count)
-  static constexpr int PW = WIDE_PARTIAL ? 32 : (BN % 80 == 0) ? (EPI == 2 /*EPI_GEGLU*/ ? (PIPE ? 32 : 80) : 40) : (BN >= 64 ? 64 : 32);
+  static constexpr int PW = WIDE_PARTIAL ? 32 : (BN % 80 == 0) ? (EPI == 2 /*EPI_GEGLU*/ ? 80 : 40) : (BN >= 64 ? 64 : 32);
   static constexpr int NP = BN / PW;
   static constexpr int LDT = PW + 4;                                      // +4 floats: conflict-free phase-1 writes
   // DUAL (experiment, off by default — see launch()): one work unit = one A tile against TWO adjacent B tiles (both TMEM
