@@ -1218,7 +1218,9 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
   // 10-11: the statistics variants as DUAL kernels (one A tile against two adjacent N tiles), for shapes with more than
   // one 128 x 160 tile per SM and an even number of N tiles (the 3x3 convs of the 32x32 level)
   constexpr bool SP = BN == 160 && CL == 1;
-  constexpr int NV = 13;  // 12: statistics + timestep embedding + y32 (ResBlock conv1 of the levels with fused statistics)
+  // 12: statistics + timestep embedding + y32 (ResBlock conv1), 13: statistics + res32 + y32 (ResBlock conv2), 14: statistics +
+  // res32 + y (SpatialTransformer proj_out) — the operand sets the network actually issues (tools: log of ops.conv2d kwargs)
+  constexpr int NV = 15;
   const KernelFn all[NV] = {gemm_tcgen05_kernel<BN, CL, EPI_PLAIN>, gemm_tcgen05_kernel<BN, CL, EPI_SILU>,
                             gemm_tcgen05_kernel<BN, CL, EG>, gemm_tcgen05_kernel<BN, CL, EPI_PARTIAL>,
                             gemm_tcgen05_kernel<BN, CL, EPI_STATS>,
@@ -1226,18 +1228,20 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
                             gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 4 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_PLAIN, SP ? 5 : 0>,
                             gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0>,
                             gemm_tcgen05_kernel<BN, CL, EPI_STATS, 0, SP ? 1 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 7 : 0, SP ? 1 : 0>,
-                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 10 : 0>};
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 10 : 0>, gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 3 : 0>,
+                            gemm_tcgen05_kernel<BN, CL, EPI_STATS, SP ? 5 : 0>};
   const size_t smems[NV] = {Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_SILU>::SMEM, Cfg<BN, CL, EG>::SMEM,
                             Cfg<BN, CL, EPI_PARTIAL>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM,
                             Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_PLAIN>::SMEM,
                             Cfg<BN, CL, EPI_PLAIN>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM,
-                            Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM};
+                            Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM,
+                            Cfg<BN, CL, EPI_STATS>::SMEM, Cfg<BN, CL, EPI_STATS>::SMEM};
   const int threads[NV] = {Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_SILU>::THREADS, Cfg<BN, CL, EG>::THREADS,
                            Cfg<BN, CL, EPI_PARTIAL>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS,
                            Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_PLAIN>::THREADS,
                            Cfg<BN, CL, EPI_PLAIN>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS,
                            Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::THREADS, Cfg<BN, CL, EPI_STATS, SP ? 1 : 0>::THREADS,
-                           Cfg<BN, CL, EPI_STATS>::THREADS};
+                           Cfg<BN, CL, EPI_STATS>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS, Cfg<BN, CL, EPI_STATS>::THREADS};
   static bool configured = false;
   if (!configured) {
     for (int i = 0; i < NV; ++i) {
@@ -1329,6 +1333,8 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
     const int spec = (ep.res ? 1 : 0) | (ep.y32 ? 2 : 0) | (ep.y ? 4 : 0);
     if (variant == 0 && spec >= 2 && spec <= 5) variant = 3 + spec;
     else if (variant == 4 && spec == 7) variant = 9;
+    else if (variant == 4 && spec == 3) variant = 13;
+    else if (variant == 4 && spec == 5) variant = 14;
   } else if (SP && variant == 4 && ep.emb && !ep.res && ep.y32 && !ep.y && !mp.debug) {
     variant = 12;
   }

@@ -32,7 +32,7 @@ SHAPES = {
     "conv1280_4x4": (16, 4, 4, 1280, 1280, 3, "emb32"),
     "conv2560_4x4": (16, 4, 4, 2560, 1280, 3, "emb32"),
     "conv320_c1": (16, 32, 32, 320, 320, 3, "emb32st"),   # ResBlock conv1 as the network runs it: + GroupNorm statistics
-    "conv320_c2": (16, 32, 32, 320, 320, 3, "res32st"),   # ResBlock conv2: fp32 residual, bf16 + fp32 out, statistics
+    "conv320_c2": (16, 32, 32, 320, 320, 3, "res32st"),   # ResBlock conv2: fp32 residual, fp32 out, statistics
     "conv960_c1": (16, 32, 32, 960, 320, 3, "emb32st"),
     "up640": (16, 16, 16, 640, 640, 3, "upst"),           # Upsample conv: 16x16 -> 32x32, N = 640
     "ff1_320": (16, 32, 32, 320, 2560, 1, "geglu"),
@@ -69,7 +69,7 @@ for name, (N, H, W, C, K, R, epi) in SHAPES.items():
             args = (x, w, None)
             kw.update(emb=torch.randn(N, K, device=DEV).bfloat16(), y32=y32, stats=st)
         elif epi == "res32st":
-            args = (x, w, torch.empty(Mo, K, device=DEV, dtype=torch.bfloat16))
+            args = (x, w, None)  # as the network issues it: fp32 residual in, fp32 out, statistics, no bf16 copy
             kw.update(residual=torch.randn(Mo, K, device=DEV), y32=y32, stats=st)
         else:
             args = (x, w, torch.empty(Mo, K, device=DEV, dtype=torch.bfloat16))
