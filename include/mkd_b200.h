@@ -31,14 +31,16 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 6
+#define MKD_ABI_VERSION 7
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 
 enum { MKD_BF16 = 0, MKD_F32 = 1 };
 enum { MKD_OK = 0, MKD_E_INVALID = -1, MKD_E_ALIGN = -2, MKD_E_ARCH = -3, MKD_E_CUDA = -4, MKD_E_WORKSPACE = -5 };
 enum { MKD_ACT_NONE = 0, MKD_ACT_SILU = 1, MKD_ACT_GEGLU = 2 };
-enum { MKD_PATH_AUTO = 0, MKD_PATH_GENERIC = 1, MKD_PATH_TCGEN05 = 2 };
+enum { MKD_PATH_AUTO = 0, MKD_PATH_GENERIC = 1, MKD_PATH_TCGEN05 = 2,
+       /* tests / benchmarks: force one of the two tensor-core kernels (mkd_conv2d_path reports MKD_PATH_TCGEN05 for both) */
+       MKD_PATH_TCGEN05_SINGLE = 3, MKD_PATH_TCGEN05_PAIR = 4 };
 
 /* ---- probes ------------------------------------------------------------------------------------------- */
 int mkd_abi_version(void);          /* == MKD_ABI_VERSION */

@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libmkd_b200.so")
 
 MKD_BF16, MKD_F32 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
-PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
-ABI_VERSION = 6
+PATH_AUTO, PATH_GENERIC, PATH_TCGEN05, PATH_TCGEN05_SINGLE, PATH_TCGEN05_PAIR = 0, 1, 2, 3, 4
+ABI_VERSION = 7
 
 
 class ConvDesc(C.Structure):

@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmkd_b200.so")
-SOURCES = ["elementwise.cu", "norm.cu", "conv_generic.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tcgen05.cu"]
+SOURCES = ["elementwise.cu", "norm.cu", "conv_generic.cu", "gemm_tcgen05.cu", "gemm_pair.cu", "attention.cu", "attention_tcgen05.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          *(["-DMKD_ENABLE_TRACE"] if os.environ.get("MKD_TRACE") == "1" else []),  # %globaltimer stamps + timing switches (tools/gemm_trace.py, tools/dbg_epilogue.sh)

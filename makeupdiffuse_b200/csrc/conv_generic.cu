@@ -216,7 +216,7 @@ static int validate(const mkd_conv_desc* d) {
   MKD_REQUIRE(Hin + 2 * d->pad + d->pad_hi_extra >= d->R && Win + 2 * d->pad + d->pad_hi_extra >= d->S, MKD_E_INVALID,
               "conv2d: filter larger than input");
   MKD_REQUIRE((int64_t)d->N * Hin * Win < (1ll << 31), MKD_E_INVALID, "conv2d: too many pixels");
-  MKD_REQUIRE(d->path >= MKD_PATH_AUTO && d->path <= MKD_PATH_TCGEN05, MKD_E_INVALID, "conv2d: bad path");
+  MKD_REQUIRE(d->path >= MKD_PATH_AUTO && d->path <= MKD_PATH_TCGEN05_PAIR, MKD_E_INVALID, "conv2d: bad path");
   return MKD_OK;
 }
 
@@ -225,7 +225,7 @@ extern "C" int mkd_conv2d_path(const mkd_conv_desc* d) {
   if (rc) return rc;
   if (d->path == MKD_PATH_GENERIC) return MKD_PATH_GENERIC;
   bool ok = mkd::conv2d_tcgen05_supported(d);
-  if (d->path == MKD_PATH_TCGEN05) {
+  if (d->path >= MKD_PATH_TCGEN05) {  // forced tensor-core kernel (either of the two)
     if (!ok) return MKD_E_INVALID;  // conv2d_tcgen05_supported() left the reason in mkd_last_error()
     return MKD_PATH_TCGEN05;
   }

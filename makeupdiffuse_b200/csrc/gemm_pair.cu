@@ -1,0 +1,911 @@
+// CTA-pair implicit-GEMM convolution / GEMM on the 5th-generation tensor cores (sm_100a), cta_group::2:
+//
+//   D[256 x UN] (fp32; rows 0-127 in the leader CTA's TMEM, rows 128-255 in its peer's)
+//        += A[256 x 64] (bf16, 128 rows from each CTA's shared memory) * B[UN x 64]^T (UN / 2 weight rows from each CTA)
+//
+// One work unit = 256 output rows x (NSUB * UN) output channels, computed by the two SMs of a cluster of two CTAs.
+// Each CTA streams only its own 128 rows of A and HALF of the unit's weight rows per k-block; with NSUB = 2 every A
+// tile meets two N = 160 weight tiles, so per 64 of K an SM fetches 16 KB of activations for 640 tensor-core cycles
+// where the single-CTA kernel (gemm_tcgen05.cu) fetches 16 KB for 320.  That ratio is what paced the old main loop:
+// the activation tiles are distinct per CTA and arrive from L2 at ~44 B/clk per SM when all SMs pull
+// (tools/mma_probe.cu: 366 clk per k-block for the TMA stream alone against 320-345 clk of MMAs).
+//
+// Warp roles (384 threads; both CTAs of the pair run the same code):
+//   warp 0      TMA producer: A box (own rows) + NSUB B boxes (own half of the weight rows) per k-block into a
+//               `stages`-deep ring; loads are the .cta_group::2 form, their bytes complete on the LEADER's full barrier.
+//   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2, M = 256, N = UN; its commits are multicast to
+//               both CTAs' empty / tmem_full barriers.  Owns the (cta_group::2) TMEM allocation.
+//   warp 2      epilogue DMA thread (lane 0): TMA loads of the residual panels into panel slots ahead of the epilogue
+//               warps, TMA stores of the finished panels (cp.async.bulk.tensor shared -> global), slot recycling by
+//               bulk-group completion.  No thread ever issues a global load or store for tile data.
+//   warps 4-11  epilogue: two warpgroups take alternate 32-column panels.  thread = accumulator row = TMEM lane:
+//               tcgen05.ld 32 columns -> (+bias, +timestep embedding) * alpha + residual [SiLU] -> fp32 and / or bf16
+//               panel in shared memory, in the 128B / 64B TMA swizzle, so every shared-memory access is conflict
+//               free; optional GroupNorm statistics (column sum, sum of squares over the CTA's 128 rows) by a
+//               register transpose-reduction (31 shuffles per statistic) + one 4-warp combine.
+//   GEGLU mode (UN = 256, weight rows blocked [128 value | 128 gate]): value columns 0-127 come from the leader's
+//   weight rows, gate columns 128-255 from the peer's; a panel = 32 value + 32 gate columns -> 32 bf16 outputs.
+//
+// Split-K units write raw fp32 partials (same epilogue, no operands) to the workspace [split][M][N]; the reducer of
+// gemm_tcgen05.cu applies the fused epilogue.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+using namespace mkd;
+
+namespace mkd {
+int splitk_reduce(const mkd_conv_desc* d, int M, int pix_per_img, int splits, cudaStream_t stream);  // gemm_tcgen05.cu
+}
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;           // 16 KB: one CTA's activation tile per k-block
+constexpr int PANEL = 32;                      // epilogue panel width (columns)
+constexpr int P32_BYTES = BM * PANEL * 4;      // 16 KB: fp32 panel (128 B rows, SWIZZLE_128B)
+constexpr int P16_BYTES = BM * PANEL * 2;      // 8 KB: bf16 panel (64 B rows, SWIZZLE_64B)
+constexpr int MAX_STAGES = 8, MAX_SLOTS = 8;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8;    // EPI_WARP0 % 4 == 0: warp w reads TMEM lanes [32 (w % 4), +32)
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int SCRATCH_BYTES = 2 /*warpgroups*/ * 2 /*buffers*/ * 4 /*quadrants*/ * 32 * 8;  // GroupNorm partials
+constexpr int BAR_BYTES = 512;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct PairP {
+  // main loop
+  int kblocks, kb_per_split;
+  int conv, cblocks, S, pad;
+  int Wb, Hb, Nb, tiles_w, tiles_h;
+  int m_tiles, m_pairs, n_units, num_units;  // unit -> (n_unit fastest, m_pair, split)
+  int stages, npb, slot_bytes, off16;        // shared-memory ring depth; panel slots and their layout
+  // epilogue
+  int M, pix_per_img, lde;
+  int has_res32, has_res16, has_y32, has_y16, act;
+  int partial_rows;                          // split-K: fp32 partial rows per split (M), else 0
+  float alpha;
+  const float* bias;
+  const bf16* emb;
+  float2* stats;
+  int stats_ld;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// A wait that cannot hang the GPU: a protocol error (a barrier that is never completed) traps after ~4 s instead of
+// spinning until the driver's watchdog — or the box's time limit — kills the process.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("gemm_pair: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 255u) == 0) {
+      const unsigned long long now = gtimer();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) mbar_timeout(addr, parity);
+    }
+  }
+}
+// Shared-window addresses carry the CTA rank of a pair in bit 24: clearing it names the same offset in the leader.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// 2-SM TMA loads: the box lands in the ISSUING CTA's shared memory, its bytes complete on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// CTA-local TMA load (residual panels) and store (finished panels)
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();  // role branches diverge lanes: reconverge before the .aligned barrier
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// one MMA for the pair: D[256 x N], A 128 rows from each CTA's shared memory, B N/2 rows from each (same offsets in both)
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// commit of the pair's MMAs issued so far, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// the registers of an asynchronous tcgen05.ld carry no dependence on tcgen05.wait::ld: this empty asm "rewrites" them
+// after the wait (volatile asms keep their order), so that no use can be scheduled ahead of it
+__device__ __forceinline__ void reg_fence32(uint32_t (&r)[32]) {
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D fp32, A / B bf16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Unit {
+  int n_unit, m_pair, split, kb0, kb1;
+};
+__device__ __forceinline__ Unit decode_unit(const PairP& p, int u) {
+  Unit t;
+  t.n_unit = u % p.n_units;
+  const int rest = u / p.n_units;
+  t.m_pair = rest % p.m_pairs;
+  t.split = rest / p.m_pairs;
+  t.kb0 = t.split * p.kb_per_split;
+  t.kb1 = min(p.kblocks, t.kb0 + p.kb_per_split);
+  return t;
+}
+
+enum { MODE_PLAIN = 0, MODE_GEGLU = 1 };
+
+template <int UN, int NSUB, int MODE, int STATS>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                 const __grid_constant__ CUtensorMap r32map, const __grid_constant__ CUtensorMap r16map,
+                 const __grid_constant__ CUtensorMap y32map, const __grid_constant__ CUtensorMap y16map, const PairP p) {
+  constexpr int BH_BYTES = (UN / 2) * BK * 2;            // one CTA's half of a weight tile per k-block
+  constexpr int STAGE_BYTES = A_BYTES + NSUB * BH_BYTES;
+  constexpr int ACC_COLS = NSUB * UN;
+  constexpr int TS = 2 * ACC_COLS <= TMEM_COLS ? 2 : 1;  // accumulator buffers in TMEM
+  constexpr int PPS = UN / PANEL;                        // panels per sub-tile (plain)
+  constexpr int PPU = MODE == MODE_GEGLU ? UN / 2 / PANEL : NSUB * PPS;  // panels per unit
+  static_assert(MODE == MODE_PLAIN || (UN == 256 && NSUB == 1), "GEGLU: one 256-wide tile, [128 value | 128 gate]");
+  static_assert(UN % 32 == 0 && UN <= 256 && ACC_COLS <= TMEM_COLS, "tile shape");
+
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* slots = smem + p.stages * STAGE_BYTES;
+  float2* scratch = reinterpret_cast<float2*>(slots + p.npb * p.slot_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + (STATS ? SCRATCH_BYTES : 0));
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [MAX_SLOTS] slot is free and its residual (if any) has landed
+  uint64_t* computed_bar = res_full_bar + MAX_SLOTS; // [MAX_SLOTS] the panel in the slot is ready to be stored
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(computed_bar + MAX_SLOTS);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&bmap)) : "memory");
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(full_bar + i, 2);   // (leader's copy is the live one) both producers arrive; both CTAs' bytes land here
+      mbar_init(empty_bar + i, 1);  // multicast commit of the leader's MMA warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full_bar + i, 1);               // multicast commit
+      mbar_init(tmem_empty_bar + i, 2 * EPI_WARPS);  // (leader's copy) every epilogue warp of both CTAs
+    }
+    for (int i = 0; i < MAX_SLOTS; ++i) {
+      mbar_init(res_full_bar + i, 1);
+      mbar_init(computed_bar + i, 4);  // the four warps of the warpgroup that owns the panel
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  cluster_sync_all();  // both CTAs are resident before the paired TMEM allocation
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // the peer's barriers exist before anything arrives on them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // from here on global memory written by the previous kernel is read and its outputs may be overwritten
+
+  if (warp == 0) {
+    // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+    int s = 0;
+    uint32_t ph = 0;
+#pragma unroll 1
+    for (int u = pair_id; u < p.num_units; u += num_pairs) {
+      const Unit t = decode_unit(p, u);
+      const int m_tile = 2 * t.m_pair + (int)rank;
+      int w0 = 0, h0 = 0, n0 = 0;
+      if (p.conv) {
+        const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+        w0 = tw * p.Wb;
+        h0 = th * p.Hb;
+        n0 = tn * p.Nb;
+      }
+      const int m0 = m_tile * BM;
+      // filter-tap walk (r, sx, cb) kept incrementally: no integer divisions in the k loop
+      const int tap0 = t.kb0 / p.cblocks;
+      int cb = t.kb0 - tap0 * p.cblocks, r = tap0 / p.S;
+      int sx = tap0 - r * p.S;
+      const int nb = t.n_unit * (NSUB * UN) + (int)rank * (UN / 2);  // this CTA's half of sub-tile 0's weight rows
+#pragma unroll 1
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        mbar_wait(empty_bar + s, ph ^ 1);  // (own copy) the MMAs that read this slot have retired
+        if (elect_one()) {
+          unsigned char* sa = smem + s * STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(full_bar + s, 2 * STAGE_BYTES);
+          else mbar_arrive_cluster(full_bar + s, 0);
+          if (p.conv) tma_load_4d_2sm(&amap, full_bar + s, sa, cb * BK, w0 + sx - p.pad, h0 + r - p.pad, n0);
+          else tma_load_2d_2sm(&amap, full_bar + s, sa, kb * BK, m0);
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub)
+            tma_load_2d_2sm(&bmap, full_bar + s, sa + A_BYTES + sub * BH_BYTES, kb * BK, nb + sub * UN);
+        }
+        __syncwarp();
+        if (++cb == p.cblocks) {
+          cb = 0;
+          if (++sx == p.S) {
+            sx = 0;
+            ++r;
+          }
+        }
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only =====
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(UN, 2 * BM);
+      int s = 0, j = 0;
+      uint32_t ph = 0;
+#pragma unroll 1
+      for (int u = pair_id; u < p.num_units; u += num_pairs, ++j) {
+        const Unit t = decode_unit(p, u);
+        const int ts = j % TS, use = j / TS;
+        mbar_wait(tmem_empty_bar + ts, (use & 1) ^ 1);  // both CTAs' epilogue warps have drained this accumulator buffer
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(ts * ACC_COLS);
+#pragma unroll 1
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(full_bar + s, ph);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(sa);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+#pragma unroll
+              for (int sub = 0; sub < NSUB; ++sub) {
+                const uint64_t bdesc = make_smem_desc(sa + A_BYTES + sub * BH_BYTES);
+                // advance K inside the 128-byte swizzle atom: +32 bytes per UMMA_K (encoded >> 4)
+                umma_bf16_2sm(tacc + (uint32_t)(sub * UN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                              (kb > t.kb0 || k) ? 1u : 0u);
+              }
+            }
+            tcgen05_commit_2sm(empty_bar + s, (uint16_t)3);  // frees the slot in both CTAs once these MMAs retire
+            if (kb == t.kb1 - 1) tcgen05_commit_2sm(tmem_full_bar + ts, (uint16_t)3);
+          }
+          __syncwarp();
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== epilogue DMA thread: residual panel loads, finished panel stores, slot recycling =====
+    if (lane == 0 && pair_id < p.num_units) {
+      const int my_units = (p.num_units - pair_id + num_pairs - 1) / num_pairs;
+      const int total = my_units * PPU;
+      const int D = p.npb >= 3 ? p.npb - 2 : p.npb - 1;  // the store of panel j is issued D panels after its slot was armed
+      const bool any_res = p.has_res32 || p.has_res16;
+      const uint32_t res_bytes = (p.has_res32 ? P32_BYTES : 0) + (p.has_res16 ? P16_BYTES : 0);
+      int lu = pair_id, lq = 0, lb = 0;   // load cursor: unit, panel within the unit, slot
+      int su = pair_id, sq = 0, sb = 0;   // store cursor
+      uint32_t sph = 0;
+#pragma unroll 1
+      for (int i = 0; i < total + D; ++i) {
+        if (i < total) {
+          // the slot's previous panel (i - npb) was stored npb - D iterations ago: at most npb - D - 1 younger groups
+          if (i >= p.npb) {
+            if (D == p.npb - 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
+          const Unit t = decode_unit(p, lu);
+          const int m_tile = 2 * t.m_pair + (int)rank;
+          const int sub = lq / PPS, pp = lq - sub * PPS;
+          const int gcol = t.n_unit * (NSUB * UN) + sub * UN + pp * PANEL;
+          unsigned char* slot = slots + lb * p.slot_bytes;
+          if (any_res && m_tile < p.m_tiles) {
+            mbar_expect_tx(res_full_bar + lb, res_bytes);
+            if (p.has_res32) tma_load_2d(&r32map, res_full_bar + lb, slot, gcol, m_tile * BM);
+            if (p.has_res16) tma_load_2d(&r16map, res_full_bar + lb, slot + p.off16, gcol, m_tile * BM);
+          } else {
+            mbar_arrive(res_full_bar + lb);  // nothing to load: the slot is simply free
+          }
+          if (++lq == PPU) {
+            lq = 0;
+            lu += num_pairs;
+          }
+          if (++lb == p.npb) lb = 0;
+        }
+        if (i >= D) {
+          const Unit t = decode_unit(p, su);
+          const int m_tile = 2 * t.m_pair + (int)rank;
+          int gcol;
+          if (MODE == MODE_GEGLU) gcol = t.n_unit * (UN / 2) + sq * PANEL;
+          else {
+            const int sub = sq / PPS, pp = sq - sub * PPS;
+            gcol = t.n_unit * (NSUB * UN) + sub * UN + pp * PANEL;
+          }
+          unsigned char* slot = slots + sb * p.slot_bytes;
+          mbar_wait(computed_bar + sb, sph);
+          if (m_tile < p.m_tiles) {
+            if (p.has_y32) tma_store_2d(&y32map, slot, gcol, m_tile * BM + t.split * p.partial_rows);
+            if (p.has_y16) tma_store_2d(&y16map, slot + p.off16, gcol, m_tile * BM);
+          }
+          bulk_commit();
+          if (++sq == PPU) {
+            sq = 0;
+            su += num_pairs;
+          }
+          if (++sb == p.npb) {
+            sb = 0;
+            sph ^= 1;
+          }
+        }
+      }
+      bulk_wait_all();
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===== epilogue warps =====
+    const int wg = (warp - EPI_WARP0) >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;                      // accumulator row of this thread = TMEM lane
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const uint32_t sw128 = (uint32_t)(row & 7) << 4;       // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+    const uint32_t sw64 = (uint32_t)((row >> 1) & 3) << 4; // SWIZZLE_64B:  16-byte chunk index ^= (row / 2) % 4
+    const uint32_t slots_u32 = smem_u32(slots);
+    int g = 0, b = 0, j = 0;
+    uint32_t rph = 0;
+    [[maybe_unused]] int lp = 0;  // statistics scratch buffer parity (panels this warpgroup has reduced)
+#pragma unroll 1
+    for (int u = pair_id; u < p.num_units; u += num_pairs, ++j) {
+      const Unit t = decode_unit(p, u);
+      const int ts = j % TS, use = j / TS;
+      const int m_tile = 2 * t.m_pair + (int)rank;
+      const bool valid = m_tile < p.m_tiles;
+      const int m = m_tile * BM + row;
+      const int q_last = (((g + PPU - 1) & 1) == wg) ? PPU - 1 : PPU - 2;  // this warpgroup's last panel of the unit
+      bool waited = false;
+#pragma unroll 1
+      for (int q = 0; q < PPU; ++q, ++g) {
+        if ((g & 1) == wg) {
+          if (!waited) {
+            mbar_wait(tmem_full_bar + ts, use & 1);
+            tcgen05_fence_after();
+            waited = true;
+          }
+          const uint32_t s32 = slots_u32 + (uint32_t)(b * p.slot_bytes) + (uint32_t)(row * 128);
+          const uint32_t s16 = slots_u32 + (uint32_t)(b * p.slot_bytes + p.off16) + (uint32_t)(row * 64);
+          if constexpr (MODE == MODE_GEGLU) {
+            uint32_t av[32], ag[32];
+            const uint32_t taddr = tmem_base + lane_bits + (uint32_t)(ts * ACC_COLS + q * PANEL);
+            tmem_ld32_nowait(taddr, av);
+            tmem_ld32_nowait(taddr + UN / 2, ag);
+            const int brow = t.n_unit * UN + q * PANEL;  // weight / bias row of the panel's first value channel
+            const float4* bvp = reinterpret_cast<const float4*>(p.bias + brow);
+            const float4* bgp = reinterpret_cast<const float4*>(p.bias + brow + UN / 2);
+            mbar_wait(res_full_bar + b, rph);  // the slot is free
+            tmem_ld_wait();
+            reg_fence32(av);
+            reg_fence32(ag);
+            if (q == q_last) {  // every TMEM read of this unit by this warp is done
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(tmem_empty_bar + ts, 0);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {  // 8 outputs per 16-byte chunk
+              float o[8];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = 2 * c + h;
+                // bias rows of this 4-column piece (uniform addresses: L1 broadcast)
+                const float4 bv = p.bias ? __ldg(bvp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 bg = p.bias ? __ldg(bgp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[4 * h + 0] = (__uint_as_float(av[4 * i + 0]) + bv.x) * gelu_erf_fast(__uint_as_float(ag[4 * i + 0]) + bg.x);
+                o[4 * h + 1] = (__uint_as_float(av[4 * i + 1]) + bv.y) * gelu_erf_fast(__uint_as_float(ag[4 * i + 1]) + bg.y);
+                o[4 * h + 2] = (__uint_as_float(av[4 * i + 2]) + bv.z) * gelu_erf_fast(__uint_as_float(ag[4 * i + 2]) + bg.z);
+                o[4 * h + 3] = (__uint_as_float(av[4 * i + 3]) + bv.w) * gelu_erf_fast(__uint_as_float(ag[4 * i + 3]) + bg.w);
+              }
+              sts128u(s16 + (((uint32_t)c << 4) ^ sw64), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                      pack_bf16(o[6], o[7]));
+            }
+          } else {
+            const int sub = q / PPS, pp = q - sub * PPS;
+            const int gcol = t.n_unit * (NSUB * UN) + sub * UN + pp * PANEL;
+            uint32_t acc[32];
+            tmem_ld32_nowait(tmem_base + lane_bits + (uint32_t)(ts * ACC_COLS + sub * UN + pp * PANEL), acc);
+            // per-column operands, requested while the TMEM read is in flight (uniform addresses: one L1 line each)
+            float4 bb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              bb[i] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint4 eb[4];
+            if (p.emb) {
+              const uint4* er = reinterpret_cast<const uint4*>(p.emb + (int64_t)(min(m, p.M - 1) / p.pix_per_img) * p.lde + gcol);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) eb[c] = __ldg(er + c);
+            }
+            mbar_wait(res_full_bar + b, rph);  // the slot is free and its residual panel (if any) has landed
+            uint4 rb[4];
+            if (p.has_res16) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) rb[c] = lds128u(s16 + (((uint32_t)c << 4) ^ sw64));
+            }
+            tmem_ld_wait();
+            reg_fence32(acc);
+            if (q == q_last) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(tmem_empty_bar + ts, 0);
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float x0 = __uint_as_float(acc[4 * i + 0]) + bb[i].x, x1 = __uint_as_float(acc[4 * i + 1]) + bb[i].y;
+              float x2 = __uint_as_float(acc[4 * i + 2]) + bb[i].z, x3 = __uint_as_float(acc[4 * i + 3]) + bb[i].w;
+              if (p.emb) {
+                const uint32_t e01 = (i & 1) ? eb[i >> 1].z : eb[i >> 1].x, e23 = (i & 1) ? eb[i >> 1].w : eb[i >> 1].y;
+                x0 += __uint_as_float(e01 << 16);
+                x1 += __uint_as_float(e01 & 0xFFFF0000u);
+                x2 += __uint_as_float(e23 << 16);
+                x3 += __uint_as_float(e23 & 0xFFFF0000u);
+              }
+              x0 *= p.alpha; x1 *= p.alpha; x2 *= p.alpha; x3 *= p.alpha;
+              if (p.has_res32) {
+                const float4 r = lds128(s32 + (((uint32_t)i << 4) ^ sw128));
+                x0 += r.x; x1 += r.y; x2 += r.z; x3 += r.w;
+              }
+              if (p.has_res16) {
+                const uint32_t r01 = (i & 1) ? rb[i >> 1].z : rb[i >> 1].x, r23 = (i & 1) ? rb[i >> 1].w : rb[i >> 1].y;
+                x0 += __uint_as_float(r01 << 16);
+                x1 += __uint_as_float(r01 & 0xFFFF0000u);
+                x2 += __uint_as_float(r23 << 16);
+                x3 += __uint_as_float(r23 & 0xFFFF0000u);
+              }
+              if (p.act == MKD_ACT_SILU) {
+                x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3);
+              }
+              v[4 * i + 0] = x0; v[4 * i + 1] = x1; v[4 * i + 2] = x2; v[4 * i + 3] = x3;
+              if (p.has_y32) sts128(s32 + (((uint32_t)i << 4) ^ sw128), x0, x1, x2, x3);
+            }
+            if (p.has_y16) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                sts128u(s16 + (((uint32_t)c << 4) ^ sw64), pack_bf16(v[8 * c + 0], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                        pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+            }
+            if constexpr (STATS != 0) {
+              // column (sum, sum of squares) over this warp's 32 rows by a register transpose-reduction: after the
+              // step with offset `off` a lane keeps the half of its columns selected by bit `off` of its lane id, so
+              // lane l ends with column l.  Fixed order: deterministic.
+              float xq[32];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) xq[c] = v[c] * v[c];
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int c = 0; c < off; ++c) {
+                  const float send_s = up ? v[c] : v[c + off], keep_s = up ? v[c + off] : v[c];
+                  const float send_q = up ? xq[c] : xq[c + off], keep_q = up ? xq[c + off] : xq[c];
+                  v[c] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                  xq[c] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+                }
+              }
+              float2* scr = scratch + ((wg * 2 + (lp & 1)) * 4) * 32;
+              scr[quad * 32 + lane] = make_float2(v[0], xq[0]);
+              asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory");
+              if (quad == 0 && valid) {
+                const float2 a0 = scr[lane], a1 = scr[32 + lane], a2 = scr[64 + lane], a3 = scr[96 + lane];
+                p.stats[(int64_t)m_tile * p.stats_ld + gcol + lane] =
+                    make_float2(((a0.x + a1.x) + a2.x) + a3.x, ((a0.y + a1.y) + a2.y) + a3.y);
+              }
+              ++lp;
+            }
+          }
+          fence_proxy_async();  // this thread's panel writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(computed_bar + b);
+        }
+        if (++b == p.npb) {
+          b = 0;
+          rph ^= 1;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // no CTA leaves while its peer can still arrive on its barriers or the pair's MMAs read its smem
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(q);
+  }
+  return fn;
+}
+int encode(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+           const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw) {
+  EncodeFn fn = get_encode();
+  MKD_REQUIRE(fn != nullptr, MKD_E_CUDA, "cuTensorMapEncodeTiled entry point not found (driver too old?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MKD_REQUIRE(r == CUDA_SUCCESS, MKD_E_CUDA, "gemm_pair: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return MKD_OK;
+}
+// [rows, cols] row-major matrix of fp32 / bf16 with row pitch ld (elements); box = 32 columns x 128 rows
+int encode_panel_map(CUtensorMap* map, bool f32, const void* base, int64_t rows, int cols, int ld) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {PANEL, BM};
+  return encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 2, dims, str, box,
+                f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+struct PairPlan {
+  int un, nsub, geglu, stats;
+  int conv, M, Ktot, P, Q, Wb, Hb, Nb, tiles_w, tiles_h, m_tiles;
+  int splits, kb_per_split, stages, npb, slot_bytes, off16;
+};
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Which descriptors the pair kernel takes (stride 1, no upsample: the caller has materialised those), and how.
+bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
+  if (d->dtype != MKD_BF16 || d->stride != 1 || d->upsample || d->pad_hi_extra) return false;
+  if (d->C % BK != 0 || d->R != d->S || (d->R != 1 && d->R != 3) || d->pad != d->R / 2) return false;
+  if (d->ldx % 8 || !aligned16(d->x) || !aligned16(d->w)) return false;
+  if (d->bias && !aligned16(d->bias)) return false;
+  if (d->y && (d->ldy % 8 || !aligned16(d->y))) return false;
+  if (d->y32 && (d->ldy32 % 4 || !aligned16(d->y32))) return false;
+  if (d->residual && (!aligned16(d->residual) || d->ldr % (d->residual_dtype == MKD_F32 ? 4 : 8))) return false;
+  if (d->emb && (d->lde % 8 || !aligned16(d->emb))) return false;
+  if (d->stats && (d->act != MKD_ACT_NONE || d->stats_ld < d->K || ((uintptr_t)d->stats & 7))) return false;
+  pl.conv = d->R == 3;
+  pl.P = d->H;
+  pl.Q = d->W;
+  pl.M = d->N * d->H * d->W;
+  pl.Ktot = d->R * d->S * d->C;
+  // ragged M: TMA zero-fills the rows it loads beyond M and clips the rows it stores; statistics need whole tiles
+  if (d->stats && pl.M % BM != 0) return false;
+  if (pl.conv) {
+    if (!is_pow2(pl.Q) || !is_pow2(pl.P)) return false;
+    pl.Wb = pl.Q < BM ? pl.Q : BM;
+    pl.Hb = BM / pl.Wb < pl.P ? BM / pl.Wb : pl.P;
+    pl.Nb = BM / (pl.Wb * pl.Hb);
+    pl.tiles_w = pl.Q / pl.Wb;
+    pl.tiles_h = pl.P / pl.Hb;
+    pl.m_tiles = pl.tiles_w * pl.tiles_h * ((d->N + pl.Nb - 1) / pl.Nb);
+  } else {
+    pl.Wb = pl.Hb = pl.Nb = pl.tiles_w = pl.tiles_h = 1;
+    pl.m_tiles = (pl.M + BM - 1) / BM;
+  }
+  const int m_pairs = (pl.m_tiles + 1) / 2, kblocks = pl.Ktot / BK;
+  pl.stats = d->stats != nullptr;
+  pl.splits = 1;
+  if (d->act == MKD_ACT_GEGLU) {
+    if (d->geglu_block != 128 || d->K % 256 || !d->y || d->y32 || d->residual || d->emb || d->alpha != 1.0f || d->stats) return false;
+    pl.geglu = 1;
+    pl.un = 256;
+    pl.nsub = 1;
+  } else {
+    if (d->K % 160 != 0) return false;
+    if (d->act != MKD_ACT_NONE && d->act != MKD_ACT_SILU) return false;
+    pl.geglu = 0;
+    pl.un = 160;
+    // two N = 160 sub-tiles per A tile where that still leaves enough units for the 74 pairs (deep-K 32x32-level convs),
+    // or where the unit count is so small that the work is split along K anyway (8x8 / 4x4 levels)
+    const int units1 = m_pairs * (d->K / 160), units2 = d->K % 320 == 0 ? m_pairs * (d->K / 320) : 0;
+    const bool can_split = d->workspace && !d->stats && kblocks >= 32;
+    pl.nsub = 1;
+    if (units2 >= 48 && kblocks >= 16) pl.nsub = 2;
+    else if (units2 > 0 && units1 < 37 && can_split && kblocks >= 64) pl.nsub = 2;
+    const int units = pl.nsub == 2 ? units2 : units1;
+    if (units < 37 && can_split) {
+      int s = 74 / units;
+      if (s > kblocks / 12) s = kblocks / 12;
+      if (s > 16) s = 16;
+      while (s > 1 && (size_t)s * pl.M * d->K * sizeof(float) > d->workspace_bytes) --s;
+      if (s > 1) pl.splits = s;
+    }
+    // too few units to be worth a cluster launch: leave tiny problems to the single-CTA kernel (more, smaller tiles)
+    if (!forced && units * pl.splits < 24) return false;
+  }
+  pl.kb_per_split = (kblocks + pl.splits - 1) / pl.splits;
+  pl.splits = (kblocks + pl.kb_per_split - 1) / pl.kb_per_split;
+  // shared memory: ring stages + panel slots
+  const bool partial = pl.splits > 1;
+  const bool any32 = partial || d->y32 || (d->residual && d->residual_dtype == MKD_F32);
+  const bool any16 = !partial && (d->y || (d->residual && d->residual_dtype == MKD_BF16));
+  pl.slot_bytes = (any32 ? P32_BYTES : 0) + (any16 ? P16_BYTES : 0);
+  pl.off16 = any32 ? P32_BYTES : 0;
+  const int stage_bytes = A_BYTES + pl.nsub * (pl.un / 2) * BK * 2;
+  const int budget = SMEM_LIMIT - 1024 - BAR_BYTES - (pl.stats ? SCRATCH_BYTES : 0);
+  pl.stages = pl.kb_per_split >= 12 ? 4 : 3;
+  if (pl.stages > pl.kb_per_split && pl.kb_per_split >= 2) pl.stages = pl.kb_per_split < 3 ? 2 : 3;
+  pl.npb = (budget - pl.stages * stage_bytes) / pl.slot_bytes;
+  if (pl.npb > MAX_SLOTS) pl.npb = MAX_SLOTS;
+  while (pl.npb < 3 && pl.stages > 2) {  // (not reached with the shapes above; keeps the slot ring workable)
+    --pl.stages;
+    pl.npb = (budget - pl.stages * stage_bytes) / pl.slot_bytes;
+  }
+  if (pl.npb > MAX_SLOTS) pl.npb = MAX_SLOTS;
+  if (pl.npb < 2) return false;
+  // spare shared memory goes to ring stages
+  while (pl.stages < 6 && pl.kb_per_split > pl.stages && budget - (pl.stages + 1) * stage_bytes - pl.npb * pl.slot_bytes >= 0) ++pl.stages;
+  return true;
+}
+
+template <int UN, int NSUB, int MODE, int STATS>
+int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
+  auto kernel = gemm_pair_kernel<UN, NSUB, MODE, STATS>;
+  constexpr int STAGE_BYTES = A_BYTES + NSUB * (UN / 2) * BK * 2;
+  const size_t smem = 1024 + (size_t)pl.stages * STAGE_BYTES + (size_t)pl.npb * pl.slot_bytes + (STATS ? SCRATCH_BYTES : 0) + BAR_BYTES;
+  MKD_REQUIRE(smem <= (size_t)SMEM_LIMIT, MKD_E_INVALID, "gemm_pair: shared memory plan %zu exceeds 227 KB", smem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "gemm_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const bool partial = pl.splits > 1;
+  CUtensorMap amap, bmap, r32map, r16map, y32map, y16map;
+  int rc;
+  if (pl.conv) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t str[3] = {(cuuint64_t)d->ldx * 2, (cuuint64_t)d->ldx * 2 * d->W, (cuuint64_t)d->ldx * 2 * d->W * d->H};
+    cuuint32_t box[4] = {BK, (cuuint32_t)pl.Wb, (cuuint32_t)pl.Hb, (cuuint32_t)pl.Nb};
+    rc = encode(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)d->C, (cuuint64_t)pl.M};
+    cuuint64_t str[1] = {(cuuint64_t)d->ldx * 2};
+    cuuint32_t box[2] = {BK, BM};
+    rc = encode(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->x, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (rc) return rc;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)pl.Ktot, (cuuint64_t)d->K};
+    cuuint64_t str[1] = {(cuuint64_t)pl.Ktot * 2};
+    cuuint32_t box[2] = {BK, (cuuint32_t)(UN / 2)};
+    rc = encode(&bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  const int n_out = MODE == MODE_GEGLU ? d->K / 2 : d->K;
+  PairP p = {};
+  p.kblocks = pl.Ktot / BK;
+  p.kb_per_split = pl.kb_per_split;
+  p.conv = pl.conv;
+  p.cblocks = d->C / BK;
+  p.S = d->S;
+  p.pad = d->pad;
+  p.Wb = pl.Wb; p.Hb = pl.Hb; p.Nb = pl.Nb;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
+  p.m_tiles = pl.m_tiles;
+  p.m_pairs = (pl.m_tiles + 1) / 2;
+  p.n_units = d->K / (NSUB * UN);
+  p.num_units = p.m_pairs * p.n_units * pl.splits;
+  p.stages = pl.stages; p.npb = pl.npb; p.slot_bytes = pl.slot_bytes; p.off16 = pl.off16;
+  p.M = pl.M;
+  p.pix_per_img = pl.P * pl.Q;
+  p.lde = d->lde;
+  p.act = partial ? MKD_ACT_NONE : d->act;
+  p.alpha = partial ? 1.0f : d->alpha;
+  p.bias = partial ? nullptr : d->bias;
+  p.emb = partial ? nullptr : (const bf16*)d->emb;
+  p.stats = reinterpret_cast<float2*>(d->stats);
+  p.stats_ld = d->stats_ld;
+  r32map = r16map = y32map = y16map = amap;  // (unused maps must still be valid kernel parameters)
+  if (partial) {
+    p.has_y32 = 1;
+    p.partial_rows = pl.M;
+    rc = encode_panel_map(&y32map, true, d->workspace, (int64_t)pl.splits * pl.M, d->K, d->K);
+    if (rc) return rc;
+  } else {
+    if (d->residual && d->residual_dtype == MKD_F32) {
+      p.has_res32 = 1;
+      rc = encode_panel_map(&r32map, true, d->residual, pl.M, n_out, d->ldr);
+      if (rc) return rc;
+    }
+    if (d->residual && d->residual_dtype == MKD_BF16) {
+      p.has_res16 = 1;
+      rc = encode_panel_map(&r16map, false, d->residual, pl.M, n_out, d->ldr);
+      if (rc) return rc;
+    }
+    if (d->y32) {
+      p.has_y32 = 1;
+      rc = encode_panel_map(&y32map, true, d->y32, pl.M, n_out, d->ldy32);
+      if (rc) return rc;
+    }
+    if (d->y) {
+      p.has_y16 = 1;
+      rc = encode_panel_map(&y16map, false, d->y, pl.M, n_out, d->ldy);
+      if (rc) return rc;
+    }
+  }
+  const int max_pairs = num_sms() / 2;
+  const int pairs = p.num_units < max_pairs ? p.num_units : max_pairs;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    MKD_LAUNCH_OK(cudaLaunchKernelEx(&cfg, kernel, amap, bmap, r32map, r16map, y32map, y16map, p));
+  }
+  MKD_CHECK_LAUNCH();
+  if (partial) return splitk_reduce(d, pl.M, pl.P * pl.Q, pl.splits, stream);
+  return MKD_OK;
+}
+}  // namespace
+
+namespace mkd {
+bool conv2d_pair_supported(const mkd_conv_desc* d, bool forced) {
+  PairPlan pl = {};
+  return plan(d, pl, forced);
+}
+
+int conv2d_pair(const mkd_conv_desc* d, bool forced, cudaStream_t stream) {
+  PairPlan pl = {};
+  MKD_REQUIRE(plan(d, pl, forced), MKD_E_INVALID, "gemm_pair: unsupported shape");
+  if (pl.geglu) return launch<256, 1, MODE_GEGLU, 0>(d, pl, stream);
+  if (pl.nsub == 2) return pl.stats ? launch<160, 2, MODE_PLAIN, 1>(d, pl, stream) : launch<160, 2, MODE_PLAIN, 0>(d, pl, stream);
+  return pl.stats ? launch<160, 1, MODE_PLAIN, 1>(d, pl, stream) : launch<160, 1, MODE_PLAIN, 0>(d, pl, stream);
+}
+}  // namespace mkd

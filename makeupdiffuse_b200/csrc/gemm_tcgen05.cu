@@ -1130,7 +1130,11 @@ bool geometry(const mkd_conv_desc* d, Geometry& g) {
   g.Ktot = d->R * d->S * d->C;
   g.Kout = d->act == MKD_ACT_GEGLU ? d->K / 2 : d->K;
   if (d->K % 16 != 0 && !(d->K < 16)) { set_error("K=%d is not a multiple of 16", d->K); return false; }
-  if (d->act == MKD_ACT_GEGLU && (d->geglu_block != 80 || d->K % 160)) { set_error("GEGLU needs geglu_block 80 and K %% 160 == 0"); return false; }
+  // GEGLU row blocking: [80 value | 80 gate] per 160-row tile (single-CTA kernel) or [128 | 128] per 256-row tile (pair kernel)
+  if (d->act == MKD_ACT_GEGLU && !((d->geglu_block == 80 && d->K % 160 == 0) || (d->geglu_block == 128 && d->K % 256 == 0 && d->R == 1))) {
+    set_error("GEGLU needs geglu_block 80 (K %% 160 == 0) or 128 (K %% 256 == 0, 1x1)");
+    return false;
+  }
   if (g.conv) {
     if (!is_pow2(g.Q) || !is_pow2(g.P)) { set_error("conv H/W must be powers of two"); return false; }
     g.Wb = g.Q < BM ? g.Q : BM;
@@ -1187,31 +1191,8 @@ int cluster_pref() {  // MKD_CLUSTER=2 selects the A-multicast CTA-pair kernel f
 }
 
 template <int BN, int CL>
-int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
+int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, MainP, EpiP);
-  // stride-2 / upsample: rewrite the descriptor onto the materialised input living at the head of the workspace
-  mkd_conv_desc dd = *d_in;
-  mkd_conv_desc* d = &dd;
-  if (d_in->stride == 2 || d_in->upsample) {
-    const bool down = d_in->stride == 2;
-    const size_t bytes = down ? (size_t)d_in->N * g.P * g.Q * 9 * d_in->C * 2 : (size_t)d_in->N * g.P * g.Q * d_in->C * 2;
-    const int64_t vecs = (int64_t)(bytes / 16);
-    int blocks = (int)((vecs + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (down)
-      MKD_LAUNCH_OK(launch_pdl(im2col_s2_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx, d_in->pad));
-    else
-      MKD_LAUNCH_OK(launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx));
-    MKD_CHECK_LAUNCH();
-    const size_t used = (bytes + 1023) & ~(size_t)1023;
-    dd.x = d_in->workspace;
-    dd.workspace = (char*)d_in->workspace + used;
-    dd.workspace_bytes = d_in->workspace_bytes - used;
-    dd.stride = 1;
-    dd.upsample = 0;
-    if (down) { dd.C = 9 * d_in->C; dd.R = dd.S = 1; dd.pad = 0; dd.N = 1; dd.H = 1; dd.W = g.M; dd.ldx = dd.C; }
-    else { dd.H = g.P; dd.W = g.Q; dd.ldx = d_in->C; }
-  }
   constexpr int EG = (BN == 160 ? EPI_GEGLU : EPI_PLAIN);
   // 0-4: the epilogue variants with run-time operand dispatch; 5-9: compile-time operand sets (SPEC) of the shapes that
   // dominate a UNet step (N tile 160): y32 | res32 + y32 | y | res32 + y (plain), res32 + y32 + y (statistics)
@@ -1389,15 +1370,85 @@ int launch(const mkd_conv_desc* d_in, const Geometry& g, cudaStream_t stream) {
 // debug hook (not part of the public header): device buffer of 148*16 u64 that the next GEMM launches stamp
 extern "C" void mkd_debug_set_trace(void* p) { g_trace = static_cast<unsigned long long*>(p); }
 
+namespace {
+// Downsample (3x3 stride 2) and Upsample (nearest x2 + 3x3): materialise (im2col / upsampled copy) into the head of the
+// workspace and rewrite the descriptor onto it — a plain GEMM (im2col) or an ordinary stride-1 3x3 conv (upsample).
+int materialise(const mkd_conv_desc* d_in, const Geometry& g, mkd_conv_desc& dd, cudaStream_t stream) {
+  dd = *d_in;
+  if (d_in->stride != 2 && !d_in->upsample) return MKD_OK;
+  const bool down = d_in->stride == 2;
+  const size_t bytes = down ? (size_t)d_in->N * g.P * g.Q * 9 * d_in->C * 2 : (size_t)d_in->N * g.P * g.Q * d_in->C * 2;
+  const int64_t vecs = (int64_t)(bytes / 16);
+  int blocks = (int)((vecs + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (down)
+    MKD_LAUNCH_OK(launch_pdl(im2col_s2_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx, d_in->pad));
+  else
+    MKD_LAUNCH_OK(launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, stream, (const bf16*)d_in->x, (bf16*)d_in->workspace, d_in->N, d_in->H, d_in->W, d_in->C, d_in->ldx));
+  MKD_CHECK_LAUNCH();
+  const size_t used = (bytes + 1023) & ~(size_t)1023;
+  dd.x = d_in->workspace;
+  dd.workspace = (char*)d_in->workspace + used;
+  dd.workspace_bytes = d_in->workspace_bytes - used;
+  dd.stride = 1;
+  dd.upsample = 0;
+  if (down) { dd.C = 9 * d_in->C; dd.R = dd.S = 1; dd.pad = 0; dd.pad_hi_extra = 0; dd.N = 1; dd.H = 1; dd.W = g.M; dd.ldx = dd.C; }
+  else { dd.H = g.P; dd.W = g.Q; dd.ldx = d_in->C; }
+  return MKD_OK;
+}
+}  // namespace
+
 namespace mkd {
-bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
-  Geometry g;
-  return geometry(d, g);
+bool conv2d_pair_supported(const mkd_conv_desc* d, bool forced);          // gemm_pair.cu
+int conv2d_pair(const mkd_conv_desc* d, bool forced, cudaStream_t stream);  // gemm_pair.cu
+
+// split-K reducer for partials laid out [split][M][K] fp32 in d->workspace (also used by the pair kernel)
+int splitk_reduce(const mkd_conv_desc* d, int M, int pix_per_img, int splits, cudaStream_t stream) {
+  EpiP ep;
+  ep.M = M; ep.N_out = d->act == MKD_ACT_GEGLU ? d->K / 2 : d->K; ep.n_rows = d->K;
+  ep.ldy = d->ldy; ep.ldr = d->ldr; ep.lde = d->lde;
+  ep.pix_per_img = pix_per_img;
+  ep.act = d->act; ep.alpha = d->alpha;
+  ep.y = (bf16*)d->y; ep.bias = d->bias; ep.emb = (const bf16*)d->emb; ep.res = d->residual;
+  ep.y32 = d->y32; ep.ldy32 = d->ldy32; ep.res_f32 = d->residual_dtype == MKD_F32;
+  ep.partial = (float*)d->workspace;
+  ep.stats = nullptr; ep.stats_ld = 0;
+  int64_t total = (int64_t)M * (d->K / (d->act == MKD_ACT_GEGLU ? 16 : 8));
+  int blocks = (int)((total + 127) / 128);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  MKD_LAUNCH_OK(launch_pdl(splitk_epilogue_kernel<160>, dim3(blocks), dim3(128), 0, stream, ep, splits));
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
 }
 
-int conv2d_tcgen05(const mkd_conv_desc* d, cudaStream_t stream) {
+bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
   Geometry g;
-  MKD_REQUIRE(geometry(d, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
+  if (!geometry(d, g)) return false;
+  if (d->path == MKD_PATH_TCGEN05_PAIR) {  // forced pair kernel (tests / benchmarks): stride-1 shapes it takes only
+    if (d->stride != 1 || d->upsample || !conv2d_pair_supported(d, true)) {
+      set_error("the CTA-pair kernel does not take this shape");
+      return false;
+    }
+  }
+  return true;
+}
+
+int conv2d_tcgen05(const mkd_conv_desc* d_in, cudaStream_t stream) {
+  Geometry g;
+  MKD_REQUIRE(geometry(d_in, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
+  mkd_conv_desc dd;
+  int rc = materialise(d_in, g, dd, stream);
+  if (rc) return rc;
+  const mkd_conv_desc* d = &dd;
+  if (d_in->stride == 2 || d_in->upsample) MKD_REQUIRE(geometry(d, g), MKD_E_INVALID, "gemm_tcgen05: materialised shape rejected");
+  // the CTA-pair kernel (cta_group::2, TMA-store epilogue) takes the shapes it is built for; the single-CTA kernel
+  // keeps the rest (ragged M, narrow / odd channel counts, tiny problems)
+  const bool geglu128 = d->act == MKD_ACT_GEGLU && d->geglu_block == 128;  // a row blocking only the pair kernel reads
+  if (d_in->path != MKD_PATH_TCGEN05_SINGLE || geglu128) {
+    const bool forced = d_in->path == MKD_PATH_TCGEN05_PAIR || geglu128;
+    if (conv2d_pair_supported(d, forced)) return conv2d_pair(d, forced, stream);
+  }
+  MKD_REQUIRE(!geglu128, MKD_E_INVALID, "gemm_tcgen05: geglu_block 128 needs the CTA-pair kernel, which declined this shape");
   const int cl = (d->K > 160) ? cluster_pref() : 1;  // a pair needs two N tiles to share an A tile
   switch (pick_bn(d, g)) {
     case 160: return (cl == 2) ? launch<160, 2>(d, g, stream) : launch<160, 1>(d, g, stream);

@@ -147,7 +147,7 @@ def test_layernorm(dt, M, C):
 # ---- convolution / GEMM family -----------------------------------------------------------------------------------
 def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True, emb=False, residual=False,
               inplace=False, alpha=1.0, act=L.ACT_NONE, ldx_extra=0, ldy_extra=0, ldy_pad=0, workspace=False, seed=0,
-              y32="", res32=False):
+              y32="", res32=False, gb=None):
     """y32: "" (activation-dtype output only), "both" (+ fp32 copy) or "only" (fp32 copy only); res32: fp32 residual"""
     M = N * H * W
     xb = rnd(M, C + ldx_extra, dt=dt, seed=seed + 1)
@@ -168,11 +168,13 @@ def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True,
         assert not inplace
         y = None
     res_ref = None if res is None else res.float().clone()
-    gb = 80 if act == L.ACT_GEGLU and Ko % 80 == 0 else 16
+    if gb is None:
+        gb = 80 if act == L.ACT_GEGLU and Ko % 80 == 0 else 16
     ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV) if workspace else None
     kw = dict(N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=upsample, bias=b, emb=e, residual=res,
               alpha=alpha, act=act, geglu_block=gb, path=path, workspace=ws, y32=out32)
-    assert ops.conv2d_path(x, w, y, **kw) == (path if path else ops.conv2d_path(x, w, y, **kw))
+    want = min(path, L.PATH_TCGEN05)  # the two forced tensor-core kernels both report PATH_TCGEN05
+    assert ops.conv2d_path(x, w, y, **kw) == (want if path else ops.conv2d_path(x, w, y, **kw))
     ops.conv2d(x, w, y, **kw)
     # fp32 reference on the same (rounded) inputs
     xr = x.float().reshape(N, H, W, C).permute(0, 3, 1, 2)
@@ -283,6 +285,53 @@ def test_conv_tcgen05(case):
     conv_case(BF, L.PATH_TCGEN05, **case)
 
 
+# ---- the CTA-pair kernel (cta_group::2, TMA-store epilogue), forced: every operand set / tile plan it implements ----
+PAIR_CASES = [
+    dict(N=1, H=1, W=256, C=128, K=160, R=1),                                # one pair, one unit, two k-blocks
+    dict(N=1, H=1, W=1024, C=320, K=320, R=1),                               # bias-only GEMM, bf16 out
+    dict(N=1, H=1, W=1024, C=320, K=320, R=1, residual=True, res32=True, y32="both"),   # attention out-projection: fp32 stream in / out
+    dict(N=1, H=1, W=1024, C=320, K=320, R=1, residual=True, res32=True, y32="only"),   # fp32 stream updated in place (no bf16 copy)
+    dict(N=1, H=1, W=1000, C=320, K=960, R=1, bias=False),                   # qkv, ragged M (TMA clips the last tile)
+    dict(N=1, H=1, W=384, C=320, K=320, R=1),                                # odd number of 128-row tiles: the last pair's peer CTA idles
+    dict(N=1, H=1, W=200, C=640, K=640, R=1, inplace=True, alpha=0.5),       # zero-conv injection: bf16 residual == output
+    dict(N=1, H=1, W=2048, C=640, K=640, R=1, inplace=True, alpha=0.5, ldy_extra=640),  # ... into a concat slot
+    dict(N=1, H=1, W=256, C=320, K=320, R=1, act=L.ACT_SILU),                # SiLU epilogue
+    dict(N=1, H=1, W=512, C=1280, K=320, R=1, residual=True, res32=True),    # ff2: fp32 stream in, bf16 operand out
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, emb=True, y32="only"),          # ResBlock conv1: timestep embedding, fp32 h
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, residual=True, res32=True, y32="both", ldy_extra=320),  # conv2 into a slot + fp32
+    dict(N=4, H=16, W=16, C=640, K=640, R=3, residual=True),                 # 16x16: box = 8 rows
+    dict(N=3, H=8, W=8, C=1280, K=1280, R=3, residual=True),                 # 8x8: box spans 2 images, ragged N
+    dict(N=5, H=4, W=4, C=1280, K=1280, R=3, emb=True),                      # 4x4: box spans 8 images, one partial tile
+    dict(N=1, H=64, W=64, C=320, K=320, R=3, emb=True),                      # 512^2 level: box = 2 rows of 64
+    dict(N=2, H=16, W=16, C=960, K=640, R=3, ldx_extra=320, ldy_extra=640, residual=True),  # concat slices in / out
+    dict(N=16, H=32, W=32, C=320, K=320, R=3, emb=True, y32="only"),         # two N = 160 sub-tiles per A tile (64 units)
+    dict(N=16, H=32, W=32, C=960, K=320, R=3, residual=True, res32=True, y32="both"),   # ... deep K, fp32 in / out
+    dict(N=1, H=1, W=512, C=320, K=2560, R=1, act=L.ACT_GEGLU, gb=128),      # fused GEGLU, [128 value | 128 gate] blocks
+    dict(N=1, H=1, W=300, C=640, K=5120, R=1, act=L.ACT_GEGLU, gb=128),      # ... ragged M
+    dict(N=16, H=8, W=8, C=1280, K=1280, R=3, emb=True, y32="only", workspace=True),    # split-K (8x8 level)
+    dict(N=16, H=4, W=4, C=2560, K=1280, R=3, emb=True, workspace=True),     # split-K (4x4 level, K = 23040)
+    dict(N=16, H=8, W=8, C=5120, K=1280, R=1, residual=True, res32=True, workspace=True),  # split-K ff2
+    dict(N=8, H=4, W=4, C=1280, K=1280, R=3, residual=True, res32=True, y32="both", workspace=True),  # split-K + fp32
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_pair(case):
+    conv_case(BF, L.PATH_TCGEN05_PAIR, **case)
+
+
+def test_conv_pair_matches_single_on_hot_shapes():
+    """the step's hot shapes at batch 16 through AUTO (pair kernel) and through the forced single-CTA kernel"""
+    for c in (dict(N=16, H=32, W=32, C=320, K=320, R=3, emb=True, y32="only"),
+              dict(N=16, H=16, W=16, C=640, K=640, R=3, residual=True, res32=True, y32="both"),
+              dict(N=16, H=16, W=16, C=640, K=640, R=3, upsample=True, workspace=True),
+              dict(N=16, H=32, W=32, C=320, K=320, R=3, stride=2, workspace=True, y32="both"),
+              dict(N=1, H=1, W=16384, C=320, K=960, R=1, bias=False)):
+        e_auto = conv_case(BF, L.PATH_AUTO, **c)
+        e_single = conv_case(BF, L.PATH_TCGEN05_SINGLE, **c)
+        assert abs(e_auto - e_single) < 1e-3
+
+
 def test_conv_auto_dispatch():
     """hot shapes go to the tcgen05 kernel, odd ones to the generic kernel"""
     def path(**c):
@@ -325,8 +374,23 @@ STATS_CASES = [
 ]
 
 
+PAIR_STATS_CASES = [
+    dict(N=2, H=32, W=32, C=320, K=320, R=3, emb=True),                      # conv1 -> h + stats
+    dict(N=4, H=16, W=16, C=640, K=640, R=3, residual=True, slot=(640, 1280)),  # conv2 into a concat slot + stats slice
+    dict(N=2, H=32, W=32, C=320, K=320, R=1, inplace=True),                  # zero-conv injection re-emitting stats
+    dict(N=1, H=64, W=64, C=320, K=320, R=1, residual=True),                 # proj_out, 512^2 level
+    dict(N=16, H=32, W=32, C=320, K=320, R=3, residual=True),                # two sub-tiles per A tile
+    dict(N=3, H=16, W=16, C=1280, K=640, R=3, emb=True),                     # odd tile count
+]
+
+
+@pytest.mark.parametrize("case", PAIR_STATS_CASES)
+def test_conv_pair_stats_and_groupnorm_apply(case):
+    test_conv_stats_and_groupnorm_apply(case, path=L.PATH_TCGEN05_PAIR)
+
+
 @pytest.mark.parametrize("case", STATS_CASES)
-def test_conv_stats_and_groupnorm_apply(case):
+def test_conv_stats_and_groupnorm_apply(case, path=L.PATH_AUTO):
     """conv2d(stats=) must emit, per 128-row tile and channel, the (sum, sumsq) of exactly the fp32 values it stored;
     groupnorm_apply on those statistics must equal F.group_norm of the stored tensor."""
     N, H, W, C, K, R = (case[k] for k in "NHWCKR")
@@ -346,7 +410,7 @@ def test_conv_stats_and_groupnorm_apply(case):
     st = stb[:, off:off + K, :]
     ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV)
     ops.conv2d(x, w, y, N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=up, bias=b, emb=e, residual=res,
-               alpha=0.5 if case.get("inplace") else 1.0, workspace=ws, y32=y32, stats=st)
+               alpha=0.5 if case.get("inplace") else 1.0, workspace=ws, y32=y32, stats=st, path=path)
     t = y32.reshape(Mo // 128, 128, K)
     ref = torch.stack([t.sum(1), (t * t).sum(1)], -1)
     assert rel(st[..., 0], ref[..., 0]) < 1e-5 and rel(st[..., 1], ref[..., 1]) < 1e-5
@@ -356,7 +420,7 @@ def test_conv_stats_and_groupnorm_apply(case):
     st1 = st.clone()
     if not case.get("inplace"):
         ops.conv2d(x, w, y, N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=up, bias=b, emb=e, residual=res,
-                   workspace=ws, y32=y32, stats=st)
+                   workspace=ws, y32=y32, stats=st, path=path)
         assert torch.equal(st, st1)
     for silu in (True, False):
         for src in (y32, y):
