@@ -36,6 +36,7 @@ using namespace mkd;
 
 namespace mkd {
 int splitk_reduce(const mkd_conv_desc* d, int M, int pix_per_img, int splits, cudaStream_t stream);  // gemm_tcgen05.cu
+unsigned long long* debug_trace_ptr();                                                               // gemm_tcgen05.cu
 }
 
 namespace {
@@ -46,30 +47,71 @@ constexpr int PANEL = 32;                      // epilogue panel width (columns)
 constexpr int P32_BYTES = BM * PANEL * 4;      // 16 KB: fp32 panel (128 B rows, SWIZZLE_128B)
 constexpr int P16_BYTES = BM * PANEL * 2;      // 8 KB: bf16 panel (64 B rows, SWIZZLE_64B)
 constexpr int MAX_STAGES = 8, MAX_SLOTS = 8;
+static_assert(MAX_STAGES == MAX_SLOTS, "barrier init assumes one lane per ring / slot barrier");
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8;    // EPI_WARP0 % 4 == 0: warp w reads TMEM lanes [32 (w % 4), +32)
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int SCRATCH_BYTES = 2 /*warpgroups*/ * 2 /*buffers*/ * 4 /*quadrants*/ * 32 * 8;  // GroupNorm partials
-constexpr int BAR_BYTES = 512;
+constexpr int BIASV_FLOATS = 320;  // per-unit column vector (bias [+ the tile's timestep-embedding row]): NSUB * UN floats
+constexpr int BIASV_BYTES = 2 /*warpgroups*/ * 2 /*buffers*/ * BIASV_FLOATS * 4;
+constexpr int BAR_BYTES = 512 + BIASV_BYTES;
 constexpr int SMEM_LIMIT = 227 * 1024;
+
+// division by a launch constant: q = umulhi(n, ceil(2^32 / d)), exact while n * d < 2^32 (checked on the host).
+// Every role decodes work units; 32-bit integer divisions cost ~150 clk each, and the epilogue DMA thread ran eight of
+// them per PANEL (its pace, not the tensor cores', set the epilogue's).
+struct FastDiv {
+  uint32_t d, m;  // m == 0: d == 1
+};
+__device__ __forceinline__ int fdiv(int n, FastDiv f) { return f.m ? (int)__umulhi((uint32_t)n, f.m) : n; }
 
 struct PairP {
   // main loop
   int kblocks, kb_per_split;
   int conv, cblocks, S, pad;
   int Wb, Hb, Nb, tiles_w, tiles_h;
+  FastDiv d_n_units, d_m_pairs, d_cblocks, d_S, d_tiles_w, d_tiles_h, d_ppi;
   int m_tiles, m_pairs, n_units, num_units;  // unit -> (n_unit fastest, m_pair, split)
   int stages, npb, slot_bytes, off16;        // shared-memory ring depth; panel slots and their layout
   // epilogue
   int M, pix_per_img, lde;
   int has_res32, has_res16, has_y32, has_y16, act;
+  int emb_uniform;                           // every 128-row tile lies inside one image: its embedding row rides in the bias vector
   int partial_rows;                          // split-K: fp32 partial rows per split (M), else 0
   float alpha;
   const float* bias;
   const bf16* emb;
   float2* stats;
   int stats_ld;
+  unsigned long long* trace;  // debug: per-CTA %globaltimer stamps (mkd_debug_set_trace), else nullptr
 };
+// slot layout per CTA (16 x u64): 0 entry, 1 prologue done, 2 first TMA issued, 3 first full barrier (MMA warp), 4 unit-0 MMAs
+// issued, 5 unit-0 accumulator ready (epilogue), 6 first panel computed, 7 first store issued, 8 last store issued, 9 stores
+// drained, 10 last panel computed, 11 exit, 12 last unit's MMAs issued, 13 last TMA issued
+// (compiled in only with -DMKD_ENABLE_TRACE, i.e. `MKD_TRACE=1 python -m makeupdiffuse_b200.build --force`)
+#ifdef MKD_ENABLE_TRACE
+#define PAIR_TRACE(slot)                                                  \
+  do {                                                                    \
+    if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer();    \
+  } while (0)
+// detail region (after the 148 x 16 stamps): per CTA 16 panels x 8 clock64 stamps of epilogue warp 4 / 8 lane 0
+#define PAIR_DETAIL(k)                                                                                       \
+  do {                                                                                                       \
+    if (p.trace && lane == 0 && quad == 0 && g < 16) p.trace[148 * 16 + ((size_t)blockIdx.x * 16 + g) * 8 + (k)] = clock64(); \
+  } while (0)
+#define PAIR_DETAIL_DEP(k, reg)                                                                              \
+  do {                                                                                                       \
+    if (p.trace && lane == 0 && quad == 0 && g < 16) {                                                       \
+      long long c_;                                                                                          \
+      asm volatile("mov.u64 %0, %%clock64;\n" : "=l"(c_) : "r"(reg));                                        \
+      p.trace[148 * 16 + ((size_t)blockIdx.x * 16 + g) * 8 + (k)] = c_;                                      \
+    }                                                                                                        \
+  } while (0)
+#else
+#define PAIR_TRACE(slot) do { } while (0)
+#define PAIR_DETAIL(k) do { } while (0)
+#define PAIR_DETAIL_DEP(k, reg) do { } while (0)
+#endif
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -173,6 +215,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
   return r;
 }
+// rendezvous only (no memory ordering): both CTAs of the pair are running
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   __syncwarp();  // role branches diverge lanes: reconverge before the .aligned barrier
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -233,6 +281,61 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
 __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// Blackwell packed fp32 pipe: two IEEE fp32 results per issue slot (a three-register FFMA occupies the FMA pipe of its
+// scheduler for two cycles; the epilogue warps are bound by exactly that)
+__device__ __forceinline__ uint64_t pk(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pku(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// erf-GELU of two values at once, same approximation as gelu_erf_fast (Abramowitz-Stegun 7.1.26): returns
+// 0.5 x (1 + erf(x / sqrt 2)) for both lanes.  ~9 packed + 4 MUFU + 4 ALU instructions per pair.
+__device__ __forceinline__ uint64_t gelu_erf_fast2(uint64_t x2) {
+  float x0, x1;
+  upk(x2, x0, x1);
+  const uint64_t z2 = mul2(pk(fabsf(x0), fabsf(x1)), pk(0.70710678118654752f, 0.70710678118654752f));
+  const uint64_t den2 = fma2(z2, pk(0.3275911f, 0.3275911f), pk(1.0f, 1.0f));
+  const uint64_t arg2 = mul2(mul2(z2, pk(-1.4426950408889634f, -1.4426950408889634f)), z2);
+  float d0, d1, a0, a1, t0, t1, e0, e1;
+  upk(den2, d0, d1);
+  upk(arg2, a0, a1);
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(t1) : "f"(d1));
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e1) : "f"(a1));
+  const uint64_t t2 = pk(t0, t1);
+  // negated polynomial: q = -(a1 + t (a2 + t (a3 + t (a4 + t a5)))), so erf|x| = 1 + (q t) e
+  uint64_t q2 = fma2(t2, pk(-1.061405429f, -1.061405429f), pk(1.453152027f, 1.453152027f));
+  q2 = fma2(t2, q2, pk(-1.421413741f, -1.421413741f));
+  q2 = fma2(t2, q2, pk(0.284496736f, 0.284496736f));
+  q2 = fma2(t2, q2, pk(-0.254829592f, -0.254829592f));
+  const uint64_t erf2 = fma2(mul2(q2, t2), pk(e0, e1), pk(1.0f, 1.0f));  // erf(|x| / sqrt 2)
+  float r0, r1;
+  upk(erf2, r0, r1);
+  const uint64_t h2 = mul2(x2, pk(0.5f, 0.5f));
+  return fma2(h2, pk(copysignf(r0, x0), copysignf(r1, x1)), h2);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -257,10 +360,10 @@ struct Unit {
 };
 __device__ __forceinline__ Unit decode_unit(const PairP& p, int u) {
   Unit t;
-  t.n_unit = u % p.n_units;
-  const int rest = u / p.n_units;
-  t.m_pair = rest % p.m_pairs;
-  t.split = rest / p.m_pairs;
+  const int rest = fdiv(u, p.d_n_units);
+  t.n_unit = u - rest * p.n_units;
+  t.split = fdiv(rest, p.d_m_pairs);
+  t.m_pair = rest - t.split * p.m_pairs;
   t.kb0 = t.split * p.kb_per_split;
   t.kb1 = min(p.kblocks, t.kb0 + p.kb_per_split);
   return t;
@@ -297,25 +400,35 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
   uint64_t* res_full_bar = tmem_empty_bar + 2;       // [MAX_SLOTS] slot is free and its residual (if any) has landed
   uint64_t* computed_bar = res_full_bar + MAX_SLOTS; // [MAX_SLOTS] the panel in the slot is ready to be stored
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(computed_bar + MAX_SLOTS);
+  float* biasv = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full_bar) + 512);  // [2 warpgroups][2][BIASV_FLOATS]
+  // kernel parameters live in constant memory that is cold at every launch: touch every line now, so that the misses
+  // (~1 us when taken one after the other in front of the first TMA) overlap the prologue's barriers instead
+  asm volatile("" ::"r"(p.kblocks), "r"(p.Wb), "r"(p.num_units), "r"(p.npb), "r"(p.M), "r"(p.has_y32), "f"(p.alpha), "l"(p.bias),
+               "l"(p.stats), "r"(p.stats_ld));
 
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&bmap)) : "memory");
-    for (int i = 0; i < MAX_STAGES; ++i) {
-      mbar_init(full_bar + i, 2);   // (leader's copy is the live one) both producers arrive; both CTAs' bytes land here
-      mbar_init(empty_bar + i, 1);  // multicast commit of the leader's MMA warp
+  if (threadIdx.x == 0) PAIR_TRACE(0);
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&bmap)) : "memory");
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(tmem_full_bar + i, 1);               // multicast commit
-      mbar_init(tmem_empty_bar + i, 2 * EPI_WARPS);  // (leader's copy) every epilogue warp of both CTAs
+    // one barrier per lane: full (count 2: both producers arrive on the leader's copy, both CTAs' bytes land there),
+    // empty / tmem_full (1: multicast commit), tmem_empty (every epilogue warp of both CTAs, leader's copy),
+    // res_full (1: the DMA thread), computed (4: the warps of the warpgroup that owns the panel)
+    if (lane < MAX_STAGES) {
+      mbar_init(full_bar + lane, 2);
+      mbar_init(empty_bar + lane, 1);
+      mbar_init(res_full_bar + lane, 1);
+      mbar_init(computed_bar + lane, 4);
     }
-    for (int i = 0; i < MAX_SLOTS; ++i) {
-      mbar_init(res_full_bar + i, 1);
-      mbar_init(computed_bar + i, 4);  // the four warps of the warpgroup that owns the panel
+    if (lane < 2) {
+      mbar_init(tmem_full_bar + lane, 1);
+      mbar_init(tmem_empty_bar + lane, 2 * EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  cluster_sync_all();  // both CTAs are resident before the paired TMEM allocation
+  cluster_sync_relaxed();  // both CTAs are resident before the paired TMEM allocation
+  if (threadIdx.x == 0) PAIR_TRACE(14);
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
@@ -325,6 +438,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // from here on global memory written by the previous kernel is read and its outputs may be overwritten
+  if (threadIdx.x == 0) PAIR_TRACE(1);
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
@@ -336,21 +450,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const int m_tile = 2 * t.m_pair + (int)rank;
       int w0 = 0, h0 = 0, n0 = 0;
       if (p.conv) {
-        const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int mw = fdiv(m_tile, p.d_tiles_w), tw = m_tile - mw * p.tiles_w;
+        const int tn = fdiv(mw, p.d_tiles_h), th = mw - tn * p.tiles_h;
         w0 = tw * p.Wb;
         h0 = th * p.Hb;
         n0 = tn * p.Nb;
       }
       const int m0 = m_tile * BM;
       // filter-tap walk (r, sx, cb) kept incrementally: no integer divisions in the k loop
-      const int tap0 = t.kb0 / p.cblocks;
-      int cb = t.kb0 - tap0 * p.cblocks, r = tap0 / p.S;
+      const int tap0 = fdiv(t.kb0, p.d_cblocks);
+      int cb = t.kb0 - tap0 * p.cblocks, r = fdiv(tap0, p.d_S);
       int sx = tap0 - r * p.S;
       const int nb = t.n_unit * (NSUB * UN) + (int)rank * (UN / 2);  // this CTA's half of sub-tile 0's weight rows
 #pragma unroll 1
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
         mbar_wait(empty_bar + s, ph ^ 1);  // (own copy) the MMAs that read this slot have retired
         if (elect_one()) {
+          if (u == pair_id && kb == t.kb0) PAIR_TRACE(15);
           unsigned char* sa = smem + s * STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(full_bar + s, 2 * STAGE_BYTES);
           else mbar_arrive_cluster(full_bar + s, 0);
@@ -359,6 +475,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub)
             tma_load_2d_2sm(&bmap, full_bar + s, sa + A_BYTES + sub * BH_BYTES, kb * BK, nb + sub * UN);
+          if (u == pair_id && kb == t.kb0) PAIR_TRACE(2);
         }
         __syncwarp();
         if (++cb == p.cblocks) {
@@ -392,6 +509,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           mbar_wait(full_bar + s, ph);
           tcgen05_fence_after();
           if (elect_one()) {
+            if (j == 0 && kb == t.kb0) PAIR_TRACE(3);
             const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
             const uint64_t adesc = make_smem_desc(sa);
 #pragma unroll
@@ -405,7 +523,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               }
             }
             tcgen05_commit_2sm(empty_bar + s, (uint16_t)3);  // frees the slot in both CTAs once these MMAs retire
-            if (kb == t.kb1 - 1) tcgen05_commit_2sm(tmem_full_bar + ts, (uint16_t)3);
+            if (kb == t.kb1 - 1) {
+              tcgen05_commit_2sm(tmem_full_bar + ts, (uint16_t)3);
+              if (j == 0) PAIR_TRACE(4);
+            }
           }
           __syncwarp();
           if (++s == p.stages) {
@@ -423,8 +544,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const int D = p.npb >= 3 ? p.npb - 2 : p.npb - 1;  // the store of panel j is issued D panels after its slot was armed
       const bool any_res = p.has_res32 || p.has_res16;
       const uint32_t res_bytes = (p.has_res32 ? P32_BYTES : 0) + (p.has_res16 ? P16_BYTES : 0);
-      int lu = pair_id, lq = 0, lb = 0;   // load cursor: unit, panel within the unit, slot
-      int su = pair_id, sq = 0, sb = 0;   // store cursor
+      constexpr int OUTW = MODE == MODE_GEGLU ? UN / 2 : NSUB * UN;  // output columns of a unit (panel q starts at column 32 q)
+      // load / store cursors: unit, panel within the unit, slot; the unit's coordinates are decoded once per unit
+      struct Cursor {
+        int u, q, slot, row, col, valid;
+      };
+      auto enter_unit = [&](Cursor& c) {
+        const Unit t = decode_unit(p, c.u);
+        const int m_tile = 2 * t.m_pair + (int)rank;
+        c.valid = m_tile < p.m_tiles;
+        c.row = m_tile * BM;
+        c.col = t.n_unit * OUTW;
+        return t.split;
+      };
+      Cursor ld = {pair_id, 0, 0, 0, 0, 0}, st = {pair_id, 0, 0, 0, 0, 0};
+      enter_unit(ld);
+      int st_row_off = enter_unit(st) * p.partial_rows;
       uint32_t sph = 0;
 #pragma unroll 1
       for (int i = 0; i < total + D; ++i) {
@@ -434,51 +569,44 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             if (D == p.npb - 2) bulk_wait_read<1>();
             else bulk_wait_read<0>();
           }
-          const Unit t = decode_unit(p, lu);
-          const int m_tile = 2 * t.m_pair + (int)rank;
-          const int sub = lq / PPS, pp = lq - sub * PPS;
-          const int gcol = t.n_unit * (NSUB * UN) + sub * UN + pp * PANEL;
-          unsigned char* slot = slots + lb * p.slot_bytes;
-          if (any_res && m_tile < p.m_tiles) {
-            mbar_expect_tx(res_full_bar + lb, res_bytes);
-            if (p.has_res32) tma_load_2d(&r32map, res_full_bar + lb, slot, gcol, m_tile * BM);
-            if (p.has_res16) tma_load_2d(&r16map, res_full_bar + lb, slot + p.off16, gcol, m_tile * BM);
+          unsigned char* slot = slots + ld.slot * p.slot_bytes;
+          if (any_res && ld.valid) {
+            mbar_expect_tx(res_full_bar + ld.slot, res_bytes);
+            if (p.has_res32) tma_load_2d(&r32map, res_full_bar + ld.slot, slot, ld.col + ld.q * PANEL, ld.row);
+            if (p.has_res16) tma_load_2d(&r16map, res_full_bar + ld.slot, slot + p.off16, ld.col + ld.q * PANEL, ld.row);
           } else {
-            mbar_arrive(res_full_bar + lb);  // nothing to load: the slot is simply free
+            mbar_arrive(res_full_bar + ld.slot);  // nothing to load: the slot is simply free
           }
-          if (++lq == PPU) {
-            lq = 0;
-            lu += num_pairs;
+          if (++ld.slot == p.npb) ld.slot = 0;
+          if (++ld.q == PPU) {
+            ld.q = 0;
+            ld.u += num_pairs;
+            if (ld.u < p.num_units) enter_unit(ld);
           }
-          if (++lb == p.npb) lb = 0;
         }
         if (i >= D) {
-          const Unit t = decode_unit(p, su);
-          const int m_tile = 2 * t.m_pair + (int)rank;
-          int gcol;
-          if (MODE == MODE_GEGLU) gcol = t.n_unit * (UN / 2) + sq * PANEL;
-          else {
-            const int sub = sq / PPS, pp = sq - sub * PPS;
-            gcol = t.n_unit * (NSUB * UN) + sub * UN + pp * PANEL;
-          }
-          unsigned char* slot = slots + sb * p.slot_bytes;
-          mbar_wait(computed_bar + sb, sph);
-          if (m_tile < p.m_tiles) {
-            if (p.has_y32) tma_store_2d(&y32map, slot, gcol, m_tile * BM + t.split * p.partial_rows);
-            if (p.has_y16) tma_store_2d(&y16map, slot + p.off16, gcol, m_tile * BM);
+          unsigned char* slot = slots + st.slot * p.slot_bytes;
+          mbar_wait(computed_bar + st.slot, sph);
+          if (st.valid) {
+            if (p.has_y32) tma_store_2d(&y32map, slot, st.col + st.q * PANEL, st.row + st_row_off);
+            if (p.has_y16) tma_store_2d(&y16map, slot + p.off16, st.col + st.q * PANEL, st.row);
           }
           bulk_commit();
-          if (++sq == PPU) {
-            sq = 0;
-            su += num_pairs;
-          }
-          if (++sb == p.npb) {
-            sb = 0;
+          if (i == D) PAIR_TRACE(7);
+          PAIR_TRACE(8);
+          if (++st.slot == p.npb) {
+            st.slot = 0;
             sph ^= 1;
+          }
+          if (++st.q == PPU) {
+            st.q = 0;
+            st.u += num_pairs;
+            if (st.u < p.num_units) st_row_off = enter_unit(st) * p.partial_rows;
           }
         }
       }
-      bulk_wait_all();
+      bulk_wait_read<0>();  // shared memory must outlive the stores' reads; their global writes complete with the grid
+      PAIR_TRACE(9);
     }
   } else if (warp >= EPI_WARP0) {
     // ===== epilogue warps =====
@@ -491,6 +619,35 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     int g = 0, b = 0, j = 0;
     uint32_t rph = 0;
     [[maybe_unused]] int lp = 0;  // statistics scratch buffer parity (panels this warpgroup has reduced)
+    // ---- per-unit column vector (bias [+ embedding row]) in shared memory, one unit ahead.  A global load issued while
+    // the TMA ring saturates the L2 -> SM path takes ~1 us: requested at the top of a panel it put that latency on every
+    // panel (the whole epilogue ran at 1.2 us per panel).  Each warpgroup keeps its own copy (no cross-group barrier).
+    constexpr int ACCW = MODE == MODE_GEGLU ? UN : NSUB * UN;  // columns (weight rows) of a unit
+    static_assert(ACCW <= BIASV_FLOATS && ACCW / 4 <= 128, "bias vector");
+    const int wt = (warp - EPI_WARP0 - 4 * wg) * 32 + lane;     // thread index within the warpgroup
+    float* bias_wg = biasv + wg * 2 * BIASV_FLOATS;
+    auto load_colvec = [&](int u_) -> float4 {
+      float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (wt < ACCW / 4 && u_ < p.num_units) {
+        const Unit t_ = decode_unit(p, u_);
+        const int col = t_.n_unit * ACCW + wt * 4;
+        if (p.bias) v4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (MODE == MODE_PLAIN && p.emb && p.emb_uniform) {
+          const int mt = min(2 * t_.m_pair + (int)rank, p.m_tiles - 1);
+          const uint2 e = __ldg(reinterpret_cast<const uint2*>(p.emb + (int64_t)fdiv(mt * BM, p.d_ppi) * p.lde + col));
+          v4.x += __uint_as_float(e.x << 16);
+          v4.y += __uint_as_float(e.x & 0xFFFF0000u);
+          v4.z += __uint_as_float(e.y << 16);
+          v4.w += __uint_as_float(e.y & 0xFFFF0000u);
+        }
+        if (MODE == MODE_PLAIN) {  // the epilogue computes acc * alpha + colvec
+          v4.x *= p.alpha; v4.y *= p.alpha; v4.z *= p.alpha; v4.w *= p.alpha;
+        }
+      }
+      return v4;
+    };
+    float4 colvec_next = load_colvec(pair_id);
+    const bool emb_gather = MODE == MODE_PLAIN && p.emb && !p.emb_uniform;  // tiles spanning several images: per-row gather
 #pragma unroll 1
     for (int u = pair_id; u < p.num_units; u += num_pairs, ++j) {
       const Unit t = decode_unit(p, u);
@@ -499,6 +656,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const bool valid = m_tile < p.m_tiles;
       const int m = m_tile * BM + row;
       const int q_last = (((g + PPU - 1) & 1) == wg) ? PPU - 1 : PPU - 2;  // this warpgroup's last panel of the unit
+      // this unit's column vector -> shared memory (buffer j & 1 was last read two units ago); next unit's requested
+      float* bias_s = bias_wg + (j & 1) * BIASV_FLOATS;
+      if (wt < ACCW / 4) *reinterpret_cast<float4*>(bias_s + wt * 4) = colvec_next;
+      asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory");
+      colvec_next = load_colvec(u + num_pairs);
+      const uint32_t bias_u32 = smem_u32(bias_s);
       bool waited = false;
 #pragma unroll 1
       for (int q = 0; q < PPU; ++q, ++g) {
@@ -507,6 +670,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             mbar_wait(tmem_full_bar + ts, use & 1);
             tcgen05_fence_after();
             waited = true;
+            if (j == 0 && warp == EPI_WARP0 && lane == 0) PAIR_TRACE(5);
           }
           const uint32_t s32 = slots_u32 + (uint32_t)(b * p.slot_bytes) + (uint32_t)(row * 128);
           const uint32_t s16 = slots_u32 + (uint32_t)(b * p.slot_bytes + p.off16) + (uint32_t)(row * 64);
@@ -515,9 +679,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             const uint32_t taddr = tmem_base + lane_bits + (uint32_t)(ts * ACC_COLS + q * PANEL);
             tmem_ld32_nowait(taddr, av);
             tmem_ld32_nowait(taddr + UN / 2, ag);
-            const int brow = t.n_unit * UN + q * PANEL;  // weight / bias row of the panel's first value channel
-            const float4* bvp = reinterpret_cast<const float4*>(p.bias + brow);
-            const float4* bgp = reinterpret_cast<const float4*>(p.bias + brow + UN / 2);
+            const uint32_t bvp = bias_u32 + (uint32_t)(q * PANEL) * 4, bgp = bvp + (UN / 2) * 4;  // value / gate bias of the panel
             mbar_wait(res_full_bar + b, rph);  // the slot is free
             tmem_ld_wait();
             reg_fence32(av);
@@ -528,39 +690,40 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               if (lane == 0) mbar_arrive_cluster(tmem_empty_bar + ts, 0);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {  // 8 outputs per 16-byte chunk
-              float o[8];
+            for (int c = 0; c < 4; ++c) {  // 8 outputs per 16-byte chunk, computed as 4 packed pairs
+              uint32_t o[4];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int i = 2 * c + h;
-                // bias rows of this 4-column piece (uniform addresses: L1 broadcast)
-                const float4 bv = p.bias ? __ldg(bvp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 bg = p.bias ? __ldg(bgp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                o[4 * h + 0] = (__uint_as_float(av[4 * i + 0]) + bv.x) * gelu_erf_fast(__uint_as_float(ag[4 * i + 0]) + bg.x);
-                o[4 * h + 1] = (__uint_as_float(av[4 * i + 1]) + bv.y) * gelu_erf_fast(__uint_as_float(ag[4 * i + 1]) + bg.y);
-                o[4 * h + 2] = (__uint_as_float(av[4 * i + 2]) + bv.z) * gelu_erf_fast(__uint_as_float(ag[4 * i + 2]) + bg.z);
-                o[4 * h + 3] = (__uint_as_float(av[4 * i + 3]) + bv.w) * gelu_erf_fast(__uint_as_float(ag[4 * i + 3]) + bg.w);
+                // bias of this 4-column piece (uniform address: shared-memory broadcast)
+                const float4 bv = lds128(bvp + i * 16), bg = lds128(bgp + i * 16);
+                const uint64_t v01 = add2(pku(av[4 * i + 0], av[4 * i + 1]), pk(bv.x, bv.y));
+                const uint64_t v23 = add2(pku(av[4 * i + 2], av[4 * i + 3]), pk(bv.z, bv.w));
+                const uint64_t g01 = gelu_erf_fast2(add2(pku(ag[4 * i + 0], ag[4 * i + 1]), pk(bg.x, bg.y)));
+                const uint64_t g23 = gelu_erf_fast2(add2(pku(ag[4 * i + 2], ag[4 * i + 3]), pk(bg.z, bg.w)));
+                float r0, r1, r2, r3;
+                upk(mul2(v01, g01), r0, r1);
+                upk(mul2(v23, g23), r2, r3);
+                o[2 * h + 0] = pack_bf16(r0, r1);
+                o[2 * h + 1] = pack_bf16(r2, r3);
               }
-              sts128u(s16 + (((uint32_t)c << 4) ^ sw64), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                      pack_bf16(o[6], o[7]));
+              sts128u(s16 + (((uint32_t)c << 4) ^ sw64), o[0], o[1], o[2], o[3]);
             }
           } else {
             const int sub = q / PPS, pp = q - sub * PPS;
             const int gcol = t.n_unit * (NSUB * UN) + sub * UN + pp * PANEL;
             uint32_t acc[32];
+            PAIR_DETAIL(0);
             tmem_ld32_nowait(tmem_base + lane_bits + (uint32_t)(ts * ACC_COLS + sub * UN + pp * PANEL), acc);
-            // per-column operands, requested while the TMEM read is in flight (uniform addresses: one L1 line each)
-            float4 bb[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              bb[i] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             uint4 eb[4];
-            if (p.emb) {
-              const uint4* er = reinterpret_cast<const uint4*>(p.emb + (int64_t)(min(m, p.M - 1) / p.pix_per_img) * p.lde + gcol);
+            if (emb_gather) {
+              const uint4* er = reinterpret_cast<const uint4*>(p.emb + (int64_t)fdiv(min(m, p.M - 1), p.d_ppi) * p.lde + gcol);
 #pragma unroll
               for (int c = 0; c < 4; ++c) eb[c] = __ldg(er + c);
             }
+            const uint32_t bcol = bias_u32 + (uint32_t)(sub * UN + pp * PANEL) * 4;
             mbar_wait(res_full_bar + b, rph);  // the slot is free and its residual panel (if any) has landed
+            PAIR_DETAIL(1);
             uint4 rb[4];
             if (p.has_res16) {
 #pragma unroll
@@ -568,40 +731,69 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             }
             tmem_ld_wait();
             reg_fence32(acc);
+            PAIR_DETAIL_DEP(2, acc[31]);
+            if (g == 0 && warp == EPI_WARP0 && lane == 0) PAIR_TRACE(12);
             if (q == q_last) {
               tcgen05_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster(tmem_empty_bar + ts, 0);
             }
+            // The math runs in phases over all 32 columns: every phase is one straight-line block of independent
+            // instructions.  (One loop over 4-column pieces with the operand tests inside compiled to a chain of short
+            // basic blocks: ~350 dependent instructions at 4-5 clk each = 1400 clk per panel, the whole epilogue's pace.)
+            // v = acc * alpha + colvec, colvec = (bias + embedding row) * alpha prepared per unit.
             float v[32];
+            {
+              float4 bb[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float x0 = __uint_as_float(acc[4 * i + 0]) + bb[i].x, x1 = __uint_as_float(acc[4 * i + 1]) + bb[i].y;
-              float x2 = __uint_as_float(acc[4 * i + 2]) + bb[i].z, x3 = __uint_as_float(acc[4 * i + 3]) + bb[i].w;
-              if (p.emb) {
-                const uint32_t e01 = (i & 1) ? eb[i >> 1].z : eb[i >> 1].x, e23 = (i & 1) ? eb[i >> 1].w : eb[i >> 1].y;
-                x0 += __uint_as_float(e01 << 16);
-                x1 += __uint_as_float(e01 & 0xFFFF0000u);
-                x2 += __uint_as_float(e23 << 16);
-                x3 += __uint_as_float(e23 & 0xFFFF0000u);
+              for (int i = 0; i < 8; ++i) bb[i] = lds128(bcol + i * 16);  // uniform address: broadcast
+              const uint64_t alpha2 = pk(p.alpha, p.alpha);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                upk(fma2(pku(acc[4 * i + 0], acc[4 * i + 1]), alpha2, pk(bb[i].x, bb[i].y)), v[4 * i + 0], v[4 * i + 1]);
+                upk(fma2(pku(acc[4 * i + 2], acc[4 * i + 3]), alpha2, pk(bb[i].z, bb[i].w)), v[4 * i + 2], v[4 * i + 3]);
               }
-              x0 *= p.alpha; x1 *= p.alpha; x2 *= p.alpha; x3 *= p.alpha;
-              if (p.has_res32) {
-                const float4 r = lds128(s32 + (((uint32_t)i << 4) ^ sw128));
-                x0 += r.x; x1 += r.y; x2 += r.z; x3 += r.w;
+            }
+            if (emb_gather) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t e[4] = {eb[c].x, eb[c].y, eb[c].z, eb[c].w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  v[8 * c + 2 * h + 0] = fmaf(__uint_as_float(e[h] << 16), p.alpha, v[8 * c + 2 * h + 0]);
+                  v[8 * c + 2 * h + 1] = fmaf(__uint_as_float(e[h] & 0xFFFF0000u), p.alpha, v[8 * c + 2 * h + 1]);
+                }
               }
-              if (p.has_res16) {
-                const uint32_t r01 = (i & 1) ? rb[i >> 1].z : rb[i >> 1].x, r23 = (i & 1) ? rb[i >> 1].w : rb[i >> 1].y;
-                x0 += __uint_as_float(r01 << 16);
-                x1 += __uint_as_float(r01 & 0xFFFF0000u);
-                x2 += __uint_as_float(r23 << 16);
-                x3 += __uint_as_float(r23 & 0xFFFF0000u);
+            }
+            if (p.has_res32) {
+              float4 r[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = lds128(s32 + (((uint32_t)i << 4) ^ sw128));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                upk(add2(pk(v[4 * i + 0], v[4 * i + 1]), pk(r[i].x, r[i].y)), v[4 * i + 0], v[4 * i + 1]);
+                upk(add2(pk(v[4 * i + 2], v[4 * i + 3]), pk(r[i].z, r[i].w)), v[4 * i + 2], v[4 * i + 3]);
               }
-              if (p.act == MKD_ACT_SILU) {
-                x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3);
+            }
+            if (p.has_res16) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t e[4] = {rb[c].x, rb[c].y, rb[c].z, rb[c].w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  v[8 * c + 2 * h + 0] += __uint_as_float(e[h] << 16);
+                  v[8 * c + 2 * h + 1] += __uint_as_float(e[h] & 0xFFFF0000u);
+                }
               }
-              v[4 * i + 0] = x0; v[4 * i + 1] = x1; v[4 * i + 2] = x2; v[4 * i + 3] = x3;
-              if (p.has_y32) sts128(s32 + (((uint32_t)i << 4) ^ sw128), x0, x1, x2, x3);
+            }
+            if (p.act == MKD_ACT_SILU) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = silu_f(v[c]);
+            }
+            if (p.has_y32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                sts128(s32 + (((uint32_t)i << 4) ^ sw128), v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
             if (p.has_y16) {
 #pragma unroll
@@ -638,9 +830,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               ++lp;
             }
           }
+          if (g == 0 && warp == EPI_WARP0 && lane == 0) PAIR_TRACE(13);
+          PAIR_DETAIL(3);
           fence_proxy_async();  // this thread's panel writes -> visible to the TMA store
+          PAIR_DETAIL(4);
           __syncwarp();
           if (lane == 0) mbar_arrive(computed_bar + b);
+          PAIR_DETAIL(5);
+          if (quad == 0 && lane == 0) {
+            if (g == 0) PAIR_TRACE(6);
+            PAIR_TRACE(10);
+          }
         }
         if (++b == p.npb) {
           b = 0;
@@ -655,6 +855,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
+  if (threadIdx.x == 0) PAIR_TRACE(11);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -688,6 +889,13 @@ int encode_panel_map(CUtensorMap* map, bool f32, const void* base, int64_t rows,
   cuuint32_t box[2] = {PANEL, BM};
   return encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 2, dims, str, box,
                 f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.m = d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d);
+  return f;
 }
 
 struct PairPlan {
@@ -729,6 +937,14 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
     pl.m_tiles = (pl.M + BM - 1) / BM;
   }
   const int m_pairs = (pl.m_tiles + 1) / 2, kblocks = pl.Ktot / BK;
+  // the kernel divides by launch constants with umulhi(n, ceil(2^32 / d)), exact while n * d < 2^32
+  {
+    const uint64_t lim = 1ull << 32, units_max = (uint64_t)m_pairs * (d->K / 160 + 1) * 16 + 2 * num_sms();
+    if (units_max * (uint64_t)(d->K / 160 + 1) >= lim || units_max * (uint64_t)m_pairs >= lim ||
+        (uint64_t)(pl.M + BM) * (uint64_t)(pl.P * pl.Q) >= lim || (uint64_t)kblocks * (uint64_t)(d->C / BK) >= lim ||
+        (uint64_t)(2 * m_pairs) * (uint64_t)(pl.tiles_w * pl.tiles_h) >= lim)
+      return false;
+  }
   pl.stats = d->stats != nullptr;
   pl.splits = 1;
   if (d->act == MKD_ACT_GEGLU) {
@@ -833,6 +1049,14 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   p.n_units = d->K / (NSUB * UN);
   p.num_units = p.m_pairs * p.n_units * pl.splits;
   p.stages = pl.stages; p.npb = pl.npb; p.slot_bytes = pl.slot_bytes; p.off16 = pl.off16;
+  p.d_n_units = make_fastdiv(p.n_units);
+  p.d_m_pairs = make_fastdiv(p.m_pairs);
+  p.d_cblocks = make_fastdiv(p.cblocks);
+  p.d_S = make_fastdiv(p.S);
+  p.d_tiles_w = make_fastdiv(p.tiles_w);
+  p.d_tiles_h = make_fastdiv(p.tiles_h);
+  p.d_ppi = make_fastdiv(pl.P * pl.Q);
+
   p.M = pl.M;
   p.pix_per_img = pl.P * pl.Q;
   p.lde = d->lde;
@@ -840,8 +1064,10 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   p.alpha = partial ? 1.0f : d->alpha;
   p.bias = partial ? nullptr : d->bias;
   p.emb = partial ? nullptr : (const bf16*)d->emb;
+  p.emb_uniform = (pl.P * pl.Q) % BM == 0;
   p.stats = reinterpret_cast<float2*>(d->stats);
   p.stats_ld = d->stats_ld;
+  p.trace = debug_trace_ptr();
   r32map = r16map = y32map = y16map = amap;  // (unused maps must still be valid kernel parameters)
   if (partial) {
     p.has_y32 = 1;

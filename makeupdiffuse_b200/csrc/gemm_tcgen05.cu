@@ -1399,6 +1399,7 @@ int materialise(const mkd_conv_desc* d_in, const Geometry& g, mkd_conv_desc& dd,
 }  // namespace
 
 namespace mkd {
+unsigned long long* debug_trace_ptr() { return g_trace; }
 bool conv2d_pair_supported(const mkd_conv_desc* d, bool forced);          // gemm_pair.cu
 int conv2d_pair(const mkd_conv_desc* d, bool forced, cudaStream_t stream);  // gemm_pair.cu
 
