@@ -270,11 +270,7 @@ int launch_mma(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int 
   return MKD_OK;
 }
 bool attn_force_mma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MKD_ATTN");
-    v = (e && e[0] == 'm') ? 1 : 0;
-  }
+  static const int v = debug_switch("MKD_ATTN_MMA", 0);  // trace builds: 1 = the mma.sync kernel for every head dim (A/B runs)
   return v == 1;
 }
 }  // namespace

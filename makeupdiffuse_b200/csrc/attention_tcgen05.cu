@@ -373,11 +373,7 @@ bool attention_tcgen05_supported(int d, int ldq, int ldk, int ldv) {
 int attention_tcgen05(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d,
                       int ldq, int ldk, int ldv, int ldo, float scale, cudaStream_t st) {
   const int dn = (d + 15) / 16 * 16;
-  static int pair = -1;  // MKD_ATTN_PAIR=1: two warpgroups per CTA also for head dims <= 64 (A/B measurements)
-  if (pair < 0) {
-    const char* e = getenv("MKD_ATTN_PAIR");
-    pair = (e && e[0] == '1') ? 1 : 0;
-  }
+  static const int pair = debug_switch("MKD_ATTN_PAIR", 0);  // 1: two warpgroups per CTA also for head dims <= 64 (A/B measurements)
 #define MKD_ATTN_ARGS q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st
   if (dn <= 64 && !pair) {
     if (dn <= 16) return launch<16, 1, 2, 2>(MKD_ATTN_ARGS);

@@ -1,5 +1,6 @@
 // Shared device/host helpers for libmkd_b200 (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -118,6 +119,16 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 }
 bool pdl_enabled();
+// Experiment switches (A/B runs, timing experiments) exist only in trace builds (-DMKD_ENABLE_TRACE, i.e.
+// `MKD_TRACE=1 python -m makeupdiffuse_b200.build --force`); the shipped library has ONE code path and reads no environment.
+#ifdef MKD_ENABLE_TRACE
+inline int debug_switch(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#else
+constexpr int debug_switch(const char*, int dflt) { return dflt; }
+#endif
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

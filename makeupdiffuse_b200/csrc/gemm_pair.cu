@@ -77,7 +77,7 @@ struct PairP {
   int M, pix_per_img, lde;
   int has_res32, has_res16, has_y32, has_y16, act;
   int emb_uniform;                           // every 128-row tile lies inside one image: its embedding row rides in the bias vector
-  int partial_rows;                          // split-K: fp32 partial rows per split (M), else 0
+  int partial;                               // split-K: fp32 partials [split][M][N] through a 3-D map (ragged M clips per split)
   float alpha;
   const float* bias;
   const bf16* emb;
@@ -94,6 +94,8 @@ struct PairP {
   do {                                                                    \
     if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer();    \
   } while (0)
+// per-role progress words in shared memory, printed by a wait that times out
+#define PAIR_PROG(i, v) do { prog[i] = (v); } while (0)
 // detail region (after the 148 x 16 stamps): per CTA 16 panels x 8 clock64 stamps of epilogue warp 4 / 8 lane 0
 #define PAIR_DETAIL(k)                                                                                       \
   do {                                                                                                       \
@@ -109,6 +111,7 @@ struct PairP {
   } while (0)
 #else
 #define PAIR_TRACE(slot) do { } while (0)
+#define PAIR_PROG(i, v) do { } while (0)
 #define PAIR_DETAIL(k) do { } while (0)
 #define PAIR_DETAIL_DEP(k, reg) do { } while (0)
 #endif
@@ -139,13 +142,21 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "}\n" ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
-// A wait that cannot hang the GPU: a protocol error (a barrier that is never completed) traps after ~4 s instead of
-// spinning until the driver's watchdog — or the box's time limit — kills the process.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
-  printf("gemm_pair: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-  __trap();
+// A wait that cannot hang the GPU: a protocol error (a barrier that is never completed) traps after a few seconds instead
+// of spinning until the driver's watchdog — or the box's time limit — kills the process.  `site` names the waiting role;
+// upstream roles time out first (2 s + 0.5 s x site), so the message names the wait closest to the cause.
+enum { SITE_PROD_EMPTY = 0, SITE_MMA_FULL = 1, SITE_MMA_TMEM_EMPTY = 2, SITE_EPI_TMEM_FULL = 3, SITE_EPI_RES = 4, SITE_EPI_PREV = 4, SITE_DMA_COMPUTED = 5 };
+__device__ int g_pair_shape[8];  // last launch: M, n cols, kblocks, num_units, stages, npb, operand flags, splits
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int site, int a, int b, volatile int* prog) {
+  if ((threadIdx.x & 31) != 0 && site != SITE_DMA_COMPUTED) return;
+  if (prog) printf("gemm_pair: block %d progress prod %d mma %d dma %d wg0 %d wg1 %d\n", (int)blockIdx.x, prog[0], prog[1], prog[2], prog[3], prog[4]);
+  printf("gemm_pair: mbarrier wait timed out: site %d block %d thread %d smem 0x%x parity %u state (%d, %d); launch M %d N %d kblocks %d "
+         "units %d stages %d npb %d flags 0x%x kb_per_split %d grid %d\n",
+         site, (int)blockIdx.x, (int)threadIdx.x, bar, parity, a, b, g_pair_shape[0], g_pair_shape[1], g_pair_shape[2], g_pair_shape[3],
+         g_pair_shape[4], g_pair_shape[5], g_pair_shape[6], g_pair_shape[7], (int)gridDim.x);
+  if (site == SITE_DMA_COMPUTED) __trap();  // (the last role to time out: every other one has reported by then)
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int site, int a = 0, int b = 0, volatile int* prog = nullptr) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done, spins = 0;
   unsigned long long t0 = 0;
@@ -163,7 +174,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 255u) == 0) {
       const unsigned long long now = gtimer();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) mbar_timeout(addr, parity);
+      else if (now - t0 > 2000000000ull + 500000000ull * (unsigned)site) { mbar_timeout(addr, parity, site, a, b, prog); t0 = now; }
     }
   }
 }
@@ -192,6 +203,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(map)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
@@ -400,6 +416,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
   uint64_t* res_full_bar = tmem_empty_bar + 2;       // [MAX_SLOTS] slot is free and its residual (if any) has landed
   uint64_t* computed_bar = res_full_bar + MAX_SLOTS; // [MAX_SLOTS] the panel in the slot is ready to be stored
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(computed_bar + MAX_SLOTS);
+  [[maybe_unused]] volatile int* prog = reinterpret_cast<volatile int*>(tmem_slot + 4);  // per-role progress (trace builds), printed on a timeout
+  if (threadIdx.x < 8) prog[threadIdx.x] = -1;
   float* biasv = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full_bar) + 512);  // [2 warpgroups][2][BIASV_FLOATS]
   // kernel parameters live in constant memory that is cold at every launch: touch every line now, so that the misses
   // (~1 us when taken one after the other in front of the first TMA) overlap the prologue's barriers instead
@@ -407,6 +425,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
                "l"(p.stats), "r"(p.stats_ld));
 
   if (threadIdx.x == 0) PAIR_TRACE(0);
+  if (blockIdx.x == 0 && threadIdx.x == 96) {  // (idle warp 3) what to print if a wait times out
+    g_pair_shape[0] = p.M; g_pair_shape[1] = p.n_units * ACC_COLS; g_pair_shape[2] = p.kblocks; g_pair_shape[3] = p.num_units;
+    g_pair_shape[4] = p.stages; g_pair_shape[5] = p.npb;
+    g_pair_shape[6] = p.has_res32 | p.has_res16 << 1 | p.has_y32 << 2 | p.has_y16 << 3 | p.partial << 4 | p.conv << 5 | STATS << 6 | MODE << 7 | (p.emb != nullptr) << 8;
+    g_pair_shape[7] = p.kb_per_split;
+  }
   if (warp == 0) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
@@ -464,7 +488,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const int nb = t.n_unit * (NSUB * UN) + (int)rank * (UN / 2);  // this CTA's half of sub-tile 0's weight rows
 #pragma unroll 1
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
-        mbar_wait(empty_bar + s, ph ^ 1);  // (own copy) the MMAs that read this slot have retired
+        if (lane == 0) PAIR_PROG(0, u * 1000 + kb);
+        mbar_wait(empty_bar + s, ph ^ 1, SITE_PROD_EMPTY, u, kb, prog);  // (own copy) the MMAs that read this slot have retired
         if (elect_one()) {
           if (u == pair_id && kb == t.kb0) PAIR_TRACE(15);
           unsigned char* sa = smem + s * STAGE_BYTES;
@@ -501,12 +526,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       for (int u = pair_id; u < p.num_units; u += num_pairs, ++j) {
         const Unit t = decode_unit(p, u);
         const int ts = j % TS, use = j / TS;
-        mbar_wait(tmem_empty_bar + ts, (use & 1) ^ 1);  // both CTAs' epilogue warps have drained this accumulator buffer
+        mbar_wait(tmem_empty_bar + ts, (use & 1) ^ 1, SITE_MMA_TMEM_EMPTY, u, j, prog);  // both CTAs' epilogue warps have drained this accumulator buffer
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(ts * ACC_COLS);
 #pragma unroll 1
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(full_bar + s, ph);
+          if (lane == 0) PAIR_PROG(1, u * 1000 + kb);
+          mbar_wait(full_bar + s, ph, SITE_MMA_FULL, u, kb, prog);
           tcgen05_fence_after();
           if (elect_one()) {
             if (j == 0 && kb == t.kb0) PAIR_TRACE(3);
@@ -559,16 +585,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       };
       Cursor ld = {pair_id, 0, 0, 0, 0, 0}, st = {pair_id, 0, 0, 0, 0, 0};
       enter_unit(ld);
-      int st_row_off = enter_unit(st) * p.partial_rows;
+      int st_split = enter_unit(st);
       uint32_t sph = 0;
 #pragma unroll 1
       for (int i = 0; i < total + D; ++i) {
+        PAIR_PROG(2, i * 10);
         if (i < total) {
           // the slot's previous panel (i - npb) was stored npb - D iterations ago: at most npb - D - 1 younger groups
           if (i >= p.npb) {
             if (D == p.npb - 2) bulk_wait_read<1>();
             else bulk_wait_read<0>();
           }
+          PAIR_PROG(2, i * 10 + 1);
           unsigned char* slot = slots + ld.slot * p.slot_bytes;
           if (any_res && ld.valid) {
             mbar_expect_tx(res_full_bar + ld.slot, res_bytes);
@@ -585,13 +613,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           }
         }
         if (i >= D) {
+          PAIR_PROG(2, i * 10 + 2);
           unsigned char* slot = slots + st.slot * p.slot_bytes;
-          mbar_wait(computed_bar + st.slot, sph);
+          mbar_wait(computed_bar + st.slot, sph, SITE_DMA_COMPUTED, i, st.slot, prog);
           if (st.valid) {
-            if (p.has_y32) tma_store_2d(&y32map, slot, st.col + st.q * PANEL, st.row + st_row_off);
+            if (p.partial) tma_store_3d(&y32map, slot, st.col + st.q * PANEL, st.row, st_split);
+            else if (p.has_y32) tma_store_2d(&y32map, slot, st.col + st.q * PANEL, st.row);
             if (p.has_y16) tma_store_2d(&y16map, slot + p.off16, st.col + st.q * PANEL, st.row);
           }
           bulk_commit();
+          PAIR_PROG(2, i * 10 + 3);
           if (i == D) PAIR_TRACE(7);
           PAIR_TRACE(8);
           if (++st.slot == p.npb) {
@@ -601,7 +632,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           if (++st.q == PPU) {
             st.q = 0;
             st.u += num_pairs;
-            if (st.u < p.num_units) st_row_off = enter_unit(st) * p.partial_rows;
+            if (st.u < p.num_units) st_split = enter_unit(st);
           }
         }
       }
@@ -616,6 +647,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     const uint32_t sw128 = (uint32_t)(row & 7) << 4;       // SWIZZLE_128B: 16-byte chunk index ^= row % 8
     const uint32_t sw64 = (uint32_t)((row >> 1) & 3) << 4; // SWIZZLE_64B:  16-byte chunk index ^= (row / 2) % 4
     const uint32_t slots_u32 = smem_u32(slots);
+    // slot_order note.  A parity wait is only sound when the waiter can be at most one phase ahead of the barrier.  With an
+    // odd number of slots consecutive uses of a slot belong to ALTERNATE warpgroups, and nothing else keeps one warpgroup
+    // from running two panels ahead of the other (its residual panels may simply land first): waiting for use n of
+    // res_full[b] while use n - 1 has not completed passes at once (same parity as "use n done") and the warpgroup
+    // overwrites a slot the other one has not even started.  So before a slot's use n a warpgroup first waits for the
+    // slot's previous panel to have been computed (computed[b], use n - 1), which implies res_full[b] finished use n - 1.
     int g = 0, b = 0, j = 0;
     uint32_t rph = 0;
     [[maybe_unused]] int lp = 0;  // statistics scratch buffer parity (panels this warpgroup has reduced)
@@ -666,8 +703,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
 #pragma unroll 1
       for (int q = 0; q < PPU; ++q, ++g) {
         if ((g & 1) == wg) {
+          if (quad == 0 && lane == 0) PAIR_PROG(3 + wg, g * 10);
           if (!waited) {
-            mbar_wait(tmem_full_bar + ts, use & 1);
+            mbar_wait(tmem_full_bar + ts, use & 1, SITE_EPI_TMEM_FULL, u, j, prog);
             tcgen05_fence_after();
             waited = true;
             if (j == 0 && warp == EPI_WARP0 && lane == 0) PAIR_TRACE(5);
@@ -680,7 +718,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
             tmem_ld32_nowait(taddr, av);
             tmem_ld32_nowait(taddr + UN / 2, ag);
             const uint32_t bvp = bias_u32 + (uint32_t)(q * PANEL) * 4, bgp = bvp + (UN / 2) * 4;  // value / gate bias of the panel
-            mbar_wait(res_full_bar + b, rph);  // the slot is free
+            if (g >= p.npb) mbar_wait(computed_bar + b, rph ^ 1, SITE_EPI_PREV, g, b, prog);  // (see slot_order note)
+            mbar_wait(res_full_bar + b, rph, SITE_EPI_RES, g, b, prog);  // the slot is free
             tmem_ld_wait();
             reg_fence32(av);
             reg_fence32(ag);
@@ -722,7 +761,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
               for (int c = 0; c < 4; ++c) eb[c] = __ldg(er + c);
             }
             const uint32_t bcol = bias_u32 + (uint32_t)(sub * UN + pp * PANEL) * 4;
-            mbar_wait(res_full_bar + b, rph);  // the slot is free and its residual panel (if any) has landed
+            if (g >= p.npb) mbar_wait(computed_bar + b, rph ^ 1, SITE_EPI_PREV, g, b, prog);  // (see slot_order note)
+            mbar_wait(res_full_bar + b, rph, SITE_EPI_RES, g, b, prog);  // the slot is free and its residual panel (if any) has landed
             PAIR_DETAIL(1);
             uint4 rb[4];
             if (p.has_res16) {
@@ -832,6 +872,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           }
           if (g == 0 && warp == EPI_WARP0 && lane == 0) PAIR_TRACE(13);
           PAIR_DETAIL(3);
+          if (quad == 0 && lane == 0) PAIR_PROG(3 + wg, g * 10 + 5);
           fence_proxy_async();  // this thread's panel writes -> visible to the TMA store
           PAIR_DETAIL(4);
           __syncwarp();
@@ -1071,8 +1112,11 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   r32map = r16map = y32map = y16map = amap;  // (unused maps must still be valid kernel parameters)
   if (partial) {
     p.has_y32 = 1;
-    p.partial_rows = pl.M;
-    rc = encode_panel_map(&y32map, true, d->workspace, (int64_t)pl.splits * pl.M, d->K, d->K);
+    p.partial = 1;
+    cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)pl.M, (cuuint64_t)pl.splits};
+    cuuint64_t str[2] = {(cuuint64_t)d->K * 4, (cuuint64_t)d->K * 4 * (cuuint64_t)pl.M};
+    cuuint32_t box[3] = {PANEL, BM, 1};
+    rc = encode(&y32map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d->workspace, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   } else {
     if (d->residual && d->residual_dtype == MKD_F32) {

@@ -1157,11 +1157,7 @@ int pick_bn(const mkd_conv_desc* d, const Geometry& g) {
   // N tile (profiles/r01_mma_probe.txt): at N = 256 that is the MMA floor, at N = 160 it is 0.6 of it.  MKD_WIDE_SPLITK=0
   // disables (A/B runs).
   {
-    static int we = -1;
-    if (we < 0) {
-      const char* e = getenv("MKD_WIDE_SPLITK");
-      we = (e && e[0] == '0') ? 0 : 1;
-    }
+    static const int we = debug_switch("MKD_WIDE_SPLITK", 1);
     const int kblocks = g.Ktot / BK;
     // measured (tools/gemm_bench.py): 1024 x 1280 x 11520  39.5 -> 34.2 us; at M = 256 (4x4 level, 11 splits) it LOSES
     // (16.5 -> 17.9 us): only from 4 row tiles up
@@ -1182,12 +1178,8 @@ int pick_bn(const mkd_conv_desc* d, const Geometry& g) {
 
 unsigned long long* g_trace = nullptr;
 int cluster_pref() {  // MKD_CLUSTER=2 selects the A-multicast CTA-pair kernel for BN = 160 (measured ~2 % slower: opt-in)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MKD_CLUSTER");
-    v = (e && atoi(e) >= 1 && atoi(e) <= 2) ? atoi(e) : 1;
-  }
-  return v;
+  static const int v = debug_switch("MKD_CLUSTER", 1);
+  return v == 2 ? 2 : 1;
 }
 
 template <int BN, int CL>
@@ -1297,17 +1289,12 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   mp.half_dw = half_dw; mp.half_dh = half_dh; mp.half_dn = half_dn;
   mp.trace = g_trace;
   {
-    static int ge = -1;  // MKD_COMMIT_EVERY overrides the release granularity (experiments)
-    if (ge < 0) {
-      const char* e = getenv("MKD_COMMIT_EVERY");
-      ge = e ? atoi(e) : 0;
-    }
+    static const int ge = debug_switch("MKD_COMMIT_EVERY", 0);  // overrides the release granularity (experiments)
     mp.commit_every = ge > 0 ? ge : 1;  // measured: G = 1, 2, 3 give identical k-block times
   }
   {
     // timing experiments (RESULTS INVALID): 1 skip B loads, 2 skip MMA issue, 4 skip epilogue stores, 8 skip residual loads
-    const char* e = getenv("MKD_DEBUG_TIMING");
-    mp.debug = e ? atoi(e) : 0;
+    mp.debug = debug_switch("MKD_DEBUG_TIMING", 0);
   }
   int variant = ep.partial ? 3 : ep.stats ? 4 : (ep.act == MKD_ACT_GEGLU ? 2 : (ep.act == MKD_ACT_SILU ? 1 : 0));
   if (SP && (variant == 0 || variant == 4) && !ep.emb && (!ep.res || ep.res_f32) && !mp.debug) {
@@ -1325,11 +1312,7 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
     // K = 8640 gains (82.3 -> 77.3 us); whole step 7.28 -> 7.45 ms.  A dual k-block takes ~2.5x a single one, so the main
     // loop is NOT paced by the A tile alone: time follows the bytes that cross shared memory per k-block (TMA writes + the
     // MMA's operand reads), which DUAL does not reduce per FLOP.  Off by default; kept as the experiment it is.
-    static int de = -1;
-    if (de < 0) {
-      const char* e = getenv("MKD_DUAL");
-      de = (e && e[0] == '1') ? 1 : 0;
-    }
+    static const int de = debug_switch("MKD_DUAL", 0);
     if (SP && de && (variant == 4 || variant == 9) && splits == 1 && n_tiles % 2 == 0 && g.m_tiles * n_tiles > num_sms() && !mp.debug) {
       variant = variant == 4 ? 10 : 11;
       mp.n_tiles = n_tiles / 2;
@@ -1369,6 +1352,9 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
 
 // debug hook (not part of the public header): device buffer of 148*16 u64 that the next GEMM launches stamp
 extern "C" void mkd_debug_set_trace(void* p) { g_trace = static_cast<unsigned long long*>(p); }
+// debug hook (not part of the public header): 0 = MKD_PATH_AUTO never picks the CTA-pair kernel (bisection / A-B runs)
+static int g_pair_auto = 1;
+extern "C" void mkd_debug_set_pair_auto(int on) { g_pair_auto = on; }
 
 namespace {
 // Downsample (3x3 stride 2) and Upsample (nearest x2 + 3x3): materialise (im2col / upsampled copy) into the head of the
@@ -1445,7 +1431,7 @@ int conv2d_tcgen05(const mkd_conv_desc* d_in, cudaStream_t stream) {
   // the CTA-pair kernel (cta_group::2, TMA-store epilogue) takes the shapes it is built for; the single-CTA kernel
   // keeps the rest (ragged M, narrow / odd channel counts, tiny problems)
   const bool geglu128 = d->act == MKD_ACT_GEGLU && d->geglu_block == 128;  // a row blocking only the pair kernel reads
-  if (d_in->path != MKD_PATH_TCGEN05_SINGLE || geglu128) {
+  if ((d_in->path != MKD_PATH_TCGEN05_SINGLE && (g_pair_auto || d_in->path == MKD_PATH_TCGEN05_PAIR)) || geglu128) {
     const bool forced = d_in->path == MKD_PATH_TCGEN05_PAIR || geglu128;
     if (conv2d_pair_supported(d, forced)) return conv2d_pair(d, forced, stream);
   }

@@ -52,8 +52,8 @@ class B200ControlLDM:
         self.sqrt_recip_alphas_cumprod = f32(np.sqrt(1.0 / ac))
         self.sqrt_recipm1_alphas_cumprod = f32(np.sqrt(1.0 / ac - 1))
         self._cond_cache = {}
-        # ControlNet trunk on a second stream, concurrent with the UNet encoder (MKD_CONCURRENT=0 serialises, for A/B runs)
-        self.concurrent = os.environ.get("MKD_CONCURRENT", "1") != "0"
+        # ControlNet trunk on a second stream, concurrent with the UNet encoder (set False to serialise: profiling, A/B runs)
+        self.concurrent = True
         self._side = None
 
     @property

@@ -50,7 +50,8 @@ class Act:
 
 
 def _geglu_block(inner: int) -> int:
-    for gb in (80, 64, 32, 16, 8):
+    # 128: the CTA-pair kernel's [128 value | 128 gate] tiles (one 256-wide MMA per k-step); 80: the single-CTA kernel's
+    for gb in (128, 80, 64, 32, 16, 8):
         if inner % gb == 0:
             return gb
     raise ValueError(f"FF inner dim {inner} not supported")
@@ -92,7 +93,7 @@ class _Net(nn.Module):
         self.middle = [("res", "middle_block.0", ch, ch), ("st", "middle_block.1", ch), ("res", "middle_block.2", ch, ch)]
         self._ch, self._ds = ch, ds
         self._attn_res = tuple(attention_resolutions)
-        self.fused_gn_stats = os.environ.get("MKD_FUSED_GN", "1") != "0"  # MKD_FUSED_GN=0: always the two-phase GroupNorm
+        self.fused_gn_stats = True  # False: always the two-phase GroupNorm (A/B runs)
         self._channel_mult, self._nrb = tuple(channel_mult), num_res_blocks
         self.w: dict[str, torch.Tensor] = {}
         self._bufs: dict = {}
