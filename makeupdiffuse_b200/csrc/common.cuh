@@ -119,6 +119,21 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 }
 bool pdl_enabled();
+// L2 prefetch of this CTA's share of a launch's weights, issued by one warp BEFORE pdl_wait(): weights are cold in HBM at
+// every layer (2.4 GB per step against 126 MB of L2), the prefetch touches no SM state, and it is harmless whatever the
+// previous kernel is still writing (L2 is the coherence point).  So the weight stream starts while the previous kernel
+// drains instead of after the first full-barrier wait of the main loop.  Capped: activations should stay L2-resident.
+__device__ __forceinline__ void l2_prefetch_share(const void* base, unsigned long long bytes, int lane) {
+  constexpr unsigned long long CAP = 48ull << 20, CHUNK = 8192;
+  if (bytes > CAP) bytes = CAP;
+  const unsigned long long per = ((bytes + gridDim.x - 1) / gridDim.x + CHUNK - 1) / CHUNK * CHUNK;
+  const unsigned long long lo = (unsigned long long)blockIdx.x * per;
+  const unsigned long long hi = lo + per < bytes ? lo + per : bytes;
+  for (unsigned long long o = lo + (unsigned long long)lane * CHUNK; o < hi; o += 32 * CHUNK) {
+    const unsigned n = (unsigned)(hi - o < CHUNK ? hi - o : CHUNK);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(reinterpret_cast<const char*>(base) + o), "r"(n) : "memory");
+  }
+}
 // Experiment switches (A/B runs, timing experiments) exist only in trace builds (-DMKD_ENABLE_TRACE, i.e.
 // `MKD_TRACE=1 python -m makeupdiffuse_b200.build --force`); the shipped library has ONE code path and reads no environment.
 #ifdef MKD_ENABLE_TRACE

@@ -66,6 +66,8 @@ struct MainP {
   int half_dw, half_dh, half_dn;    // CL == 2: coordinate offset of rank 1's half of the A box (conv mode)
   int commit_every;                 // G: smem slots are released with one tcgen05.commit per G k-blocks
   int debug;                        // debug timing experiments (results invalid): 1 = skip B loads, 2 = skip MMA issue
+  const void* w;                    // weights, for the L2 prefetch ahead of pdl_wait()
+  unsigned long long w_bytes;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -421,6 +423,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI, DUAL>::THREADS), 1) gemm_tcg
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) MKD_TRACE(0);
+  if (warp == 3) l2_prefetch_share(mp.w, mp.w_bytes, lane);  // (an epilogue / idle warp: nothing to do until the first accumulator)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
@@ -1288,6 +1291,8 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   mp.n_tiles = n_groups;
   mp.half_dw = half_dw; mp.half_dh = half_dh; mp.half_dn = half_dn;
   mp.trace = g_trace;
+  mp.w = d->w;
+  mp.w_bytes = (unsigned long long)d->K * g.Ktot * 2;
   {
     static const int ge = debug_switch("MKD_COMMIT_EVERY", 0);  // overrides the release granularity (experiments)
     mp.commit_every = ge > 0 ? ge : 1;  // measured: G = 1, 2, 3 give identical k-block times
