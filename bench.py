@@ -222,7 +222,7 @@ def main():
     ctx_dev = loc["ctx"]
 
     def one_pass_device():
-        hint_dev.add_(0.0)  # bump the version: a new batch of images -> hint block + K/V are recomputed every pass
+        # a new batch of images every pass: sample_sharded starts a loop, which drops the hoisted hint block + K/V
         cond = {"c_crossattn": [ctx_dev], "c_concat": [hint_dev]}
         lat = sample_sharded(sampler, S, Bg, (4, h, h), cond, loc["x_T"], rank, world, fused_gather=args.fused_gather)
         if args.decode:  # each rank decodes its own images

@@ -70,7 +70,7 @@ struct MainP {
   unsigned long long w_bytes;
 };
 
-__device__ __forceinline__ unsigned long long gtimer() {
+[[maybe_unused]] __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
   return t;
@@ -134,48 +134,6 @@ __device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) 
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
-// ---- cta_group::2 (CTA pair) forms: kept for reference, the pair kernel now shares A by multicast instead ------------------------------------------------------------------------------
-// Shared-window addresses carry the CTA rank in bit 24: clearing it names the same offset in the pair's leader (rank 0).
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
-// 2-SM TMA loads: data lands in the ISSUING CTA's smem, the transaction bytes complete on the LEADER's mbarrier
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
-          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
-          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-// one MMA for the pair: D[256 x N] (rows 0-127 in the leader's TMEM, 128-255 in the peer's), A 128 rows from each
-// CTA's smem, B N/2 rows from each CTA's smem (same smem offsets in both)
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// commit of the pair's MMAs, arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-// arrive on the barrier at the same offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
-      : "memory");
-}
 // one lane of a converged warp (the loops around it stay warp-uniform, so their operands live in uniform registers)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -218,17 +176,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -245,7 +192,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn, int m = BM) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
 // ---- shared epilogue math (used by the main kernel and by the split-K reducer) ------------------------------
 // r[8] = accumulators of output channels [o, o+8) of row m.
@@ -296,13 +242,6 @@ __device__ __forceinline__ void epilogue_vec8(const EpiP& e, int m, int o, float
       }
     }
   }
-}
-__device__ __forceinline__ void epilogue_store16(const EpiP& e, int m, int n, float (&v)[16]) {
-  float a[8], b[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
-  epilogue_vec8(e, m, n, a);
-  epilogue_vec8(e, m, n + 8, b);
 }
 __device__ __forceinline__ void epilogue_geglu8(const EpiP& e, int m, int row_val, int row_gate, int o, float (&a)[8],
                                                 float (&g)[8]) {

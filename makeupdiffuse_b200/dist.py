@@ -62,6 +62,8 @@ def sample_sharded(sampler, S, batch_global, shape, cond_local, x_T_local, rank=
     mine = gathered[lo:hi]
     sampler.make_schedule(ddim_num_steps=S, ddim_eta=kw.pop("eta", 0.0), verbose=False)
     steps = np.flip(sampler.ddim_timesteps)
+    if hasattr(sampler, "begin_loop"):
+        sampler.begin_loop()  # this loop reads its cond afresh (B200DDIMSampler.begin_loop)
     x = x_T_local
     for i, step in enumerate(steps):
         ts = torch.full((b,), int(step), device=x.device, dtype=torch.long)

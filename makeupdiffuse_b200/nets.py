@@ -20,7 +20,6 @@ There is no PyTorch compute fallback: without the CUDA library these classes can
 from __future__ import annotations
 
 import math
-import os
 
 import torch
 import torch.nn as nn
@@ -94,6 +93,9 @@ class _Net(nn.Module):
         self._ch, self._ds = ch, ds
         self._attn_res = tuple(attention_resolutions)
         self.fused_gn_stats = True  # False: always the two-phase GroupNorm (A/B runs)
+        # bumped whenever context_kv() / hint_features() refill their (shared, static) arena buffers: a holder of earlier
+        # results — B200ControlLDM's cond cache — compares epochs to learn that the buffers now hold another cond's data
+        self.arena_epoch = 0
         self._channel_mult, self._nrb = tuple(channel_mult), num_res_blocks
         self.w: dict[str, torch.Tensor] = {}
         self._bufs: dict = {}
@@ -248,8 +250,11 @@ class _Net(nn.Module):
         return self._buf("gn_ws", 1, ops.groupnorm_workspace_bytes(N) // 4, torch.float32)
 
     def _stats_ok(self, N, H, W):
-        """fused GroupNorm statistics: bf16 path, whole 128-row tiles per sample (so a tile never spans two samples)"""
-        return self._hi and self.fused_gn_stats and (H * W) % 128 == 0
+        """fused GroupNorm statistics: bf16 path, whole 128-row tiles per sample (so a tile never spans two samples), and
+        power-of-two maps — the only ones the tensor-core 3x3 kernels (which emit the statistics) take; other sizes
+        (48 x 48 for 384^2 images, ...) run the generic conv and the two-phase GroupNorm"""
+        pow2 = lambda v: v > 0 and v & (v - 1) == 0  # noqa: E731
+        return self._hi and self.fused_gn_stats and (H * W) % 128 == 0 and pow2(H) and pow2(W)
 
     def _stats(self, name, rows, cols):
         key = ("st_" + name, rows, cols)
@@ -366,6 +371,7 @@ class _Net(nn.Module):
         """attn2 K/V projections of the (step-invariant) text context for every SpatialTransformer: hoisted out of
         the 50-step loop (SURVEY.md §7 hard part 7).  context: [B, L, context_dim] fp32/bf16."""
         B, Lc, D = context.shape
+        self.arena_epoch += 1
         ctx = self._buf("ctx", B * Lc, D)
         ctx.copy_(context.reshape(B * Lc, D))
         out = {}
@@ -496,6 +502,7 @@ class B200ControlNet(_Net):
         """input_hint_block(hint): independent of x and t, so computed once per batch of images, not once per step.
         hint: [B, 6, 8h, 8w] fp32 in [0,1] = cat(source, reference) (makeup_diffuse.py:56).  Returns [B*h*w, mc]."""
         B, Cc, H, W = hint.shape
+        self.arena_epoch += 1
         chans = [c for c, _ in self.HINT] + [self.mc]
         strides = [s for _, s in self.HINT] + [1]
         pow2 = lambda v: v > 0 and v & (v - 1) == 0  # noqa: E731

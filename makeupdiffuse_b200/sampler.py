@@ -104,6 +104,7 @@ class B200DDIMSampler:
                       dynamic_threshold=None, **kwargs):
         dev = self.model.device
         b = shape[0]
+        self.begin_loop()
         img = torch.randn(shape, device=dev) if x_T is None else x_T
         inter = {"x_inter": [img], "pred_x0": [img]}
         steps = np.flip(self.ddim_timesteps)
@@ -126,6 +127,16 @@ class B200DDIMSampler:
                 inter["x_inter"].append(img)
                 inter["pred_x0"].append(pred_x0)
         return img, inter
+
+    def begin_loop(self):
+        """A sampling loop starts: whatever was hoisted for an earlier cond (the model's hint features and K/V, the
+        doubled CFG cond) is dropped, so the loop reads its conditioning tensors as they are NOW — also when the caller
+        refilled the same tensors in a way torch's version counter does not see.  Loops driven from outside
+        (makeupdiffuse_b200.dist.sample_sharded, a caller's own loop over denoising_step) call this themselves."""
+        self._cfg_cache = None
+        inv = getattr(self.model, "invalidate_cond_cache", None)
+        if inv is not None:
+            inv()
 
     def p_sample_ddim(self, *a, **k):
         with torch.no_grad():
@@ -153,8 +164,14 @@ class B200DDIMSampler:
         g = self._graph
         # the graph only depends on shapes: every per-cond tensor it reads (hint features, cross-attention K/V) lives
         # in a static arena buffer that model._prepare() refills in place when the cond changes
-        key = (tuple(x.shape), c["c_concat"] is None, tuple(tuple(v.shape) for v in c["c_crossattn"]), id(self.model),
-               getattr(self.model, "only_mid_control", False), tuple(getattr(self.model, "control_scales", ())))
+        m = self.model
+        nets = [getattr(m, "control_model", None), getattr(getattr(m, "model", None), "diffusion_model", None)]
+        key = (tuple(x.shape), c["c_concat"] is None, tuple(tuple(v.shape) for v in c["c_crossattn"]), id(m),
+               getattr(m, "only_mid_control", False), tuple(getattr(m, "control_scales", ())),
+               # a graph holds raw pointers and the launch structure of the moment it was captured: reloaded weights
+               # (new tensors), another stream layout or another GroupNorm path need a new capture
+               getattr(m, "_weights_epoch", 0), getattr(m, "concurrent", None),
+               tuple(getattr(n, "fused_gn_stats", None) for n in nets))
         if g is None or g["key"] != key:
             sx, st = x.clone(), t.clone()
             self.model.apply_model(sx, st, c)  # warm-up: allocates every static buffer, fills the cond cache
@@ -230,6 +247,7 @@ class B200DDIMSampler:
         steps = np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps
         steps = steps[:t_start]
         total = steps.shape[0]
+        self.begin_loop()
         x = x_latent
         for i, step in enumerate(np.flip(steps)):
             ts = torch.full((x_latent.shape[0],), int(step), device=x_latent.device, dtype=torch.long)

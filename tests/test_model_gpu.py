@@ -109,7 +109,12 @@ def test_module_level_call_forms(tiny):
     assert rel(tiny.f32.model.diffusion_model(x=x, timesteps=t, context=ctx, control=ref_ctrl, only_mid_control=True), ref_mid) < TOL_F32
 
 
-def _teacher_forced(bundle, B, h, cdim, S, cfg_scale=1.0):
+def _teacher_forced(bundle, B, h, cdim, S, cfg_scale=1.0, modes=("bf16", "f32"), f32_every=1):
+    """The oracle drives the trajectory (its own x_t at every step); at each step the B200 path evaluates the SAME
+    (x_t, t, cond).  Returned per mode: the relative L2 error of eps ITSELF — with guidance, of the doubled [uncond; cond]
+    batch the network returns (cddim.py:39) and of the guided combination e_u + s (e_c - e_u) (cddim.py:40) — and, as a
+    check of the fused update kernel, of x_prev / pred_x0 (affine in eps, so always smaller)."""
+    from makeupdiffuse_b200.sampler import _cat_uncond_first
     cond, x = make_cond(B, h, cdim, seed=11)
     uc = None
     if cfg_scale != 1.0:
@@ -118,38 +123,54 @@ def _teacher_forced(bundle, B, h, cdim, S, cfg_scale=1.0):
     so = MKDDIMSampler(bundle.oracle)
     so.make_schedule(S, ddim_eta=0.0, verbose=False)
     steps = np.flip(so.ddim_timesteps)
-    out = {"bf16": [], "f32": []}
-    samplers = {k: B200DDIMSampler(getattr(bundle, k), use_cuda_graph=False) for k in out}
+    out = {k: {"eps": [], "guided": [], "update": []} for k in modes}
+    samplers = {k: B200DDIMSampler(getattr(bundle, k), use_cuda_graph=False) for k in modes}
     for s in samplers.values():
         s.make_schedule(S, ddim_eta=0.0, verbose=False)
+    cc = cond if uc is None else _cat_uncond_first(uc, cond)
     xt = x
     for i, step in enumerate(steps):
         index = S - i - 1
         ts = torch.full((B,), int(step), device=DEV, dtype=torch.long)
+        xx, tt = (xt, ts) if uc is None else (torch.cat([xt] * 2), torch.cat([ts] * 2))
         with torch.no_grad():
+            e_ref = bundle.oracle.apply_model(xx, tt, cc)
             x_next, p0 = so.denoising_step(xt, cond, ts, index, unconditional_guidance_scale=cfg_scale,
                                            unconditional_conditioning=uc)
         for k, s in samplers.items():
+            if k == "f32" and i % f32_every:
+                continue
+            e = getattr(bundle, k).apply_model(xx, tt, cc)
+            out[k]["eps"].append(rel(e, e_ref))
+            if uc is not None:
+                gd = lambda v: v[:B] + cfg_scale * (v[B:] - v[:B])  # noqa: E731
+                out[k]["guided"].append(rel(gd(e), gd(e_ref)))
             xn, pp = s.denoising_step(xt, cond, ts, index, unconditional_guidance_scale=cfg_scale,
                                       unconditional_conditioning=uc)
-            # x_prev / pred_x0 are affine in eps: compare the eps they imply
-            out[k].append(max(rel(xn, x_next), rel(pp, p0)))
+            out[k]["update"].append(max(rel(xn, x_next), rel(pp, p0)))
         xt = x_next
     return out
 
 
 def test_sampler_teacher_forced_tiny(tiny):
     r = _teacher_forced(tiny, 2, 16, 64, S=10)
-    print("teacher-forced per-step rel-L2: fp32-check max %.2e, bf16 max %.2e" % (max(r["f32"]), max(r["bf16"])))
-    assert max(r["f32"]) < TOL_F32, r["f32"]
-    assert max(r["bf16"]) < TOL_BF16_TINY, r["bf16"]
+    print("teacher-forced per-step eps rel-L2: fp32-check max %.2e, bf16 max %.2e (x_prev / pred_x0: %.2e / %.2e)"
+          % (max(r["f32"]["eps"]), max(r["bf16"]["eps"]), max(r["f32"]["update"]), max(r["bf16"]["update"])))
+    assert max(r["f32"]["eps"]) < TOL_F32, r["f32"]
+    assert max(r["bf16"]["eps"]) < TOL_BF16_TINY, r["bf16"]
+    assert max(r["f32"]["update"]) < TOL_F32 and max(r["bf16"]["update"]) < TOL_BF16_TINY
 
 
 def test_sampler_teacher_forced_cfg_tiny(tiny):
     r = _teacher_forced(tiny, 2, 16, 64, S=5, cfg_scale=9.0)
-    print("teacher-forced CFG-9 per-step rel-L2: fp32-check max %.2e, bf16 max %.2e" % (max(r["f32"]), max(r["bf16"])))
-    assert max(r["f32"]) < 5 * TOL_F32, r["f32"]   # CFG scale 9 amplifies eps differences ~9x
-    assert max(r["bf16"]) < 5 * TOL_BF16_TINY, r["bf16"]
+    print("teacher-forced CFG-9 per-step rel-L2: eps of the doubled batch fp32-check max %.2e, bf16 max %.2e; "
+          "guided combination %.2e / %.2e" % (max(r["f32"]["eps"]), max(r["bf16"]["eps"]), max(r["f32"]["guided"]),
+                                              max(r["bf16"]["guided"])))
+    # the network output (what north_star's gate is on) is held to the plain gates; e_u + 9 (e_c - e_u) amplifies the
+    # DIFFERENCE of two nearly equal halves (same hint, other context), so its relative error is larger by construction:
+    # stated bound 5x (measured 2.6x on this net)
+    assert max(r["f32"]["eps"]) < TOL_F32 and max(r["bf16"]["eps"]) < TOL_BF16_TINY, r
+    assert max(r["f32"]["guided"]) < 5 * TOL_F32 and max(r["bf16"]["guided"]) < 5 * TOL_BF16_TINY, r
 
 
 def psnr(a, b):
@@ -171,7 +192,7 @@ def test_free_running_psnr_and_graph(tiny):
     assert len(inter["pred_x0"]) == len(ref_inter["pred_x0"])
     p32, p16 = psnr(a, ref), psnr(b, ref)
     print(f"free-running PSNR vs oracle: fp32-check {p32:.1f} dB, bf16 {p16:.1f} dB")
-    assert p32 > 60 and p16 > 25, (p32, p16)
+    assert p32 > 126 and p16 > 53, (p32, p16)  # measured 135.9 / 62.5 dB: gates within 10 dB of the measurement
 
 
 def test_sampler_kats_on_b200(tiny, monkeypatch):
@@ -238,7 +259,7 @@ def test_interpolation_sweep_config5(tiny):
     assert torch.equal(a[2], a[3]) and torch.equal(b[2], b[3])
     p32, p16 = psnr(a, ref), psnr(b, ref)
     print(f"interpolation sweep (S=20) PSNR vs oracle: fp32-check {p32:.1f} dB, bf16 {p16:.1f} dB")
-    assert p32 > 60 and p16 > 25, (p32, p16)
+    assert p32 > 124 and p16 > 51, (p32, p16)  # measured 134.3 / 60.3 dB
 
 
 @pytest.mark.parametrize("h,B", [(32, 2), (64, 1)])
@@ -308,3 +329,62 @@ def test_full_size_batch16_properties():
     assert r < TOL_BF16  # (the injecting epilogue re-emits the GroupNorm statistics of the slot: other summation order)
     del m
     torch.cuda.empty_cache()
+
+
+# ---- configs[1] / configs[3] at their real sizes against the oracle --------------------------------------------------------
+@pytest.fixture(scope="module")
+def full():
+    b = Bundle({})
+    yield b
+    del b
+    torch.cuda.empty_cache()
+
+
+def test_full_size_batch16_teacher_forced_all_50_steps(full):
+    """BASELINE.json configs[1] as benchmarked — yaml networks, batch 16, 256^2, DDIM-50 — teacher-forced over ALL 50
+    steps, comparing eps itself with the fp32 oracle (TF32 off) on the oracle's own x_t: the launch set (tile shapes,
+    split-K plans, the CTA-pair instantiations) is exactly the benchmark's.  fp32 check mode every 5th step."""
+    r = _teacher_forced(full, 16, 32, 768, S=50, f32_every=5)
+    e16, e32 = r["bf16"]["eps"], r["f32"]["eps"]
+    print("full-size batch-16 teacher-forced DDIM-50: eps rel-L2 bf16 max %.2e mean %.2e (steps %d), fp32-check max %.2e (steps %d)"
+          % (max(e16), sum(e16) / len(e16), len(e16), max(e32), len(e32)))
+    assert len(e16) == 50 and max(e16) < TOL_BF16, e16
+    assert max(e32) < TOL_F32, e32
+
+
+def test_full_size_cfg9_512(full):
+    """BASELINE.json configs[3]'s per-GPU shape: 512^2, classifier-free guidance scale 9, 4 samples -> 8 rows through the
+    networks (diffusion_makeup.py:399-408).  Three timesteps, teacher-forced."""
+    r = _teacher_forced(full, 4, 64, 768, S=4, cfg_scale=9.0, f32_every=2)
+    print("full-size 512^2 CFG-9 (8 rows): eps rel-L2 bf16 max %.2e, fp32-check max %.2e; guided combination bf16 max %.2e, "
+          "fp32-check max %.2e" % (max(r["bf16"]["eps"]), max(r["f32"]["eps"]), max(r["bf16"]["guided"]), max(r["f32"]["guided"])))
+    assert max(r["bf16"]["eps"]) < TOL_BF16 and max(r["f32"]["eps"]) < TOL_F32, r
+    assert max(r["bf16"]["guided"]) < 5 * TOL_BF16 and max(r["f32"]["guided"]) < 5 * TOL_F32, r
+
+
+def test_full_size_free_running_decoded_images(full):
+    """yaml networks, 50 free-running bf16 steps (CUDA-graph path), then the first-stage decoder: PSNR of the decoded
+    IMAGES against the oracle pipeline (fp32 UNet+ControlNet loop -> fp32 oracle decoder).  Stated bound: 40 dB."""
+    from makeupdiffuse_b200 import B200FirstStageDecoder
+    from oracle.vae import OracleFirstStageDecoder, decode_first_stage
+    B, h, S = 2, 32, 50
+    cond, x = make_cond(B, h, 768, seed=41)
+    with torch.no_grad():
+        ref, _ = MKDDIMSampler(full.oracle).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    lat, _ = B200DDIMSampler(full.bf16, use_cuda_graph=True).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    lat32, _ = B200DDIMSampler(full.f32, use_cuda_graph=False).sample(S, B, (4, h, h), cond, eta=0.0, x_T=x, verbose=False)
+    with torch.device(DEV):
+        ovae = OracleFirstStageDecoder().eval()
+    sd = seeded_state_dict(ovae, 0, prefix="first_stage_model.")
+    full.bf16.attach_first_stage_decoder(B200FirstStageDecoder(dtype=torch.bfloat16).load_state_dict(sd))
+    img = full.bf16.decode_first_stage(lat)
+    with torch.no_grad():
+        img_ref = decode_first_stage(ovae, ref, full.bf16.scale_factor)
+    to01 = lambda v: ((v.float().clamp(-1, 1) + 1) / 2)  # noqa: E731  (what save_local writes, diffusion_makeup.py:344-358)
+    mse = float(((to01(img) - to01(img_ref)) ** 2).mean())
+    p_img = 10 * math.log10(1.0 / mse)
+    p_lat, p_lat32 = psnr(lat, ref), psnr(lat32, ref)
+    print(f"full-size free-running DDIM-50: latent PSNR bf16 {p_lat:.1f} dB, fp32-check {p_lat32:.1f} dB; decoded image PSNR (bf16 "
+          f"sampler + bf16 decoder vs fp32 oracle pipeline) {p_img:.1f} dB")
+    # measured 53.8 / 66.4 / 135.8 dB: the stated bound is 40 dB on the images; the gates sit within 10 dB of the measurement
+    assert p_img > 44 and p_lat > 56 and p_lat32 > 125, (p_img, p_lat, p_lat32)

@@ -51,6 +51,109 @@ def test_param_counts_and_keys_full_size():
     assert tuple(sd["input_hint_block.14.weight"].shape) == (320, 256, 3, 3)
 
 
+def published_manifest(controlnet):
+    """Every state-dict key and shape of the SD-1.5 latent UNet / the ControlNet as published,
+    enumerated from the table there — NOT from the oracle's module tree, which is what it pins."""
+    mc, ctx, emb = 320, 768, 1280
+    m = {}
+
+    def lin(k, o, i, bias=True):
+        m[k + ".weight"] = (o, i)
+        if bias:
+            m[k + ".bias"] = (o,)
+
+    def conv(k, o, i, r):
+        m[k + ".weight"] = (o, i, r, r)
+        m[k + ".bias"] = (o,)
+
+    def norm(k, c):
+        m[k + ".weight"] = (c,)
+        m[k + ".bias"] = (c,)
+
+    def res(k, ci, co):
+        norm(k + ".in_layers.0", ci)
+        conv(k + ".in_layers.2", co, ci, 3)
+        lin(k + ".emb_layers.1", co, emb)
+        norm(k + ".out_layers.0", co)
+        conv(k + ".out_layers.3", co, co, 3)
+        if ci != co:
+            conv(k + ".skip_connection", co, ci, 1)
+
+    def st(k, c):
+        norm(k + ".norm", c)
+        conv(k + ".proj_in", c, c, 1)
+        t = k + ".transformer_blocks.0"
+        for n in ("norm1", "norm2", "norm3"):
+            norm(f"{t}.{n}", c)
+        for a, kv in (("attn1", c), ("attn2", ctx)):
+            lin(f"{t}.{a}.to_q", c, c, bias=False)
+            lin(f"{t}.{a}.to_k", c, kv, bias=False)
+            lin(f"{t}.{a}.to_v", c, kv, bias=False)
+            lin(f"{t}.{a}.to_out.0", c, c)
+        lin(f"{t}.ff.net.0.proj", 8 * c, c)
+        lin(f"{t}.ff.net.2", c, 4 * c)
+        conv(k + ".proj_out", c, c, 1)
+
+    lin("time_embed.0", emb, mc)
+    lin("time_embed.2", emb, emb)
+    conv("input_blocks.0.0", mc, 4, 3)
+    enc = [(1, 320, 320, True), (2, 320, 320, True), (3, None, 320, None), (4, 320, 640, True), (5, 640, 640, True),
+           (6, None, 640, None), (7, 640, 1280, True), (8, 1280, 1280, True), (9, None, 1280, None), (10, 1280, 1280, False),
+           (11, 1280, 1280, False)]
+    skip = [320]
+    for i, ci, co, attn in enc:
+        if ci is None:
+            conv(f"input_blocks.{i}.0.op", co, co, 3)
+        else:
+            res(f"input_blocks.{i}.0", ci, co)
+            if attn:
+                st(f"input_blocks.{i}.1", co)
+        skip.append(co)
+    res("middle_block.0", 1280, 1280)
+    st("middle_block.1", 1280)
+    res("middle_block.2", 1280, 1280)
+    if controlnet:
+        ch = [6, 16, 16, 32, 32, 96, 96, 256, 320]
+        for j in range(8):
+            conv(f"input_hint_block.{2 * j}", ch[j + 1], ch[j], 3)
+        for j, c in enumerate(skip):
+            conv(f"zero_convs.{j}.0", c, c, 1)
+        conv("middle_block_out.0", 1280, 1280, 1)
+        assert skip == [320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280]
+        return m
+    dec = [(0, 1280, False, False), (1, 1280, False, False), (2, 1280, False, True), (3, 1280, True, False),
+           (4, 1280, True, False), (5, 1280, True, True), (6, 640, True, False), (7, 640, True, False), (8, 640, True, True),
+           (9, 320, True, False), (10, 320, True, False), (11, 320, True, False)]
+    h, widths = 1280, []
+    for i, co, attn, up in dec:
+        ci = h + skip.pop()
+        widths.append(ci)
+        res(f"output_blocks.{i}.0", ci, co)
+        if attn:
+            st(f"output_blocks.{i}.1", co)
+        if up:
+            conv(f"output_blocks.{i}.{2 if attn else 1}.conv", co, co, 3)
+        h = co
+    assert widths == [2560, 2560, 2560, 2560, 2560, 1920, 1920, 1280, 960, 960, 640, 640]  # Appendix A, last line
+    norm("out.0", 320)
+    conv("out.2", 4, 320, 3)
+    return m
+
+
+def test_full_manifest_of_both_networks_matches_the_published_checkpoints():
+    """every key and every shape of the oracle's ControlNet and UNet state dicts == the published manifest (SURVEY.md
+    Appendix A): the structural pin of rows A7 / A8, complete rather than sampled"""
+    with torch.device("meta"):
+        cn, un = ControlNet(), ControlledUnetModel()
+    for net, want in ((cn, published_manifest(True)), (un, published_manifest(False))):
+        got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        assert sorted(got) == sorted(want), (sorted(set(got) ^ set(want))[:8])
+        assert got == want, [k for k in got if got[k] != want[k]][:8]
+    assert len(published_manifest(False)) == 686
+    assert sum(int(np.prod(v)) for v in published_manifest(False).values()) == 859_520_964
+    assert sum(int(np.prod(v)) for v in published_manifest(True).values()) == 361_279_552
+
+
 def test_K1_schedule():
     ac = linear_beta_alphas_cumprod().astype(np.float32)
     np.testing.assert_allclose(ac[[0, 1, 981, 999]], [0.999149978, 0.998296022, 0.005775500, 0.004660098],
