@@ -86,38 +86,53 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def run_oracle_cpu(n_ddim_steps, reps, size, warmup=1):
-    """the reference's CPU path = the fp32 oracle on all host threads; returns (seconds per UNet+ControlNet step, cores)"""
-    import torch
-    from oracle import MKDDIMSampler, OracleControlLDM, seeded_state_dict
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    h = size // 8
-    model = OracleControlLDM().eval()
-    seeded_state_dict(model, 0)
-    for p in model.parameters():
-        p.requires_grad_(False)
-    g = torch.Generator().manual_seed(1234)
-    cond = {"c_crossattn": [torch.randn(1, 77, 768, generator=g)], "c_concat": [torch.rand(1, 6, size, size, generator=g)]}
-    x = torch.randn(1, 4, h, h, generator=g)
-    s = MKDDIMSampler(model)
-    s.make_schedule(50, ddim_eta=0.0, verbose=False)
-    times = []
-    with torch.no_grad():
-        for r in range(warmup + reps):
+class OracleCPU:
+    """the reference's CPU path = the fp32 oracle on all host threads: ONE source/reference pair (BASELINE.json configs[0]),
+    DDIM-50 schedule; run(n) times the first n steps of the loop, run(50) the whole loop"""
+
+    def __init__(self, size, cfg=1.0, ddim_steps=50):
+        import torch
+        from oracle import MKDDIMSampler, OracleControlLDM, seeded_state_dict
+        self.torch = torch
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        h = size // 8
+        model = OracleControlLDM().eval()
+        seeded_state_dict(model, 0)
+        for p in model.parameters():
+            p.requires_grad_(False)
+        g = torch.Generator().manual_seed(1234)
+        self.cond = {"c_crossattn": [torch.randn(1, 77, 768, generator=g)], "c_concat": [torch.rand(1, 6, size, size, generator=g)]}
+        self.x = torch.randn(1, 4, h, h, generator=g)
+        self.guide = {}
+        if cfg != 1.0:
+            self.guide = dict(unconditional_guidance_scale=cfg, unconditional_conditioning={
+                "c_crossattn": [torch.randn(1, 77, 768, generator=g)], "c_concat": self.cond["c_concat"]})
+        self.s = MKDDIMSampler(model)
+        self.s.make_schedule(ddim_steps, ddim_eta=0.0, verbose=False)
+
+    def run(self, n):
+        with self.torch.no_grad():
             t0 = time.perf_counter()
-            s.reconstruct(x, cond, t_start=n_ddim_steps)  # the first n steps of the 50-step schedule
-            dt = time.perf_counter() - t0
-            if r >= warmup:
-                times.append(dt)
-    return times, cores
+            self.s.reconstruct(self.x, self.cond, t_start=n, **self.guide)  # the first n steps of the schedule
+            return time.perf_counter() - t0
 
 
 def workload_config(args, world):
     B, S, size = args.batch, args.ddim_steps, args.size
-    return {"workload": f"{size}x{size}, DDIM-{S} eta 0, ControlNet (6-ch hint) conditioning, no CFG, "
-                        f"batch {B} per GPU (global {B * world}), random-init (seeded non-zero) weights of "
-                        "base_diffusion_makeup.yaml = BASELINE.json configs[1]"
+    cfg, sweep, gb = getattr(args, "cfg", 1.0), getattr(args, "sweep", False), getattr(args, "global_batch", 0)
+    if sweep:
+        which = "BASELINE.json configs[4] (makeup interpolation sweep: 1 source x 8 references x 5 blend weights = 40 samples)"
+    elif cfg != 1.0:
+        which = "BASELINE.json configs[3]" + ("" if (size, B * world) == (512, 32) else " shape family (quoted: 512^2, global batch 32 on 8 GPUs)")
+    elif gb:
+        which = "BASELINE.json configs[2]" + ("" if (size, gb) == (256, 128) else " family (quoted: 256^2, global batch 128)")
+    else:
+        which = "BASELINE.json configs[1]" + ("" if (size, B) == (256, 16) else " family (quoted: 256^2, batch 16)")
+    return {"workload": f"{size}x{size}, DDIM-{S} eta 0, ControlNet (6-ch hint) conditioning, "
+                        + (f"classifier-free guidance scale {cfg:g} (doubled [uncond; cond] batch), " if cfg != 1.0 else "no CFG, ")
+                        + f"batch {B} per GPU (global {B * world}), random-init (seeded non-zero) weights of "
+                        f"base_diffusion_makeup.yaml = {which}"
                         + (" + first-stage (VAE) decode of the samples to images" if getattr(args, "decode", False) else "")
                         + (" + CLIP text encoding of the prompt tokens and uint8 image grid in every e2e pass" if getattr(args, "pipeline", False) else ""),
             "parallelism": f"batch-sharded x{world}, one all-gather of final latents"
@@ -128,21 +143,33 @@ def workload_config(args, world):
 
 
 def reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: ldm / cldm are not vendored)
+    on the box's host cores.  Each of the K timed steps is a bounded sample — the first 4 of the 50 DDIM steps of one
+    image pair — and ONE untimed-by-the-contract extra pass runs the whole 50-step loop (BASELINE.json configs[0] exactly
+    as written), reported next to it as `full_loop`."""
     if rank != 0:
         return
-    n = 4  # DDIM steps per bench step: a bounded sample of the 50-step workload, one image pair
-    times, cores = run_oracle_cpu(n, args.steps, args.size, warmup=max(1, min(args.warmup, 2)))
+    S = 20 if args.sweep else args.ddim_steps
+    o = OracleCPU(args.size, args.cfg, S)
+    n = 4  # DDIM steps per bench step
+    for _ in range(max(1, min(args.warmup, 2))):
+        o.run(1)
+    full_s = o.run(S)
+    times = [o.run(n) for _ in range(args.steps)]
     sec_per_model_step = statistics.mean(times) / n
-    ips = 1.0 / (50 * sec_per_model_step)
-    line = {"impl": "reference", "metric": "DDIM-50 makeup images/sec at 256^2", "value": ips, "unit": "images/s",
+    ips = 1.0 / (S * sec_per_model_step)
+    cores = o.cores
+    line = {"impl": "reference", "metric": f"DDIM-{S} makeup images/sec at {args.size}^2", "value": ips, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, int(os.environ.get("WORLD_SIZE", 1))),
+            "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, int(os.environ.get("WORLD_SIZE", 1))),
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} of 50 DDIM steps of ONE {args.size}^2 source/reference pair per bench step (fp32, "
-                                       f"all {cores} host threads), images/s = 1 / (50 x seconds per UNet+ControlNet step); "
+                             "sample": f"{n} of {S} DDIM steps of ONE {args.size}^2 source/reference pair per bench step (fp32, "
+                                       f"all {cores} host threads), images/s = 1 / ({S} x seconds per UNet+ControlNet step); "
                                        "images are independent, so throughput does not depend on the batch; "
-                                       "oracle = PyTorch restatement (the reference's ldm/cldm dependency is not vendored)"},
+                                       "oracle = PyTorch restatement (the reference's ldm/cldm dependency is not vendored)",
+                             "full_loop": {"value": 1.0 / full_s, "unit": "images/s", "seconds": full_s,
+                                           "what": f"the whole {S}-step loop of one pair, run once (BASELINE.json configs[0] as written)"}},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "ms_per_unet_controlnet_step": 1e3 * sec_per_model_step}
     print(json.dumps(line), flush=True)
@@ -158,6 +185,14 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="whole-job batch, split evenly over the GPUs (BASELINE.json configs[2]: 128 on 2 / 4 / 8 GPUs = 64 / 32 / 16 "
+                         "per GPU; configs[3]: 32); strong scaling.  Default 0: --batch images per GPU (weak scaling)")
+    ap.add_argument("--cfg", type=float, default=1.0,
+                    help="classifier-free guidance scale (configs[3]: 9): every step runs the doubled [uncond; cond] batch")
+    ap.add_argument("--sweep", action="store_true",
+                    help="configs[4]: makeup interpolation sweep, 1 source x 8 references x 5 blend weights = 40 samples, "
+                         "20-step DDIM, sharded over the GPUs")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-gather", action="store_true",
@@ -195,8 +230,19 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    B, S, size, h = args.batch, args.ddim_steps, args.size, args.size // 8
-    Bg = B * world
+    if args.sweep:
+        args.ddim_steps, args.global_batch = 20, 40
+    S, size, h = args.ddim_steps, args.size, args.size // 8
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} does not divide over {world} GPUs")
+        Bg, B = args.global_batch, args.global_batch // world
+        args.batch = B
+    else:
+        B = args.batch
+        Bg = B * world
+    cfg = args.cfg != 1.0
+    rows = 2 * B if cfg else B  # batch rows one UNet+ControlNet evaluation sees
 
     model = B200ControlLDM(dtype=torch.bfloat16, device=dev)
     model.load_state_dict(synthetic_state_dict(model, 0, dev))
@@ -214,26 +260,47 @@ def main():
         model.attach_cond_stage_model(clip)
         tok_host = torch.randint(0, 49406, (B, 77), generator=torch.Generator().manual_seed(7)).pin_memory()
         dtok = torch.empty(B, 77, dtype=torch.long, device=dev)
-    data = synthetic_batch(Bg, size, 768, seed=1234, device=dev)  # whole-job batch from one generator, then sliced
     lo, hi = shard_bounds(Bg, rank, world)
-    loc = {k: v[lo:hi].contiguous() for k, v in data.items()}
-    del data
-    hint_dev = torch.cat([loc["src"], loc["ref"]], 1)  # c_concat = cat(src, ref) (makeup_diffuse.py:56)
-    ctx_dev = loc["ctx"]
+    if args.sweep:
+        # 1 source x 8 references x 5 blend weights (README.md:25; BASELINE.json configs[4]) as one batch of 40 for the
+        # unchanged sampler, from one generator; every rank builds the whole (small) job and keeps its shard
+        from makeupdiffuse_b200.sweep import interpolation_cond
+        one = synthetic_batch(9, size, 768, seed=1234, device=dev)
+        cond_all = interpolation_cond(one["src"][:1], one["ref"][1:9], [0.0, 0.25, 0.5, 0.75, 1.0], one["ctx"][:1])
+        assert cond_all["c_concat"][0].shape[0] == Bg
+        loc = {"hint": cond_all["c_concat"][0][lo:hi].contiguous(), "ctx": cond_all["c_crossattn"][0][lo:hi].contiguous(),
+               "x_T": one["x_T"][:1].expand(B, -1, -1, -1).contiguous()}
+        del one, cond_all
+    else:
+        data = synthetic_batch(Bg, size, 768, seed=1234, device=dev)  # whole-job batch from one generator, then sliced
+        loc = {k: v[lo:hi].contiguous() for k, v in data.items()}
+        loc["hint"] = torch.cat([loc.pop("src"), loc.pop("ref")], 1)  # c_concat = cat(src, ref) (makeup_diffuse.py:56)
+        del data
+    hint_dev, ctx_dev = loc["hint"], loc["ctx"]
+    guide = {}
+    uctx_dev = None
+    if cfg:
+        # the unconditional branch: another context (the reference encodes the empty prompt), the SAME hint
+        # (uc_cat = c_cat, diffusion_makeup.py:399-402)
+        uctx_dev = torch.randn(B, 77, 768, device=dev, generator=torch.Generator(device=dev).manual_seed(4321 + rank))
+        guide = dict(unconditional_guidance_scale=args.cfg,
+                     unconditional_conditioning={"c_crossattn": [uctx_dev], "c_concat": [hint_dev]})
 
     def one_pass_device():
         # a new batch of images every pass: sample_sharded starts a loop, which drops the hoisted hint block + K/V
         cond = {"c_crossattn": [ctx_dev], "c_concat": [hint_dev]}
-        lat = sample_sharded(sampler, S, Bg, (4, h, h), cond, loc["x_T"], rank, world, fused_gather=args.fused_gather)
+        lat = sample_sharded(sampler, S, Bg, (4, h, h), cond, loc["x_T"], rank, world, fused_gather=args.fused_gather, **guide)
         if args.decode:  # each rank decodes its own images
             return model.decode_first_stage(lat[lo:hi])
         return lat
 
     # host-side (pinned) copies for the end-to-end arm
-    pin = {k: loc[k].cpu().pin_memory() for k in ("src", "ref", "ctx", "x_T")}
-    dsrc, dref, dctx, dxt = (torch.empty_like(loc[k]) for k in ("src", "ref", "ctx", "x_T"))
-    dhint = torch.empty_like(hint_dev)
-    out_host = torch.empty(B, 4, h, h, dtype=torch.float32).pin_memory()
+    pin = {k: loc[k].cpu().pin_memory() for k in ("hint", "ctx", "x_T")}
+    dhint, dctx, dxt = (torch.empty_like(loc[k]) for k in ("hint", "ctx", "x_T"))
+    if cfg:
+        pin["uctx"] = uctx_dev.cpu().pin_memory()
+        ductx = torch.empty_like(uctx_dev)
+    out_host = torch.empty(Bg, 4, h, h, dtype=torch.float32).pin_memory()
     h2d = sum(pin[k].numel() * 4 for k in pin)
     d2h = out_host.numel() * 4
     if args.pipeline:
@@ -246,8 +313,10 @@ def main():
         d2h += img_host.numel() * 4
 
     def one_pass_e2e():
-        dsrc.copy_(pin["src"], non_blocking=True)
-        dref.copy_(pin["ref"], non_blocking=True)
+        """the public API with HOST inputs: H2D of this rank's hint / context / x_T, the sharded sampling call
+        (makeupdiffuse_b200.dist.sample_sharded: B200DDIMSampler steps + the all-gather of the final latents; at one GPU it
+        is the B200DDIMSampler.sample loop), D2H of the gathered latents"""
+        dhint.copy_(pin["hint"], non_blocking=True)
         if args.pipeline:
             dtok.copy_(tok_host, non_blocking=True)
             ctx_e2e = model.get_learned_conditioning(dtok)  # token ids: encoded every pass (no prompt cache)
@@ -255,13 +324,20 @@ def main():
             dctx.copy_(pin["ctx"], non_blocking=True)
             ctx_e2e = dctx
         dxt.copy_(pin["x_T"], non_blocking=True)
-        torch.cat([dsrc, dref], 1, out=dhint)
         cond = {"c_crossattn": [ctx_e2e], "c_concat": [dhint]}
-        out, _ = sampler.sample(S, B, (4, h, h), cond, eta=0.0, x_T=dxt, verbose=False)  # the public API call
+        g2 = {}
+        if cfg:
+            ductx.copy_(pin["uctx"], non_blocking=True)
+            g2 = dict(unconditional_guidance_scale=args.cfg,
+                      unconditional_conditioning={"c_crossattn": [ductx], "c_concat": [dhint]})
+        if world == 1 and not args.fused_gather:
+            out, _ = sampler.sample(S, B, (4, h, h), cond, eta=0.0, x_T=dxt, verbose=False, **g2)  # the public API call
+        else:
+            out = sample_sharded(sampler, S, Bg, (4, h, h), cond, dxt, rank, world, fused_gather=args.fused_gather, **g2)
         if args.pipeline:
-            img_host.copy_(ops.image_grid_u8(model.decode_first_stage(out), nrow=8), non_blocking=True)
+            img_host.copy_(ops.image_grid_u8(model.decode_first_stage(out[lo:hi] if world > 1 else out), nrow=8), non_blocking=True)
         elif args.decode:
-            img_host.copy_(model.decode_first_stage(out), non_blocking=True)
+            img_host.copy_(model.decode_first_stage(out[lo:hi] if world > 1 else out), non_blocking=True)
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host
@@ -303,15 +379,20 @@ def main():
     roof, table = None, []
     if rank == 0:
         cond = {"c_crossattn": [ctx_dev], "c_concat": [hint_dev]}
-        t = torch.full((B,), 501, device=dev, dtype=torch.long)
+        px = loc["x_T"]
+        if cfg:  # the evaluation the guided loop runs: [uncond; cond] rows (cddim.py:18-39)
+            from makeupdiffuse_b200.sampler import _cat_uncond_first
+            cond = _cat_uncond_first(guide["unconditional_conditioning"], cond)
+            px = torch.cat([px] * 2)
+        t = torch.full((rows,), 501, device=dev, dtype=torch.long)
         was_concurrent, model.concurrent = model.concurrent, False  # one stream: a launch's events bracket it alone
-        model.apply_model(loc["x_T"], t, cond)
+        model.apply_model(px, t, cond)
         torch.cuda.synchronize()
         ops.PROFILE = []
         torch.cuda._sleep(int(0.25 * 1.9e9))  # let the host run ahead so launches queue back to back on the GPU
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        model.apply_model(loc["x_T"], t, cond)
+        model.apply_model(px, t, cond)
         s1.record()
         torch.cuda.synchronize()
         serial_ms = s0.elapsed_time(s1)
@@ -368,9 +449,14 @@ def main():
             if calls and fam in other:
                 other[fam]["ms_events"], other[fam]["ms"] = other[fam]["ms"], replay_ms(calls)
         achieved = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0
-        traffic, fam_path = None, os.path.join(ROOT, "profiles", "r01_ncu_families.json")
-        if os.path.exists(fam_path) and B == 16 and size == 256:  # the ncu pass was taken on this workload
-            traffic = json.load(open(fam_path))["families"].get("gemm_tcgen05_kernel", {}).get("dram_bytes_per_launch")
+        traffic = None
+        for fam_path in (os.path.join(ROOT, "profiles", f) for f in ("r02_ncu_families.json", "r01_ncu_families.json")):
+            if os.path.exists(fam_path) and rows == 16 and size == 256:  # the ncu pass was taken on this workload
+                fams = json.load(open(fam_path))["families"]
+                gem = [fams[k] for k in ("gemm_pair_kernel", "gemm_tcgen05_kernel") if k in fams and fams[k].get("dram_bytes_per_launch")]
+                if gem:  # average DRAM bytes per launch over the two tensor-core GEMM kernels
+                    traffic = round(sum(f["dram_bytes_per_launch"] * f["launches"] for f in gem) / sum(f["launches"] for f in gem))
+                    break
         att = other.get("attention")
         att_flops = sum(r["flops"] for r in attn_prof)
         others = {}
@@ -385,14 +471,15 @@ def main():
                 others[k] = {"bound": "hbm", "achieved": gbs, "peak": pk["gbs"], "unit": "GB/s", "frac": gbs / pk["gbs"],
                              "launches_per_eval": other[k]["n"], "kernel_ms_per_eval": other[k]["ms"],
                              "note": "1 read + 1 write per element; inputs were just written by the producer (L2-resident)"}
-        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (implicit-GEMM conv / linear)", "achieved": achieved,
+        roof = {"bound": "tensor", "kernel": "gemm_pair_kernel + gemm_tcgen05_kernel (tcgen05 implicit-GEMM conv / linear: CTA-pair and "
+                                             "single-CTA forms)", "achieved": achieved,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
                 "peak_source": f"{pk['src']} sustained bf16 ({pk['tflops_burst']} burst)", "launches_per_eval": len(tc),
                 "kernel_ms_per_eval": tc_ms, "kernel_ms_per_eval_event_pairs": tc_ms_inplace,
                 "share_of_serial_eval_event_pairs": tc_ms_inplace / serial_ms if serial_ms else None,
                 "timing": "the eval's tcgen05 launches replayed back to back as one CUDA graph, 2 events, mean of 5",
                 "generic_conv_ms_per_eval": gen_ms,
-                "whole_step_frac": (F_STEP.get(size, 0) * B / (ms_model_step / 1e3) / 1e12) / pk["tflops"],
+                "whole_step_frac": (F_STEP.get(size, 0) * rows / (ms_model_step / 1e3) / 1e12) / pk["tflops"],
                 "others": others}
         for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
             table.append({"path": "tcgen05" if key[0] == _lib.PATH_TCGEN05 else "generic", "M": key[1], "N": key[2],
@@ -408,17 +495,18 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of configs[0] ----------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = 8
-        times, cores = run_oracle_cpu(n, 1, size, warmup=1)
-        sps = times[0] / n
-        cpu = {"value": 1.0 / (50 * sps), "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{n} of 50 DDIM steps, one {size}^2 pair, fp32 oracle on {cores} host threads "
-                         f"({1e3 * sps:.0f} ms per UNet+ControlNet step), extrapolated to 50 steps"}
+        o = OracleCPU(size, args.cfg, S)
+        o.run(1)
+        full_s = o.run(S)  # BASELINE.json configs[0] as written: the whole loop of one pair, not an extrapolation
+        cpu = {"value": 1.0 / full_s, "unit": "images/s", "cores": o.cores, "kind": "port",
+               "sample": f"the full {S}-step DDIM loop of ONE {size}^2 source/reference pair (BASELINE.json configs[0]), fp32 oracle on "
+                         f"{o.cores} host threads, run once after a one-step warm-up: {full_s:.1f} s = "
+                         f"{1e3 * full_s / S:.0f} ms per UNet+ControlNet step"}
 
     if rank == 0:
-        line = {"metric": "DDIM-50 makeup images/sec at 256^2", "value": ips, "unit": "images/s", "n_gpus": world,
+        line = {"metric": f"DDIM-{S} makeup images/sec at {size}^2", "value": ips, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(args, world),
                 "ms_per_unet_controlnet_step": ms_model_step,
                 "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

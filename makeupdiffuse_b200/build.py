@@ -19,6 +19,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          *([f"-DMKD_EPI_PIPE={os.environ['MKD_EPI_PIPE']}"] if os.environ.get("MKD_EPI_PIPE") else []),  # A/B builds of the GEMM epilogue
          *([f"-DMKD_MAX_STAGES={os.environ['MKD_MAX_STAGES']}"] if os.environ.get("MKD_MAX_STAGES") else []),  # pipeline-depth experiments
          *([f"-DMKD_GEGLU_PIPE={os.environ['MKD_GEGLU_PIPE']}"] if os.environ.get("MKD_GEGLU_PIPE") else []),  # A/B: GEGLU epilogue
+         *os.environ.get("MKD_EXTRA_NVCC_FLAGS", "").split(),  # ablation builds (tools/), never set for the shipped library
          "-Xptxas", "-v"]
 
 

@@ -306,6 +306,306 @@ __global__ void __launch_bounds__(ACfg<DN, NWG_, KST_, VST_>::THREADS, ACfg<DN, 
   }
 }
 
+// ---- head dims <= 64: two independent 64-key half pipelines per 128 queries, two CTAs per SM -----------------------
+// The keys of a row are split between two warpgroups that share nothing but Q: warpgroup g takes the 64-key halves
+// g, g + 2, ... with its own issuer warp (TMA loads of its K / V halves, its S and PV MMAs), its own S buffer (64 TMEM
+// columns), P buffer (16 KB), K / V rings (2 x 8 KB each), O accumulator and running (max, sum).  The two partial
+// results of a row are merged once after the key loop:
+//   m = max(m0, m1), a_g = 2^((m_g - m) scale), O = (a0 O0 + a1 O1) / (a0 l0 + a1 l1).
+// 16 softmax warps per SM (4 per scheduler) at <= 96 registers (a thread holds 64 scores, not 128); issuers are whole
+// warps walking warp-uniform loops with one elected lane issuing (an `if (lane == 0)` region costs ~15 instructions of
+// uniformisation loop per MMA), descriptors built once and advanced by constants.
+// Measured (profiles/r02_attention.txt): 446 us on 8 x 8 heads x 4096 tokens (385 TFLOP/s; whole-tile kernel above: 452),
+// 70.8 us on 16 x 8 x 1024 (was 75).  The experiments that led here say no single pipe bounds this loop: timing-only builds
+// without the exp2, without the P stores, without the MMAs, without the K / V loads each moved the time by < 3 % (all of
+// them together: -32 %); in this form XU runs at 63 %, L2 tag lookups at 47 % (71 % on the busiest slice: 80-byte rows at
+// head dim 40), issue slots at 50 %, commit -> barrier latency is ~110 clk, one unobstructed iteration of a warpgroup is
+// 1 630 clk against 3 100-3 600 with four of them on an SM.
+// Barriers of stream g, u-th half: s_full (commit), s_free (4 warps: S is in registers), p_full (4 warps), pv_done
+// (commit: P may be rewritten, O holds every half up to u), k_full / v_full[2].
+constexpr int HKV = 64;
+constexpr int HB = HKV * 128;  // bytes of one [64 keys][64 ch] half tile
+
+template <int DN>
+__global__ void __launch_bounds__(320, 2)
+    attn_split_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                      const __grid_constant__ CUtensorMap vmap, bf16* __restrict__ o, int Nq, int Nkv, int d, int ldo, float sl2) {
+  static_assert(DN % 16 == 0 && DN <= 64, "one 64-channel chunk per head");
+  constexpr int TCOLS = 256;          // S_g at column 64 g, O_g at column 128 + 64 g
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  unsigned char* Qs = smem;                 // [128 queries][64 ch]
+  unsigned char* Ks = Qs + CH;              // [2 streams][2 slots][64 keys][64 ch]
+  unsigned char* Vs = Ks + 4 * HB;          // [2 streams][2 slots][64 keys][64 ch]
+  unsigned char* Ps = Vs + 4 * HB;          // [2 streams][128 queries][64 keys]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(Ps + 2 * CH);
+  uint64_t* s_full = q_full + 1;   // [2]
+  uint64_t* s_free = s_full + 2;   // [2]
+  uint64_t* p_full = s_free + 2;   // [2]
+  uint64_t* pv_done = p_full + 2;  // [2]
+  uint64_t* k_full = pv_done + 2;  // [2 streams][2 slots]
+  uint64_t* v_full = k_full + 4;   // [2 streams][2 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_full + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_ISSUE = 8;  // warps 8, 9: issuer of stream 0 / 1
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int H = (Nkv + HKV - 1) / HKV;    // 64-key halves; stream g owns halves g, g + 2, ...
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&qmap);
+    prefetch_tensormap(&kmap);
+    prefetch_tensormap(&vmap);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full + i, 1);
+      mbar_init(s_free + i, 4);
+      mbar_init(p_full + i, 4);
+      mbar_init(pv_done + i, 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(v_full + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_ISSUE) tmem_alloc<TCOLS>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  if (warp >= W_ISSUE) {
+    // ===== issuer of stream g: the whole warp walks the loop (warp-uniform waits), one elected lane issues; descriptors are
+    // built once and advanced by constants, the k loops are unrolled at compile time =====
+    const int g = warp - W_ISSUE;
+    const int n = (H - g + 1) >> 1;  // halves of this stream
+    constexpr uint32_t idesc_s = idesc_bf16(BQ, HKV, false);
+    constexpr uint32_t idesc_o = idesc_bf16(BQ, DN, true);
+    constexpr int KS = DN / 16;  // 16-channel steps of Q K^T (channels beyond d are zero-filled by the TMA unit)
+    unsigned char* Kg = Ks + g * 2 * HB;
+    unsigned char* Vg = Vs + g * 2 * HB;
+    const uint64_t qdesc = smem_desc_sw128(smem_u32(Qs));
+    const uint64_t kdesc0 = smem_desc_sw128(smem_u32(Kg));
+    const uint64_t vdesc0 = smem_desc_sw128(smem_u32(Vg), CH);
+    const uint64_t pdesc = smem_desc_sw128(smem_u32(Ps + g * CH));
+    const uint32_t dS = tmem_base + (uint32_t)(g * HKV), dO = tmem_base + (uint32_t)(2 * HKV + g * 64);
+    auto load_k = [&](int u) {  // K half g + 2 u into slot u & 1
+      if (elect_one()) {
+        mbar_expect_tx(k_full + 2 * g + (u & 1), HB);
+        tma_load_4d(&kmap, k_full + 2 * g + (u & 1), Kg + (u & 1) * HB, 0, h, (g + 2 * u) * HKV, b);
+      }
+      __syncwarp();
+    };
+    auto load_v = [&](int u) {
+      if (elect_one()) {
+        mbar_expect_tx(v_full + 2 * g + (u & 1), HB);
+        tma_load_4d(&vmap, v_full + 2 * g + (u & 1), Vg + (u & 1) * HB, 0, h, (g + 2 * u) * HKV, b);
+      }
+      __syncwarp();
+    };
+    auto issue_s = [&](int u) {  // S(u) = Q K(u)^T from K slot u & 1
+      mbar_wait(k_full + 2 * g + (u & 1), (u >> 1) & 1);
+      fence_after();
+      if (elect_one()) {
+        const uint64_t kd = kdesc0 + (uint64_t)((u & 1) * (HB >> 4));
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_bf16_ss(dS, qdesc + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_s, ks > 0);
+        commit(s_full + g);
+      }
+      __syncwarp();
+    };
+    if (n > 0) {
+      if (g == 0 && elect_one()) {
+        mbar_expect_tx(q_full, CH);
+        tma_load_4d(&qmap, q_full, Qs, 0, h, q0, b);
+      }
+      __syncwarp();
+      load_k(0);
+      load_v(0);
+      if (n > 1) {
+        load_k(1);
+        load_v(1);
+      }
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      // Slot reuse without a blocking wait on this stream's own commits: s_free(u) says S(u) is in registers, so K slot
+      // u & 1 is free a whole iteration before S(u + 2) needs it; p_full(u) is sent only after the warpgroup has seen
+      // pv_done(u - 1), so V slot (u + 1) & 1 is free one iteration before PV(u + 1) needs it.
+      for (int u = 0; u < n; ++u) {
+        const int s = u & 1;
+        if (u + 1 < n) {
+          mbar_wait(s_free + g, u & 1);
+          if (u + 2 < n) load_k(u + 2);
+          issue_s(u + 1);
+        }
+        mbar_wait(v_full + 2 * g + s, (u >> 1) & 1);
+        mbar_wait(p_full + g, u & 1);    // P(u) is in smem and any rescale of O is done
+        fence_after();
+        if (u >= 1 && u + 1 < n) load_v(u + 1);
+        if (elect_one()) {
+          const uint64_t vd = vdesc0 + (uint64_t)(s * (HB >> 4));
+          const int kvalid = Nkv - (g + 2 * u) * HKV;
+          if (kvalid >= HKV) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) mma_bf16_ss(dO, pdesc + (uint64_t)(kk * 2), vd + (uint64_t)(kk * 128), idesc_o, u > 0 || kk > 0);
+          } else {  // keys beyond Nkv carry P = 0: skip whole 16-key steps
+            const int steps = (kvalid + 15) >> 4;
+            for (int kk = 0; kk < steps; ++kk) mma_bf16_ss(dO, pdesc + (uint64_t)(kk * 2), vd + (uint64_t)(kk * 128), idesc_o, u > 0 || kk > 0);
+          }
+          commit(pv_done + g);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== softmax warpgroups: thread = query row, warpgroup g = stream g =====
+    const int g = warp >> 2, row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + (uint32_t)(g * HKV);
+    const uint32_t tO = tmem_base + lane_base + (uint32_t)(2 * HKV + g * 64);
+    const uint32_t pw = smem_u32(Ps + g * CH + row * 128) + (((uint32_t)row & 7u) << 4);  // 16-byte unit j of the row: pw ^ (j << 4)
+    float m_used = -INFINITY, l = 0.f;
+    int u = 0;
+    for (int hh = g; hh < H; hh += 2, ++u) {
+      mbar_wait(s_full + g, u & 1);
+      fence_after();
+      uint32_t v[2][32];
+      tmem_ld32_nowait(tS, v[0]);
+      tmem_ld32_nowait(tS + 32, v[1]);
+      tmem_ld_wait();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free + g);  // S_g may be overwritten by Q K(u + 1)^T
+      const int kvalid = Nkv - hh * HKV;       // < 64 only in the last half
+      if (kvalid < HKV) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c][i] = (c * 32 + i >= kvalid) ? 0xff800000u : v[c][i];
+        }
+      }
+      float mx8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx8[i] = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) mx8[(i >> 1) & 7] = max3(mx8[(i >> 1) & 7], __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
+      }
+      const float mx = fmaxf(max3(mx8[0], mx8[1], mx8[2]), max3(mx8[3], mx8[4], max3(mx8[5], mx8[6], mx8[7])));
+      // The round trip p_full -> issuer -> PV -> commit -> pv_done is ~1 500 clk: waiting for pv_done(u - 1) HERE (before the
+      // exp2 phase) left the warpgroup idle for a third of every iteration.  Only the P stores and the (rare) rescale of O
+      // depend on it, so the exp2 phase runs first, into registers (64 scores become 32 packed bf16 pairs).
+      if (__any_sync(0xffffffffu, (mx - m_used) * sl2 > 8.0f)) {  // lazy rescale (warp-uniform: TMEM accesses are collective)
+        const float m_new = fmaxf(m_used, mx);
+        const float corr = ex2((m_used - m_new) * sl2);
+        l *= corr;
+        m_used = m_new;
+        if (u > 0) {
+          mbar_wait(pv_done + g, (u - 1) & 1);  // O_g holds every half up to u - 1
+          fence_after();
+#pragma unroll
+          for (int gg = 0; gg < DN / 16; ++gg) {
+            uint32_t r[16];
+            tmem_ld16_nowait(tO + gg * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+            tmem_st16(tO + gg * 16, r);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mb = m_used * sl2;
+      const uint64_t sl2x2 = pack2(sl2, sl2), nmbx2 = pack2(-mb, -mb);
+      uint64_t sum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
+      uint32_t pk[2][16];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a0, a1;
+          unpack2(ffma2(pack2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sl2x2, nmbx2), a0, a1);
+          const float p0 = ex2(a0), p1 = ex2(a1);
+          sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], pack2(p0, p1));
+          __nv_bfloat162 hh2 = __floats2bfloat162_rn(p0, p1);
+          pk[c][i >> 1] = *reinterpret_cast<uint32_t*>(&hh2);
+        }
+      }
+      if (u > 0) {  // this stream's previous PV has retired: P_g may be rewritten
+        mbar_wait(pv_done + g, (u - 1) & 1);
+        fence_after();
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(pw ^ ((uint32_t)(c * 4 + jj) << 4)), "r"(pk[c][4 * jj]),
+                       "r"(pk[c][4 * jj + 1]), "r"(pk[c][4 * jj + 2]), "r"(pk[c][4 * jj + 3])
+                       : "memory");
+      }
+      {
+        float s0, s1, s2, s3;
+        unpack2(fadd2(sum2[0], sum2[1]), s0, s1);
+        unpack2(fadd2(sum2[2], sum2[3]), s2, s3);
+        l += (s0 + s1) + (s2 + s3);
+      }
+      fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + g);
+    }
+    // merge of the two streams' partial results.  The (max, sum) pairs travel through the stream's own P buffer, dead
+    // after its last PV; with a single half stream 1 has no keys (O_1 was never written)
+    const bool two = H > 1;
+    float2* ml = reinterpret_cast<float2*>(Ps);  // [g * CH / 8 + row]
+    if (u > 0) {
+      mbar_wait(pv_done + g, (u - 1) & 1);  // this stream's last PV
+      ml[g * (CH / 8) + row] = make_float2(m_used, l);
+    }
+    fence_before();
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");  // both warpgroups: every PV has retired, (max, sum) pairs are published
+    fence_after();
+    const float2 mo = (g == 0 && !two) ? make_float2(-INFINITY, 0.f) : ml[(g ^ 1) * (CH / 8) + row];
+    const float m = fmaxf(m_used, mo.x);
+    const float a_own = ex2((m_used - m) * sl2), a_oth = ex2((mo.x - m) * sl2);  // (-inf - m = -inf -> 0: a stream without keys)
+    const float inv = 1.0f / (l * a_own + mo.y * a_oth);
+    const float c_own = a_own * inv, c_oth = a_oth * inv;
+    const uint32_t tO_oth = tmem_base + lane_base + (uint32_t)(2 * HKV + (g ^ 1) * 64);
+    const int q = q0 + row;
+    bf16* dst = o + ((int64_t)b * Nq + q) * ldo + h * d;
+#pragma unroll
+    for (int gg = 0; gg < DN / 16; ++gg) {
+      if ((gg & 1) != g) continue;  // the two warpgroups share the store work by 16-channel groups
+      uint32_t r0[16], r1[16];
+      if (g == 0 || two) tmem_ld16_nowait(tO + gg * 16, r0);  // warp-collective: every lane loads, only real rows / channels store
+      if (g == 1 || two) tmem_ld16_nowait(tO_oth + gg * 16, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        if (q < Nq && gg * 16 + hlf * 8 < d) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float own = (g == 0 || two) ? __uint_as_float(r0[hlf * 8 + i]) * c_own : 0.f;
+            const float oth = (g == 1 || two) ? __uint_as_float(r1[hlf * 8 + i]) * c_oth : 0.f;
+            f[i] = own + oth;
+          }
+          store8(dst + gg * 16 + hlf * 8, f);
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == W_ISSUE) {
+    fence_after();
+    tmem_dealloc<TCOLS>(tmem_base);
+  }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -322,10 +622,10 @@ EncodeFn get_encode() {
 }
 
 // (head dim, heads, tokens, batch) view of a [batch * tokens, ld] matrix whose head h occupies columns [h*d, (h+1)*d)
-int head_map(CUtensorMap* map, const bf16* base, int d, int heads, int ntok, int B, int ld) {
+int head_map(CUtensorMap* map, const bf16* base, int d, int heads, int ntok, int B, int ld, int box_rows = 128) {
   cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)ntok, (cuuint64_t)B};
   cuuint64_t str[3] = {(cuuint64_t)d * 2, (cuuint64_t)ld * 2, (cuuint64_t)ntok * ld * 2};
-  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
   return tma_encode_bf16(map, base, 4, dims, str, box);
 }
 
@@ -347,6 +647,28 @@ int launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int head
   dim3 grid((Nq + BQ * C::NWG - 1) / (BQ * C::NWG), heads, B);
   MKD_LAUNCH_OK(launch_pdl(attn_tcgen05_kernel<DN, NWG, KST, VST>, grid, dim3(C::THREADS), C::SMEM, st, qm, km, vm, o, Nq, Nkv, d, ldo,
                            scale * 1.4426950408889634f));
+  MKD_CHECK_LAUNCH();
+  return MKD_OK;
+}
+
+template <int DN>
+int launch_half(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d, int ldq, int ldk,
+                int ldv, int ldo, float scale, cudaStream_t st) {
+  constexpr size_t SMEM = (size_t)7 * CH + 17 * 8 + 16;  // Q, 2 x 2 K and V half tiles, 2 P buffers + barriers + TMEM slot
+  static_assert(2 * SMEM <= 227 * 1024, "two CTAs per SM");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_split_kernel<DN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "attention_tcgen05: cudaFuncSetAttribute(%zu): %s", SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  CUtensorMap qm, km, vm;
+  int rc;
+  if ((rc = head_map(&qm, q, d, heads, Nq, B, ldq))) return rc;
+  if ((rc = head_map(&km, k, d, heads, Nkv, B, ldk, HKV))) return rc;
+  if ((rc = head_map(&vm, v, d, heads, Nkv, B, ldv, HKV))) return rc;
+  dim3 grid((Nq + BQ - 1) / BQ, heads, B);
+  MKD_LAUNCH_OK(launch_pdl(attn_split_kernel<DN>, grid, dim3(320), SMEM, st, qm, km, vm, o, Nq, Nkv, d, ldo, scale * 1.4426950408889634f));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
@@ -373,16 +695,16 @@ bool attention_tcgen05_supported(int d, int ldq, int ldk, int ldv) {
 int attention_tcgen05(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int heads, int Nq, int Nkv, int d,
                       int ldq, int ldk, int ldv, int ldo, float scale, cudaStream_t st) {
   const int dn = (d + 15) / 16 * 16;
-  static const int pair = debug_switch("MKD_ATTN_PAIR", 0);  // 1: two warpgroups per CTA also for head dims <= 64 (A/B measurements)
+  static const int whole = debug_switch("MKD_ATTN_WHOLE", 0);  // 1: whole-tile kernel also for head dims <= 64 (A/B measurements)
 #define MKD_ATTN_ARGS q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st
-  if (dn <= 64 && !pair) {
-    if (dn <= 16) return launch<16, 1, 2, 2>(MKD_ATTN_ARGS);
-    if (dn <= 32) return launch<32, 1, 2, 2>(MKD_ATTN_ARGS);
-    if (dn <= 48) return launch<48, 1, 2, 2>(MKD_ATTN_ARGS);
-    return launch<64, 1, 2, 2>(MKD_ATTN_ARGS);
+  if (dn <= 64 && !whole) {  // half-tile kernel: two softmax warpgroups per 128 queries, two CTAs per SM
+    if (dn <= 16) return launch_half<16>(MKD_ATTN_ARGS);
+    if (dn <= 32) return launch_half<32>(MKD_ATTN_ARGS);
+    if (dn <= 48) return launch_half<48>(MKD_ATTN_ARGS);
+    return launch_half<64>(MKD_ATTN_ARGS);
   }
-  if (dn <= 48) return launch<48, 2, 2, 2>(MKD_ATTN_ARGS);
-  if (dn <= 64) return launch<64, 2, 2, 2>(MKD_ATTN_ARGS);
+  if (dn <= 48) return launch<48, 1, 2, 2>(MKD_ATTN_ARGS);
+  if (dn <= 64) return launch<64, 1, 2, 2>(MKD_ATTN_ARGS);
   if (dn <= 80) return launch<80, 2, 2, 1>(MKD_ATTN_ARGS);
   if (dn <= 128) return launch<128, 2, 2, 1>(MKD_ATTN_ARGS);
   return launch<160, 1, 2, 1>(MKD_ATTN_ARGS);

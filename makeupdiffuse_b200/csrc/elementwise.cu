@@ -11,10 +11,12 @@
 namespace mkd {
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
+  char tmp[sizeof(g_err)];  // an argument may be mkd_last_error() itself (a decline reason quoted by the next message)
   va_list ap;
   va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  vsnprintf(tmp, sizeof(tmp), fmt, ap);
   va_end(ap);
+  memcpy(g_err, tmp, sizeof(g_err));
 }
 bool pdl_enabled() {
   // on: 6.97 -> 6.74 ms per UNet+ControlNet step (round 2; it measured slightly negative in round 1, before the launch

@@ -985,7 +985,7 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
   {
     const uint64_t lim = 1ull << 32, units_max = (uint64_t)m_pairs * (d->K / 160 + 1) * 16 + 2 * num_sms();
     if (units_max * (uint64_t)(d->K / 160 + 1) >= lim || units_max * (uint64_t)m_pairs >= lim ||
-        (uint64_t)(pl.M + BM) * (uint64_t)(pl.P * pl.Q) >= lim || (uint64_t)kblocks * (uint64_t)(d->C / BK) >= lim ||
+        (d->emb && (uint64_t)(pl.M + BM) * (uint64_t)(pl.P * pl.Q) >= lim) ||  // (rows / pixels-per-image: embedding rows only) (uint64_t)kblocks * (uint64_t)(d->C / BK) >= lim ||
         (uint64_t)(2 * m_pairs) * (uint64_t)(pl.tiles_w * pl.tiles_h) >= lim)
       return false;
   }
@@ -1099,7 +1099,7 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   p.d_S = make_fastdiv(p.S);
   p.d_tiles_w = make_fastdiv(p.tiles_w);
   p.d_tiles_h = make_fastdiv(p.tiles_h);
-  p.d_ppi = make_fastdiv(pl.P * pl.Q);
+  p.d_ppi = make_fastdiv(d->emb ? pl.P * pl.Q : 1);
 
   p.M = pl.M;
   p.pix_per_img = pl.P * pl.Q;

@@ -36,6 +36,21 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand fetch)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+// one lane of a converged warp, chosen by the hardware: the compiler sees a warp-uniform predicate, so tcgen05 / TMA
+// instructions inside take their operands from uniform registers directly (an `if (lane == 0)` region makes it wrap
+// every such instruction in a uniformisation loop: ~15 extra instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

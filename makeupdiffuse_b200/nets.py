@@ -274,8 +274,19 @@ class _Net(nn.Module):
     # ---- building blocks ---------------------------------------------------------------------------------------
     def _conv(self, x, wkey, y, N, H, W, R=1, **kw):
         """y: activation-dtype output view or None; kw may carry y32= (fp32 copy), residual=, emb=, act= ..."""
+        if kw.get("stride", 1) == 2 or kw.get("upsample"):
+            # the library materialises the im2col matrix (stride 2) / the x2-upsampled input in the workspace
+            rows = N * (H // 2) * (W // 2) * 9 if kw.get("stride", 1) == 2 else N * 4 * H * W
+            self._grow_ws(rows * x.shape[1] * 2 + _SPLITK_WS_BYTES)
         ops.conv2d(x, self.w[wkey + ".w"], y, N=N, H=H, W=W, R=R, S=R, pad=R // 2 if "pad" not in kw else kw.pop("pad"),
                    bias=self.w.get(wkey + ".b"), workspace=self._ws, **kw)
+
+    def _grow_ws(self, need):
+        """large batches outgrow the default workspace; a replaced buffer stays alive (captured graphs of other shapes
+        still point into it)"""
+        if need > self._ws.numel() * 4:
+            self._ws_retired = getattr(self, "_ws_retired", []) + [self._ws]
+            self._ws = torch.empty(-(-need // 4), dtype=torch.float32, device=self._device)
 
     def _linear(self, x, wkey, y, **kw):
         ops.conv2d(x, self.w[wkey + ".w"], y, N=1, H=1, W=x.shape[0], bias=self.w.get(wkey + ".b"), workspace=self._ws, **kw)

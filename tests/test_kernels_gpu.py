@@ -308,6 +308,8 @@ PAIR_CASES = [
     dict(N=16, H=32, W=32, C=960, K=320, R=3, residual=True, res32=True, y32="both"),   # ... deep K, fp32 in / out
     dict(N=1, H=1, W=512, C=320, K=2560, R=1, act=L.ACT_GEGLU, gb=128),      # fused GEGLU, [128 value | 128 gate] blocks
     dict(N=1, H=1, W=300, C=640, K=5120, R=1, act=L.ACT_GEGLU, gb=128),      # ... ragged M
+    dict(N=1, H=1, W=66000, C=64, K=256, R=1, act=L.ACT_GEGLU, gb=128),      # more than 2^16 rows (batch 64+ at 32x32)
+    dict(N=1, H=1, W=16384, C=1280, K=320, R=1, residual=True, res32=True),  # ff2 at batch 16: 3 panel slots, two sub-tiles (slot-order race)
     dict(N=16, H=8, W=8, C=1280, K=1280, R=3, emb=True, y32="only", workspace=True),    # split-K (8x8 level)
     dict(N=16, H=4, W=4, C=2560, K=1280, R=3, emb=True, workspace=True),     # split-K (4x4 level, K = 23040)
     dict(N=16, H=8, W=8, C=5120, K=1280, R=1, residual=True, res32=True, workspace=True),  # split-K ff2
@@ -446,7 +448,10 @@ def test_conv_stats_rejected_on_generic_path():
                                                (2, 8, 16, 16, 160), (2, 8, 1024, 77, 40), (2, 8, 64, 77, 160),
                                                (1, 4, 100, 77, 16), (1, 4, 64, 64, 32), (2, 2, 200, 130, 64),
                                                (1, 8, 4096, 4096, 40), (2, 8, 300, 300, 8), (1, 3, 513, 257, 96),
-                                               (1, 2, 129, 128, 128), (2, 1, 256, 256, 512)])  # last: the VAE decoder's single 512-wide head (SIMT kernel)
+                                               (1, 2, 129, 128, 128), (2, 1, 256, 256, 512),  # last: the VAE decoder's single 512-wide head (SIMT kernel)
+                                               # split-KV kernel (head dims <= 64): one half only, odd halves, ragged halves
+                                               (2, 4, 128, 40, 40), (2, 4, 130, 64, 48), (1, 8, 256, 192, 40), (1, 2, 70, 321, 64),
+                                               (1, 8, 1024, 1000, 40)])
 def test_attention(dt, B, heads, Nq, Nkv, d):
     C = heads * d
     self_attn = Nq == Nkv

@@ -20,7 +20,9 @@ ORDER = [0, 14, 1, 15, 2, 3, 4, 5, 12, 13, 6, 7, 10, 8, 9, 11]
 SHAPES = {"sq320_plain": (16, 32, 32, 320, 320, 1, "plain"), "sq320_res32": (16, 32, 32, 320, 320, 1, "res32"),
           "qkv_320": (16, 32, 32, 320, 960, 1, "plain"), "conv320": (16, 32, 32, 320, 320, 3, "emb32"),
           "sq1280_plain": (16, 8, 8, 1280, 1280, 1, "plain"), "conv1280": (16, 8, 8, 1280, 1280, 3, "emb32"),
-          "ff1_320": (16, 32, 32, 320, 2560, 1, "geglu")}
+          "ff1_320": (16, 32, 32, 320, 2560, 1, "geglu"),
+          "conv1280_4x4": (16, 4, 4, 1280, 1280, 3, "emb32"), "sq1280_m256": (16, 4, 4, 1280, 1280, 1, "plain"),
+          "conv2560_4x4": (16, 4, 4, 2560, 1280, 3, "emb32"), "ff2_1280": (16, 8, 8, 5120, 1280, 1, "res32")}
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 ws = torch.empty(96 << 20, dtype=torch.uint8, device=DEV)
 for name, (N, H, W, C, K, R, epi) in SHAPES.items():
