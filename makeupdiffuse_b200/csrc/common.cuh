@@ -123,16 +123,23 @@ bool pdl_enabled();
 // every layer (2.4 GB per step against 126 MB of L2), the prefetch touches no SM state, and it is harmless whatever the
 // previous kernel is still writing (L2 is the coherence point).  So the weight stream starts while the previous kernel
 // drains instead of after the first full-barrier wait of the main loop.  Capped: activations should stay L2-resident.
-__device__ __forceinline__ void l2_prefetch_share(const void* base, unsigned long long bytes, int lane) {
-  constexpr unsigned long long CAP = 48ull << 20, CHUNK = 8192;
-  if (bytes > CAP) bytes = CAP;
-  const unsigned long long per = ((bytes + gridDim.x - 1) / gridDim.x + CHUNK - 1) / CHUNK * CHUNK;
-  const unsigned long long lo = (unsigned long long)blockIdx.x * per;
-  const unsigned long long hi = lo + per < bytes ? lo + per : bytes;
-  for (unsigned long long o = lo + (unsigned long long)lane * CHUNK; o < hi; o += 32 * CHUNK) {
-    const unsigned n = (unsigned)(hi - o < CHUNK ? hi - o : CHUNK);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(reinterpret_cast<const char*>(base) + o), "r"(n) : "memory");
+// `share` = bytes per CTA, computed on the host (l2_prefetch_share_bytes): the 64-bit divisions this took on the device
+// (~0.5 us in front of the prologue's first cluster barrier, where warp 3's arrival is waited for) are gone.
+__device__ __forceinline__ void l2_prefetch_share(const void* base, unsigned long long bytes, unsigned share, int lane) {
+  constexpr unsigned CHUNK = 8192;
+  const unsigned long long lo = (unsigned long long)blockIdx.x * share;
+  if (lo >= bytes) return;
+  const unsigned span = (unsigned)(bytes - lo < share ? bytes - lo : share);
+  for (unsigned o = (unsigned)lane * CHUNK; o < span; o += 32 * CHUNK) {
+    const unsigned n = span - o < CHUNK ? span - o : CHUNK;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(reinterpret_cast<const char*>(base) + lo + o), "r"(n) : "memory");
   }
+}
+// host: caps the prefetched bytes (activations should stay L2-resident) and splits them over the grid in whole 8 KB chunks
+inline void l2_prefetch_plan(unsigned long long w_bytes, int grid, unsigned long long& bytes, unsigned& share) {
+  constexpr unsigned long long CAP = 48ull << 20, CHUNK = 8192;
+  bytes = w_bytes > CAP ? CAP : w_bytes;
+  share = (unsigned)(((bytes + grid - 1) / grid + CHUNK - 1) / CHUNK * CHUNK);
 }
 // Experiment switches (A/B runs, timing experiments) exist only in trace builds (-DMKD_ENABLE_TRACE, i.e.
 // `MKD_TRACE=1 python -m makeupdiffuse_b200.build --force`); the shipped library has ONE code path and reads no environment.

@@ -84,7 +84,8 @@ struct PairP {
   float2* stats;
   int stats_ld;
   const void* w;              // weights, for the L2 prefetch ahead of pdl_wait()
-  unsigned long long w_bytes;
+  unsigned long long w_bytes;  // (capped) bytes to prefetch, w_share of them per CTA
+  unsigned w_share;
   unsigned long long* trace;  // debug: per-CTA %globaltimer stamps (mkd_debug_set_trace), else nullptr
 };
 // slot layout per CTA (16 x u64): 0 entry, 1 prologue done, 2 first TMA issued, 3 first full barrier (MMA warp), 4 unit-0 MMAs
@@ -427,7 +428,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
                "l"(p.stats), "r"(p.stats_ld));
 
   if (threadIdx.x == 0) PAIR_TRACE(0);
-  if (warp == 3) l2_prefetch_share(p.w, p.w_bytes, lane);
+  if (warp == 3) l2_prefetch_share(p.w, p.w_bytes, p.w_share, lane);
   if (blockIdx.x == 0 && threadIdx.x == 96) {  // (idle warp 3) what to print if a wait times out
     g_pair_shape[0] = p.M; g_pair_shape[1] = p.n_units * ACC_COLS; g_pair_shape[2] = p.kblocks; g_pair_shape[3] = p.num_units;
     g_pair_shape[4] = p.stages; g_pair_shape[5] = p.npb;
@@ -1113,7 +1114,6 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   p.stats_ld = d->stats_ld;
   p.trace = debug_trace_ptr();
   p.w = d->w;
-  p.w_bytes = (unsigned long long)d->K * pl.Ktot * 2;
   r32map = r16map = y32map = y16map = amap;  // (unused maps must still be valid kernel parameters)
   if (partial) {
     p.has_y32 = 1;
@@ -1147,6 +1147,7 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = p.num_units < max_pairs ? p.num_units : max_pairs;
+  l2_prefetch_plan((unsigned long long)d->K * pl.Ktot * 2, 2 * pairs, p.w_bytes, p.w_share);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);

@@ -67,7 +67,8 @@ struct MainP {
   int commit_every;                 // G: smem slots are released with one tcgen05.commit per G k-blocks
   int debug;                        // debug timing experiments (results invalid): 1 = skip B loads, 2 = skip MMA issue
   const void* w;                    // weights, for the L2 prefetch ahead of pdl_wait()
-  unsigned long long w_bytes;
+  unsigned long long w_bytes;       // (capped) bytes to prefetch, w_share of them per CTA
+  unsigned w_share;
 };
 
 [[maybe_unused]] __device__ __forceinline__ unsigned long long gtimer() {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__((Cfg<BN, CL, EPI, DUAL>::THREADS), 1) gemm_tcg
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) MKD_TRACE(0);
-  if (warp == 3) l2_prefetch_share(mp.w, mp.w_bytes, lane);  // (an epilogue / idle warp: nothing to do until the first accumulator)
+  if (warp == 3) l2_prefetch_share(mp.w, mp.w_bytes, mp.w_share, lane);  // (an epilogue / idle warp: nothing to do until the first accumulator)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
@@ -1231,7 +1232,6 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   mp.half_dw = half_dw; mp.half_dh = half_dh; mp.half_dn = half_dn;
   mp.trace = g_trace;
   mp.w = d->w;
-  mp.w_bytes = (unsigned long long)d->K * g.Ktot * 2;
   {
     static const int ge = debug_switch("MKD_COMMIT_EVERY", 0);  // overrides the release granularity (experiments)
     mp.commit_every = ge > 0 ? ge : 1;  // measured: G = 1, 2, 3 give identical k-block times
@@ -1265,6 +1265,7 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   mp.num_units = g.m_tiles * mp.n_tiles * splits;  // cluster-level work units
   const int max_clusters = num_sms() / CL;
   const int grid = CL * (mp.num_units < max_clusters ? mp.num_units : max_clusters);
+  l2_prefetch_plan((unsigned long long)d->K * g.Ktot * 2, grid, mp.w_bytes, mp.w_share);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
