@@ -68,7 +68,7 @@ __device__ __forceinline__ int fdiv(int n, FastDiv f) { return f.m ? (int)__umul
 struct PairP {
   // main loop
   int kblocks, kb_per_split;
-  int conv, cblocks, S, pad;
+  int conv, cblocks, S, pad, stride;  // stride 2: the activation map walks the input with element strides (1, 2, 2, 1)
   int Wb, Hb, Nb, tiles_w, tiles_h;
   FastDiv d_n_units, d_m_pairs, d_cblocks, d_S, d_tiles_w, d_tiles_h, d_ppi;
   int m_tiles, m_pairs, n_units, num_units;  // unit -> (n_unit fastest, m_pair, split)
@@ -480,8 +480,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       if (p.conv) {
         const int mw = fdiv(m_tile, p.d_tiles_w), tw = m_tile - mw * p.tiles_w;
         const int tn = fdiv(mw, p.d_tiles_h), th = mw - tn * p.tiles_h;
-        w0 = tw * p.Wb;
-        h0 = th * p.Hb;
+        w0 = tw * p.Wb * p.stride;  // input coordinate of the tile's first output pixel (before the filter-tap offset)
+        h0 = th * p.Hb * p.stride;
         n0 = tn * p.Nb;
       }
       const int m0 = m_tile * BM;
@@ -918,10 +918,11 @@ EncodeFn get_encode() {
   return fn;
 }
 int encode(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
-           const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw) {
+           const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw, int spatial_stride = 1) {
   EncodeFn fn = get_encode();
   MKD_REQUIRE(fn != nullptr, MKD_E_CUDA, "cuTensorMapEncodeTiled entry point not found (driver too old?)");
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // element (traversal) strides: a box dimension of b with stride e delivers ceil(b / e) elements, every e-th one
+  cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
   CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MKD_REQUIRE(r == CUDA_SUCCESS, MKD_E_CUDA, "gemm_pair: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -951,10 +952,17 @@ struct PairPlan {
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// Which descriptors the pair kernel takes (stride 1, no upsample: the caller has materialised those), and how.
+// Which descriptors the pair kernel takes, and how.  Stride 1 (1x1, 3x3 / pad 1) and the stride-2 Downsample convs
+// (3x3, pad 1: input pixel 2 p + r - 1, read through a tensor map with element strides 2 — no im2col pass); upsample
+// convs arrive here materialised by the caller.
 bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
-  if (d->dtype != MKD_BF16 || d->stride != 1 || d->upsample || d->pad_hi_extra) return false;
-  if (d->C % BK != 0 || d->R != d->S || (d->R != 1 && d->R != 3) || d->pad != d->R / 2) return false;
+  if (d->dtype != MKD_BF16 || d->upsample) return false;
+  if (d->C % BK != 0 || d->R != d->S || (d->R != 1 && d->R != 3)) return false;
+  if (d->stride == 1) {
+    if (d->pad != d->R / 2 || d->pad_hi_extra) return false;
+  } else {
+    if (d->stride != 2 || d->R != 3 || d->H % 2 || d->W % 2 || d->pad != 1 || d->pad_hi_extra || d->W > 256) return false;
+  }
   if (d->ldx % 8 || !aligned16(d->x) || !aligned16(d->w)) return false;
   if (d->bias && !aligned16(d->bias)) return false;
   if (d->y && (d->ldy % 8 || !aligned16(d->y))) return false;
@@ -963,9 +971,9 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
   if (d->emb && (d->lde % 8 || !aligned16(d->emb))) return false;
   if (d->stats && (d->act != MKD_ACT_NONE || d->stats_ld < d->K || ((uintptr_t)d->stats & 7))) return false;
   pl.conv = d->R == 3;
-  pl.P = d->H;
-  pl.Q = d->W;
-  pl.M = d->N * d->H * d->W;
+  pl.P = d->H / d->stride;
+  pl.Q = d->W / d->stride;
+  pl.M = d->N * pl.P * pl.Q;  // output rows (stride 2: a quarter of the input pixels)
   pl.Ktot = d->R * d->S * d->C;
   // ragged M: TMA zero-fills the rows it loads beyond M and clips the rows it stores; statistics need whole tiles
   if (d->stats && pl.M % BM != 0) return false;
@@ -1063,8 +1071,8 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   if (pl.conv) {
     cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t str[3] = {(cuuint64_t)d->ldx * 2, (cuuint64_t)d->ldx * 2 * d->W, (cuuint64_t)d->ldx * 2 * d->W * d->H};
-    cuuint32_t box[4] = {BK, (cuuint32_t)pl.Wb, (cuuint32_t)pl.Hb, (cuuint32_t)pl.Nb};
-    rc = encode(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    cuuint32_t box[4] = {BK, (cuuint32_t)(pl.Wb * d->stride), (cuuint32_t)(pl.Hb * d->stride), (cuuint32_t)pl.Nb};
+    rc = encode(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, d->stride);
   } else {
     cuuint64_t dims[2] = {(cuuint64_t)d->C, (cuuint64_t)pl.M};
     cuuint64_t str[1] = {(cuuint64_t)d->ldx * 2};
@@ -1087,6 +1095,7 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   p.cblocks = d->C / BK;
   p.S = d->S;
   p.pad = d->pad;
+  p.stride = d->stride;
   p.Wb = pl.Wb; p.Hb = pl.Hb; p.Nb = pl.Nb;
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.m_tiles = pl.m_tiles;

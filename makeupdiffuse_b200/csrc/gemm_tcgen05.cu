@@ -1353,10 +1353,17 @@ int splitk_reduce(const mkd_conv_desc* d, int M, int pix_per_img, int splits, cu
   return MKD_OK;
 }
 
+// the stride-2 Downsample convs the CTA-pair kernel reads in place (element-strided tensor map): no im2col, no workspace
+static bool pair_takes_strided(const mkd_conv_desc* d) {
+  return d->stride == 2 && !d->upsample && d->path != MKD_PATH_TCGEN05_SINGLE && (g_pair_auto || d->path == MKD_PATH_TCGEN05_PAIR) &&
+         conv2d_pair_supported(d, d->path == MKD_PATH_TCGEN05_PAIR);
+}
+
 bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
+  if (pair_takes_strided(d)) return true;
   Geometry g;
   if (!geometry(d, g)) return false;
-  if (d->path == MKD_PATH_TCGEN05_PAIR) {  // forced pair kernel (tests / benchmarks): stride-1 shapes it takes only
+  if (d->path == MKD_PATH_TCGEN05_PAIR) {  // forced pair kernel (tests / benchmarks): only the shapes it takes
     if (d->stride != 1 || d->upsample || !conv2d_pair_supported(d, true)) {
       set_error("the CTA-pair kernel does not take this shape");
       return false;
@@ -1366,6 +1373,7 @@ bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
 }
 
 int conv2d_tcgen05(const mkd_conv_desc* d_in, cudaStream_t stream) {
+  if (pair_takes_strided(d_in)) return conv2d_pair(d_in, d_in->path == MKD_PATH_TCGEN05_PAIR, stream);
   Geometry g;
   MKD_REQUIRE(geometry(d_in, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
   mkd_conv_desc dd;

@@ -314,6 +314,11 @@ PAIR_CASES = [
     dict(N=16, H=4, W=4, C=2560, K=1280, R=3, emb=True, workspace=True),     # split-K (4x4 level, K = 23040)
     dict(N=16, H=8, W=8, C=5120, K=1280, R=1, residual=True, res32=True, workspace=True),  # split-K ff2
     dict(N=8, H=4, W=4, C=1280, K=1280, R=3, residual=True, res32=True, y32="both", workspace=True),  # split-K + fp32
+    # stride-2 Downsample convs read in place through an element-strided tensor map (no im2col, no workspace)
+    dict(N=16, H=32, W=32, C=320, K=320, R=3, stride=2, y32="both"),         # 32x32 -> 16x16 at batch 16
+    dict(N=3, H=16, W=16, C=640, K=640, R=3, stride=2),                      # 16x16 -> 8x8: box spans 2 images, ragged N
+    dict(N=16, H=8, W=8, C=1280, K=1280, R=3, stride=2, workspace=True),     # 8x8 -> 4x4: split-K
+    dict(N=2, H=64, W=64, C=320, K=320, R=3, stride=2, y32="only"),          # 512^2 level: 64x64 -> 32x32
 ]
 
 
@@ -349,7 +354,8 @@ def test_conv_auto_dispatch():
     assert path(N=16, H=1, W=1024, C=320, K=960) == L.PATH_TCGEN05
     assert path(N=16, H=32, W=32, C=4, K=320, R=3) == L.PATH_GENERIC
     assert path(N=16, H=32, W=32, C=320, K=320, R=3, stride=2, ws=True) == L.PATH_TCGEN05
-    assert path(N=16, H=32, W=32, C=320, K=320, R=3, stride=2) == L.PATH_GENERIC  # no workspace to materialise into
+    assert path(N=16, H=32, W=32, C=320, K=320, R=3, stride=2) == L.PATH_TCGEN05  # CTA-pair kernel: strided map, no workspace
+    assert path(N=16, H=32, W=32, C=64, K=64, R=3, stride=2) == L.PATH_GENERIC  # single-CTA kernel: no workspace to materialise into
 
 
 def test_conv_rejects_bad_descriptors():
@@ -383,6 +389,7 @@ PAIR_STATS_CASES = [
     dict(N=1, H=64, W=64, C=320, K=320, R=1, residual=True),                 # proj_out, 512^2 level
     dict(N=16, H=32, W=32, C=320, K=320, R=3, residual=True),                # two sub-tiles per A tile
     dict(N=3, H=16, W=16, C=1280, K=640, R=3, emb=True),                     # odd tile count
+    dict(N=16, H=32, W=32, C=320, K=320, R=3, stride=2),                     # Downsample in place (element-strided map) + stats
 ]
 
 
