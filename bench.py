@@ -410,7 +410,7 @@ def main():
         prof = [r for r in prof if r["op"] == "conv2d"]
         agg = {}
         for r in prof:
-            key = (r["path"], r["M"], r["K"], r["C"], r["R"], r["stride"], r["up"])
+            key = (r["path"], r["M"], r["K"], r["C"], r["R"], r["stride"], r["up"], r.get("C2", 0))
             a = agg.setdefault(key, {"n": 0, "ms": 0.0, "flops": 0.0})
             a["n"] += 1; a["ms"] += r["ms"]; a["flops"] += r["flops"]
         tc = [r for r in prof if r["path"] == _lib.PATH_TCGEN05]
@@ -483,7 +483,7 @@ def main():
                 "others": others}
         for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
             table.append({"path": "tcgen05" if key[0] == _lib.PATH_TCGEN05 else "generic", "M": key[1], "N": key[2],
-                          "C": key[3], "R": key[4], "stride": key[5], "up": key[6], "count": a["n"], "ms": round(a["ms"], 4),
+                          "C": key[3], "R": key[4], "stride": key[5], "up": key[6], "C2": key[7], "count": a["n"], "ms": round(a["ms"], 4),
                           "tflops": round(a["flops"] / (a["ms"] / 1e3) / 1e12, 1) if a["ms"] else None})
         if args.profile_out:
             with open(args.profile_out, "w") as f:

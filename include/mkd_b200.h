@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 7
+#define MKD_ABI_VERSION 8
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 
@@ -164,6 +164,16 @@ typedef struct mkd_conv_desc {
   /* extra zero padding on the bottom / right edge only (0 or 1).  The VAE encoder's Downsample is
    * F.pad(x, (0,1,0,1)) followed by a 3x3 stride-2 conv without padding: pad = 0, pad_hi_extra = 1. */
   int pad_hi_extra;
+  /* optional second 1x1 term over another input with the output's pixels (ABI v8; NULL = absent):
+   *   acc[n,p,q,k] += sum_{c < C2} X2[n,p,q,c] * Wt[k][R*S*C + c]
+   * The weight rows are then [R][S][C] followed by C2 more columns (row pitch R*S*C + C2) and `bias` is the sum of the
+   * two layers' biases.  This is a ResBlock's `out_layers` 3x3 conv and its 1x1 `skip_connection` (upstream
+   * ldm ResBlock._forward: `self.skip_connection(x) + h`) as ONE contraction: the skip projection neither runs as its own
+   * GEMM nor travels through memory as an fp32 tensor.  stride must be 1, C2 % 64 == 0, ldx2 % 8 == 0; only the tensor-core
+   * CTA-pair kernel takes it: mkd_conv2d_path() returns MKD_E_INVALID when that kernel declines the shape (the caller then
+   * issues the two layers separately). */
+  const void* x2;
+  int C2, ldx2;
 } mkd_conv_desc;
 
 int mkd_conv2d(const mkd_conv_desc* d, mkd_stream_t stream);

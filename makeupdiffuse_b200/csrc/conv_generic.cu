@@ -207,6 +207,12 @@ static int validate(const mkd_conv_desc* d) {
   MKD_REQUIRE(!d->residual || d->ldr >= kout, MKD_E_INVALID, "conv2d: ldr too small");
   MKD_REQUIRE(!d->emb || d->lde >= kout, MKD_E_INVALID, "conv2d: lde too small");
   MKD_REQUIRE(d->act >= MKD_ACT_NONE && d->act <= MKD_ACT_GEGLU, MKD_E_INVALID, "conv2d: bad act");
+  if (d->x2) {
+    MKD_REQUIRE(d->C2 > 0 && d->ldx2 >= d->C2, MKD_E_INVALID, "conv2d: x2 term needs C2 > 0 and ldx2 >= C2");
+    MKD_REQUIRE(d->dtype == MKD_BF16 && d->stride == 1 && !d->upsample && d->act != MKD_ACT_GEGLU && d->path != MKD_PATH_GENERIC &&
+                    d->path != MKD_PATH_TCGEN05_SINGLE,
+                MKD_E_INVALID, "conv2d: the x2 term is bf16, stride 1, no upsample / GEGLU, tensor-core CTA-pair kernel only");
+  }
   if (d->act == MKD_ACT_GEGLU) {
     MKD_REQUIRE(d->K % 2 == 0 && d->geglu_block > 0 && (d->K / 2) % d->geglu_block == 0, MKD_E_INVALID,
                 "conv2d: GEGLU needs K even and K/2 %% geglu_block == 0");
@@ -225,6 +231,7 @@ extern "C" int mkd_conv2d_path(const mkd_conv_desc* d) {
   if (rc) return rc;
   if (d->path == MKD_PATH_GENERIC) return MKD_PATH_GENERIC;
   bool ok = mkd::conv2d_tcgen05_supported(d);
+  if (d->x2 && !ok) return MKD_E_INVALID;  // no other kernel takes the second term: the caller issues the two layers separately
   if (d->path >= MKD_PATH_TCGEN05) {  // forced tensor-core kernel (either of the two)
     if (!ok) return MKD_E_INVALID;  // conv2d_tcgen05_supported() left the reason in mkd_last_error()
     return MKD_PATH_TCGEN05;

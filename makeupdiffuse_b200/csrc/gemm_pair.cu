@@ -68,6 +68,7 @@ __device__ __forceinline__ int fdiv(int n, FastDiv f) { return f.m ? (int)__umul
 struct PairP {
   // main loop
   int kblocks, kb_per_split;
+  int kb_main;  // k-blocks of the filter-tap walk over `x`; blocks [kb_main, kblocks) read the second 1x1 term `x2` (amap2)
   int conv, cblocks, S, pad, stride;  // stride 2: the activation map walks the input with element strides (1, 2, 2, 1)
   int Wb, Hb, Nb, tiles_w, tiles_h;
   FastDiv d_n_units, d_m_pairs, d_cblocks, d_S, d_tiles_w, d_tiles_h, d_ppi;
@@ -392,8 +393,8 @@ enum { MODE_PLAIN = 0, MODE_GEGLU = 1 };
 
 template <int UN, int NSUB, int MODE, int STATS>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
-                 const __grid_constant__ CUtensorMap r32map, const __grid_constant__ CUtensorMap r16map,
+gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap amap2,
+                 const __grid_constant__ CUtensorMap bmap, const __grid_constant__ CUtensorMap r32map, const __grid_constant__ CUtensorMap r16map,
                  const __grid_constant__ CUtensorMap y32map, const __grid_constant__ CUtensorMap y16map, const PairP p) {
   constexpr int BH_BYTES = (UN / 2) * BK * 2;            // one CTA's half of a weight tile per k-block
   constexpr int STAGE_BYTES = A_BYTES + NSUB * BH_BYTES;
@@ -439,6 +440,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&bmap)) : "memory");
+      if (p.kb_main < p.kblocks) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&amap2)) : "memory");
     }
     // one barrier per lane: full (count 2: both producers arrive on the leader's copy, both CTAs' bytes land there),
     // empty / tmem_full (1: multicast commit), tmem_empty (every epilogue warp of both CTAs, leader's copy),
@@ -499,7 +501,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
           unsigned char* sa = smem + s * STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(full_bar + s, 2 * STAGE_BYTES);
           else mbar_arrive_cluster(full_bar + s, 0);
-          if (p.conv) tma_load_4d_2sm(&amap, full_bar + s, sa, cb * BK, w0 + sx - p.pad, h0 + r - p.pad, n0);
+          if (kb >= p.kb_main) {  // second term: the 1x1 filter over x2 (same pixels as the output tile, no tap offset)
+            if (p.conv) tma_load_4d_2sm(&amap2, full_bar + s, sa, (kb - p.kb_main) * BK, w0, h0, n0);
+            else tma_load_2d_2sm(&amap2, full_bar + s, sa, (kb - p.kb_main) * BK, m0);
+          } else if (p.conv) tma_load_4d_2sm(&amap, full_bar + s, sa, cb * BK, w0 + sx - p.pad, h0 + r - p.pad, n0);
           else tma_load_2d_2sm(&amap, full_bar + s, sa, kb * BK, m0);
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub)
@@ -970,11 +975,15 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
   if (d->residual && (!aligned16(d->residual) || d->ldr % (d->residual_dtype == MKD_F32 ? 4 : 8))) return false;
   if (d->emb && (d->lde % 8 || !aligned16(d->emb))) return false;
   if (d->stats && (d->act != MKD_ACT_NONE || d->stats_ld < d->K || ((uintptr_t)d->stats & 7))) return false;
+  // second 1x1 term (mkd_conv_desc.x2): extra k-blocks at the end of the walk, read through a second activation map
+  if (d->x2 && (d->stride != 1 || d->C2 <= 0 || d->C2 % BK || d->ldx2 % 8 || d->ldx2 < d->C2 || !aligned16(d->x2) ||
+                d->act == MKD_ACT_GEGLU))
+    return false;
   pl.conv = d->R == 3;
   pl.P = d->H / d->stride;
   pl.Q = d->W / d->stride;
   pl.M = d->N * pl.P * pl.Q;  // output rows (stride 2: a quarter of the input pixels)
-  pl.Ktot = d->R * d->S * d->C;
+  pl.Ktot = d->R * d->S * d->C + (d->x2 ? d->C2 : 0);
   // ragged M: TMA zero-fills the rows it loads beyond M and clips the rows it stores; statistics need whole tiles
   if (d->stats && pl.M % BM != 0) return false;
   if (pl.conv) {
@@ -1066,7 +1075,7 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
     configured = true;
   }
   const bool partial = pl.splits > 1;
-  CUtensorMap amap, bmap, r32map, r16map, y32map, y16map;
+  CUtensorMap amap, amap2, bmap, r32map, r16map, y32map, y16map;
   int rc;
   if (pl.conv) {
     cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
@@ -1080,6 +1089,21 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
     rc = encode(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->x, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
   }
   if (rc) return rc;
+  amap2 = amap;  // (an unused map must still be a valid kernel parameter)
+  if (d->x2) {   // same boxes over the second input: its pixels are the output's (stride 1), its channels the extra k-blocks
+    if (pl.conv) {
+      cuuint64_t dims[4] = {(cuuint64_t)d->C2, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+      cuuint64_t str[3] = {(cuuint64_t)d->ldx2 * 2, (cuuint64_t)d->ldx2 * 2 * d->W, (cuuint64_t)d->ldx2 * 2 * d->W * d->H};
+      cuuint32_t box[4] = {BK, (cuuint32_t)pl.Wb, (cuuint32_t)pl.Hb, (cuuint32_t)pl.Nb};
+      rc = encode(&amap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->x2, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      cuuint64_t dims[2] = {(cuuint64_t)d->C2, (cuuint64_t)pl.M};
+      cuuint64_t str[1] = {(cuuint64_t)d->ldx2 * 2};
+      cuuint32_t box[2] = {BK, BM};
+      rc = encode(&amap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->x2, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    if (rc) return rc;
+  }
   {
     cuuint64_t dims[2] = {(cuuint64_t)pl.Ktot, (cuuint64_t)d->K};
     cuuint64_t str[1] = {(cuuint64_t)pl.Ktot * 2};
@@ -1090,6 +1114,7 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   const int n_out = MODE == MODE_GEGLU ? d->K / 2 : d->K;
   PairP p = {};
   p.kblocks = pl.Ktot / BK;
+  p.kb_main = d->R * d->S * d->C / BK;
   p.kb_per_split = pl.kb_per_split;
   p.conv = pl.conv;
   p.cblocks = d->C / BK;
@@ -1172,7 +1197,7 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    MKD_LAUNCH_OK(cudaLaunchKernelEx(&cfg, kernel, amap, bmap, r32map, r16map, y32map, y16map, p));
+    MKD_LAUNCH_OK(cudaLaunchKernelEx(&cfg, kernel, amap, amap2, bmap, r32map, r16map, y32map, y16map, p));
   }
   MKD_CHECK_LAUNCH();
   if (partial) return splitk_reduce(d, pl.M, pl.P * pl.Q, pl.splits, stream);

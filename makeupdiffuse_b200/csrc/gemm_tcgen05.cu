@@ -1360,6 +1360,11 @@ static bool pair_takes_strided(const mkd_conv_desc* d) {
 }
 
 bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
+  if (d->x2) {  // second 1x1 term: the CTA-pair kernel or nothing
+    if (d->path != MKD_PATH_TCGEN05_SINGLE && d->stride == 1 && !d->upsample && conv2d_pair_supported(d, d->path == MKD_PATH_TCGEN05_PAIR)) return true;
+    set_error("conv2d: the x2 term needs the CTA-pair kernel, which declined this shape");
+    return false;
+  }
   if (pair_takes_strided(d)) return true;
   Geometry g;
   if (!geometry(d, g)) return false;
@@ -1373,7 +1378,7 @@ bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
 }
 
 int conv2d_tcgen05(const mkd_conv_desc* d_in, cudaStream_t stream) {
-  if (pair_takes_strided(d_in)) return conv2d_pair(d_in, d_in->path == MKD_PATH_TCGEN05_PAIR, stream);
+  if (d_in->x2 || pair_takes_strided(d_in)) return conv2d_pair(d_in, d_in->path == MKD_PATH_TCGEN05_PAIR, stream);
   Geometry g;
   MKD_REQUIRE(geometry(d_in, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
   mkd_conv_desc dd;

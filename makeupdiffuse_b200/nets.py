@@ -93,6 +93,8 @@ class _Net(nn.Module):
         self._ch, self._ds = ch, ds
         self._attn_res = tuple(attention_resolutions)
         self.fused_gn_stats = True  # False: always the two-phase GroupNorm (A/B runs)
+        self.fuse_skip = True       # False: ResBlock skip projections always as their own GEMM (A/B runs)
+        self._fuse_ok: dict = {}
         # bumped whenever context_kv() / hint_features() refill their (shared, static) arena buffers: a holder of earlier
         # results — B200ControlLDM's cond cache — compares epochs to learn that the buffers now hold another cond's data
         self.arena_epoch = 0
@@ -150,6 +152,13 @@ class _Net(nn.Module):
                 if layer[2] != layer[3]:
                     self._put(key + ".sk.w", self._krsc(g(key + ".skip_connection.weight")), True)
                     self._put(key + ".sk.b", g(key + ".skip_connection.bias"))
+                    if self._hi:
+                        # out_layers conv + skip_connection as ONE contraction (mkd_conv_desc.x2): weight rows
+                        # [3][3][cout] followed by the cin columns of the 1x1 projection, biases summed
+                        co = layer[3]
+                        self._put(key + ".c2sk.w", torch.cat([self._krsc(g(key + ".out_layers.3.weight")).reshape(co, -1),
+                                                              g(key + ".skip_connection.weight").reshape(co, -1)], 1), True)
+                        self._put(key + ".c2sk.b", g(key + ".out_layers.3.bias") + g(key + ".skip_connection.bias"))
             elif kind == "st":
                 tb = key + ".transformer_blocks.0."
                 self._put(key + ".gn.g", g(key + ".norm.weight")); self._put(key + ".gn.b", g(key + ".norm.bias"))
@@ -332,6 +341,10 @@ class _Net(nn.Module):
         self._conv(t1, key + ".c1", h_lo, N, H, W, R=3, emb=e, y32=h_hi, stats=h_st)
         t2 = self._buf("gn_b", M, cout)
         self._gn(Act(h_lo, h_hi, h_st), t2, N, self.w[key + ".gn2.g"], self.w[key + ".gn2.b"], 1e-5, True)
+        if cin != cout and self._skip_fuses(key, t2, x.lo, y, N, H, W):
+            # h = conv2(...) + skip_connection(x): the 1x1 projection rides as extra k-blocks of the 3x3 conv's GEMM
+            self._conv(t2, key + ".c2sk", y.lo, N, H, W, R=3, x2=x.lo, y32=y.hi, stats=y.st)
+            return
         if cin != cout:
             s_lo, s_hi = self._side("res_sk", M, cout)
             self._conv(x.lo, key + ".sk", s_lo, N, H, W, R=1, y32=s_hi)
@@ -339,6 +352,19 @@ class _Net(nn.Module):
         else:
             sk = x.src()
         self._conv(t2, key + ".c2", y.lo, N, H, W, R=3, residual=sk, y32=y.hi, stats=y.st)
+
+    def _skip_fuses(self, key, t2, x_lo, y, N, H, W):
+        """can this ResBlock's out conv take its skip projection as a second term?  (bf16 path, CTA-pair kernel shapes;
+        asked once per (layer, shape))"""
+        if not (self._hi and self.fuse_skip and x_lo is not None and key + ".c2sk.w" in self.w):
+            return False
+        ck = (key, N, H, W, y.lo is None, y.hi is None, y.st is None)
+        ok = self._fuse_ok.get(ck)
+        if ok is None:
+            ok = ops.conv2d_supported(t2, self.w[key + ".c2sk.w"], y.lo, N=N, H=H, W=W, R=3, S=3, pad=1, x2=x_lo,
+                                      bias=self.w[key + ".c2sk.b"], workspace=self._ws, y32=y.hi, stats=y.st)
+            self._fuse_ok[ck] = ok
+        return ok
 
     def _st(self, layer, x, y, ctx_kv, N, H, W):
         """x, y: Act.  The token stream xs (x += attn1, += attn2, += ff) lives in fp32 until its last update, which

@@ -193,13 +193,15 @@ def softmax_rows(x2d, y2d, scale=1.0):
 
 def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None,
                    residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None,
-                   y32=None, stats=None, pad_hi_extra=0) -> L.ConvDesc:
-    """y2d: output in the activation dtype (or None); y32: optional fp32 copy of the same result."""
+                   y32=None, stats=None, pad_hi_extra=0, x2=None) -> L.ConvDesc:
+    """y2d: output in the activation dtype (or None); y32: optional fp32 copy of the same result.
+    x2: optional second input [N*H*W, C2] of a fused 1x1 term (mkd_conv_desc.x2): w is then [K, R*S*C + C2]."""
     px, ldx = _rows(x2d)
     Cc = x2d.shape[1]
     K = w.shape[0]
+    C2 = 0 if x2 is None else x2.shape[1]
     assert x2d.shape[0] == N * H * W, (x2d.shape, N, H, W)
-    assert w.is_contiguous() and w.numel() == K * R * S * Cc and w.dtype == x2d.dtype
+    assert w.is_contiguous() and w.numel() == K * (R * S * Cc + C2) and w.dtype == x2d.dtype
     d = L.ConvDesc()
     d.dtype = _dt(x2d)
     d.residual_dtype = d.dtype
@@ -235,6 +237,10 @@ def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=
         assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[1:] == (K, 2)
         assert stats.stride(2) == 1 and stats.stride(1) == 2 and stats.stride(0) % 2 == 0
         d.stats, d.stats_ld = stats.data_ptr(), stats.stride(0) // 2
+    if x2 is not None:
+        assert x2.dtype == x2d.dtype and x2.shape[0] == x2d.shape[0] and stride == 1 and not upsample
+        d.x2, d.ldx2 = _rows(x2)
+        d.C2 = C2
     return d
 
 
@@ -251,8 +257,8 @@ def conv2d(x2d, w, y2d, **kw):
     Hi, Wi = (2 * d.H, 2 * d.W) if d.upsample else (d.H, d.W)
     P = (Hi + 2 * d.pad + d.pad_hi_extra - d.R) // d.stride + 1
     Q = (Wi + 2 * d.pad + d.pad_hi_extra - d.S) // d.stride + 1
-    PROFILE.append({"op": "conv2d", "path": path, "flops": 2.0 * d.N * P * Q * d.K * d.R * d.S * d.C, "M": d.N * P * Q, "K": d.K,
-                    "C": d.C, "R": d.R, "stride": d.stride, "up": d.upsample, "e0": e0, "e1": e1, "desc": d})
+    PROFILE.append({"op": "conv2d", "path": path, "flops": 2.0 * d.N * P * Q * d.K * (d.R * d.S * d.C + d.C2), "M": d.N * P * Q, "K": d.K,
+                    "C": d.C, "C2": d.C2, "R": d.R, "stride": d.stride, "up": d.upsample, "e0": e0, "e1": e1, "desc": d})
 
 
 def conv2d_path(x2d, w, y2d, **kw) -> int:
@@ -261,6 +267,12 @@ def conv2d_path(x2d, w, y2d, **kw) -> int:
     if rc < 0:
         L.check(rc, "conv2d_path")
     return rc
+
+
+def conv2d_supported(x2d, w, y2d, **kw) -> bool:
+    """does some kernel take this descriptor?  (False for a fused `x2` term the CTA-pair kernel declines: the caller then
+    issues the two layers as two launches)"""
+    return L.load().mkd_conv2d_path(C.byref(make_conv_desc(x2d, w, y2d, **kw))) >= 0
 
 
 def run_conv_desc(d: L.ConvDesc):

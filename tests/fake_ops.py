@@ -104,10 +104,15 @@ def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
 
 def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None, residual=None,
            alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None, y32=None, stats=None,
-           pad_hi_extra=0):
+           pad_hi_extra=0, x2=None):
     C = x2d.shape[1]
     K = w.shape[0]
-    assert x2d.shape[0] == N * H * W and w.numel() == K * R * S * C
+    C2 = 0 if x2 is None else x2.shape[1]
+    assert x2d.shape[0] == N * H * W and w.numel() == K * (R * S * C + C2)
+    w2 = None
+    if x2 is not None:  # fused second 1x1 term (mkd_conv_desc.x2): weight rows [R][S][C] + C2 columns
+        assert stride == 1 and not upsample and act != L.ACT_GEGLU
+        w, w2 = w.reshape(K, -1)[:, :R * S * C], w.reshape(K, -1)[:, R * S * C:]
     xr = x2d.float().reshape(N, H, W, C).permute(0, 3, 1, 2)
     if upsample:
         xr = F.interpolate(xr, scale_factor=2, mode="nearest")
@@ -116,6 +121,8 @@ def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, b
     acc = F.conv2d(xr, w.float().reshape(K, R, S, C).permute(0, 3, 1, 2), None if bias is None else bias.float(),
                    stride=stride, padding=pad)
     Mo = acc.shape[0] * acc.shape[2] * acc.shape[3]
+    if w2 is not None:
+        acc = acc + (x2.float() @ w2.float().t()).reshape(N, H, W, K).permute(0, 3, 1, 2)
     if emb is not None:
         acc = acc + emb.float()[:, :, None, None]
     acc = (acc * alpha).permute(0, 2, 3, 1).reshape(Mo, K)
@@ -139,6 +146,12 @@ def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, b
         if out is not None:
             assert out.shape == acc.shape, (out.shape, acc.shape)
             out.copy_(acc)
+
+
+def conv2d_supported(x2d, w, y2d, **kw):
+    """the contract of the x2 term: stride 1, C2 % 64 == 0, K % 160 == 0 (the CTA-pair kernel's tiles)"""
+    x2 = kw.get("x2")
+    return x2 is None or (x2.shape[1] % 64 == 0 and w.shape[0] % 160 == 0 and x2d.shape[1] % 64 == 0)
 
 
 def attention(q2d, k2d, v2d, o2d, *, B, heads, Nq, Nkv, d, scale):
@@ -173,4 +186,4 @@ def image_grid_u8(images, nrow, padding=2, clamp=True, rescale=True):
 
 
 ALL = ["image_grid_u8", "attention_causal", "embed_tokens", "device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
-       "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "softmax_rows", "conv2d", "attention"]
+       "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "softmax_rows", "conv2d", "conv2d_supported", "attention"]

@@ -147,13 +147,19 @@ def test_layernorm(dt, M, C):
 # ---- convolution / GEMM family -----------------------------------------------------------------------------------
 def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True, emb=False, residual=False,
               inplace=False, alpha=1.0, act=L.ACT_NONE, ldx_extra=0, ldy_extra=0, ldy_pad=0, workspace=False, seed=0,
-              y32="", res32=False, gb=None):
-    """y32: "" (activation-dtype output only), "both" (+ fp32 copy) or "only" (fp32 copy only); res32: fp32 residual"""
+              y32="", res32=False, gb=None, C2=0):
+    """y32: "" (activation-dtype output only), "both" (+ fp32 copy) or "only" (fp32 copy only); res32: fp32 residual;
+    C2: channels of a fused second 1x1 term over another input (mkd_conv_desc.x2), 0 = none"""
     M = N * H * W
     xb = rnd(M, C + ldx_extra, dt=dt, seed=seed + 1)
     x = xb[:, ldx_extra:]
     w_oihw = rnd(K, C, R, R, seed=seed + 2, scale=1.0 / math.sqrt(C * R * R)).to(dt)
     w = w_oihw.permute(0, 2, 3, 1).contiguous()
+    x2 = w2 = None
+    if C2:  # the second input is a channel slice of a wider buffer, like a decoder concat
+        x2 = rnd(M, C2 + 64, dt=dt, seed=seed + 7)[:, 64:]
+        w2 = rnd(K, C2, seed=seed + 8, scale=1.0 / math.sqrt(C2)).to(dt)
+        w = torch.cat([w.reshape(K, -1), w2], 1).contiguous()
     b = 0.5 * rnd(K, seed=seed + 3) if bias else None
     e = rnd(N, K + 8, dt=dt, seed=seed + 4)[:, 8:] if emb else None
     Hi, Wi = (2 * H, 2 * W) if upsample else (H, W)
@@ -172,7 +178,7 @@ def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True,
         gb = 80 if act == L.ACT_GEGLU and Ko % 80 == 0 else 16
     ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV) if workspace else None
     kw = dict(N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=upsample, bias=b, emb=e, residual=res,
-              alpha=alpha, act=act, geglu_block=gb, path=path, workspace=ws, y32=out32)
+              alpha=alpha, act=act, geglu_block=gb, path=path, workspace=ws, y32=out32, x2=x2)
     want = min(path, L.PATH_TCGEN05)  # the two forced tensor-core kernels both report PATH_TCGEN05
     assert ops.conv2d_path(x, w, y, **kw) == (want if path else ops.conv2d_path(x, w, y, **kw))
     ops.conv2d(x, w, y, **kw)
@@ -189,6 +195,8 @@ def conv_case(dt, path, N, H, W, C, K, R=1, stride=1, upsample=False, bias=True,
     else:
         br = b
     acc = F.conv2d(xr.double(), wr.double(), None if br is None else br.double(), stride=stride, padding=R // 2)
+    if C2:
+        acc = acc + (x2.double() @ w2.double().t()).reshape(N, H, W, K).permute(0, 3, 1, 2)
     if emb:
         acc = acc + e.double()[:, :, None, None]
     acc = acc * alpha
@@ -319,6 +327,13 @@ PAIR_CASES = [
     dict(N=3, H=16, W=16, C=640, K=640, R=3, stride=2),                      # 16x16 -> 8x8: box spans 2 images, ragged N
     dict(N=16, H=8, W=8, C=1280, K=1280, R=3, stride=2, workspace=True),     # 8x8 -> 4x4: split-K
     dict(N=2, H=64, W=64, C=320, K=320, R=3, stride=2, y32="only"),          # 512^2 level: 64x64 -> 32x32
+    # ResBlock out conv + 1x1 skip projection of the block input as one contraction (second activation map, x2)
+    dict(N=16, H=32, W=32, C=320, K=320, R=3, C2=960, y32="only"),           # decoder, 32x32: cat 960 -> 320
+    dict(N=16, H=16, W=16, C=640, K=640, R=3, C2=320, y32="both"),           # encoder 320 -> 640
+    dict(N=16, H=8, W=8, C=1280, K=1280, R=3, C2=2560, workspace=True),      # 8x8 level: split-K, a split starts inside x2's blocks
+    dict(N=16, H=4, W=4, C=1280, K=1280, R=3, C2=2560, y32="only", workspace=True),  # 4x4 level
+    dict(N=3, H=16, W=16, C=640, K=640, R=3, C2=1920, y32="only"),           # ragged N (box spans 2 images)
+    dict(N=1, H=1, W=4096, C=640, K=320, R=1, C2=320),                       # two 1x1 terms (2-D maps)
 ]
 
 
@@ -358,6 +373,23 @@ def test_conv_auto_dispatch():
     assert path(N=16, H=32, W=32, C=64, K=64, R=3, stride=2) == L.PATH_GENERIC  # single-CTA kernel: no workspace to materialise into
 
 
+def test_conv_x2_term_only_where_the_pair_kernel_runs():
+    """a fused second term on a shape the CTA-pair kernel declines is reported as unsupported (the caller then issues two
+    launches), never silently routed to a kernel that would ignore x2"""
+    def ok(N, H, W, C, K, C2, **kw):
+        x, x2 = rnd(N * H * W, C, dt=BF), rnd(N * H * W, C2, dt=BF)
+        w = rnd(K, 9 * C + C2, dt=BF)
+        y = torch.empty(N * H * W, K, device=DEV, dtype=BF)
+        return ops.conv2d_supported(x, w, y, N=N, H=H, W=W, R=3, S=3, pad=1, x2=x2, **kw)
+    assert ok(16, 32, 32, 320, 320, 640)
+    assert not ok(1, 8, 8, 64, 64, 64)            # K % 160 != 0: single-CTA kernel territory
+    assert not ok(16, 32, 32, 320, 320, 72)       # C2 % 64 != 0
+    assert not ok(1, 8, 8, 320, 320, 640)         # too few units for a cluster launch, no workspace to split along K
+    with pytest.raises(RuntimeError):
+        x, x2 = rnd(64, 64, dt=BF), rnd(64, 64, dt=BF)
+        ops.conv2d(x, rnd(64, 9 * 64 + 64, dt=BF), torch.empty(64, 64, device=DEV, dtype=BF), N=1, H=8, W=8, R=3, S=3, pad=1, x2=x2)
+
+
 def test_conv_rejects_bad_descriptors():
     x = torch.empty(64, 64, device=DEV, dtype=BF)
     w = torch.empty(64, 64, device=DEV, dtype=BF)
@@ -390,6 +422,7 @@ PAIR_STATS_CASES = [
     dict(N=16, H=32, W=32, C=320, K=320, R=3, residual=True),                # two sub-tiles per A tile
     dict(N=3, H=16, W=16, C=1280, K=640, R=3, emb=True),                     # odd tile count
     dict(N=16, H=32, W=32, C=320, K=320, R=3, stride=2),                     # Downsample in place (element-strided map) + stats
+    dict(N=16, H=32, W=32, C=320, K=320, R=3, C2=640),                       # out conv + skip projection + stats
 ]
 
 
@@ -409,6 +442,10 @@ def test_conv_stats_and_groupnorm_apply(case, path=L.PATH_AUTO):
     x = rnd(M, C, dt=BF, seed=1)
     w = (rnd(K, R, R, C, dt=F32, seed=2) / math.sqrt(C * R * R)).to(BF)
     b = rnd(K, seed=3)
+    x2 = None
+    if case.get("C2"):  # fused second 1x1 term
+        x2 = rnd(M, case["C2"], dt=BF, seed=9)
+        w = torch.cat([w.reshape(K, -1), (rnd(K, case["C2"], seed=10) / math.sqrt(case["C2"])).to(BF)], 1).contiguous()
     e = rnd(N, K, dt=BF, seed=4) if case.get("emb") else None
     off, width = case.get("slot", (0, K))
     yb = rnd(Mo, width, dt=BF, seed=5)
@@ -419,7 +456,7 @@ def test_conv_stats_and_groupnorm_apply(case, path=L.PATH_AUTO):
     st = stb[:, off:off + K, :]
     ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV)
     ops.conv2d(x, w, y, N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=up, bias=b, emb=e, residual=res,
-               alpha=0.5 if case.get("inplace") else 1.0, workspace=ws, y32=y32, stats=st, path=path)
+               alpha=0.5 if case.get("inplace") else 1.0, workspace=ws, y32=y32, stats=st, path=path, x2=x2)
     t = y32.reshape(Mo // 128, 128, K)
     ref = torch.stack([t.sum(1), (t * t).sum(1)], -1)
     assert rel(st[..., 0], ref[..., 0]) < 1e-5 and rel(st[..., 1], ref[..., 1]) < 1e-5
@@ -429,7 +466,7 @@ def test_conv_stats_and_groupnorm_apply(case, path=L.PATH_AUTO):
     st1 = st.clone()
     if not case.get("inplace"):
         ops.conv2d(x, w, y, N=N, H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, upsample=up, bias=b, emb=e, residual=res,
-                   workspace=ws, y32=y32, stats=st, path=path)
+                   workspace=ws, y32=y32, stats=st, path=path, x2=x2)
         assert torch.equal(st, st1)
     for silu in (True, False):
         for src in (y32, y):
