@@ -302,9 +302,13 @@ __global__ void __launch_bounds__(GG_THREADS) gn_group_kernel(const T* __restric
 // GroupNorm as one streaming pass: the producer's GEMM epilogue already emitted, per 128-row tile and channel, the
 // (sum, sum of squares) of the values it stored (mkd_conv_desc.stats).  Prologue: per-channel totals of this sample
 // (fixed order: deterministic) -> 32 group statistics (one warp per group) -> per-channel scale / shift in smem; then
-// y = act(x * scale + shift) over this CTA's row chunk, 8 channels per thread, 4 rows in flight.
+// y = act(x * scale + shift) over this CTA's row chunk, 8 channels per thread, 4 rows per batch.
+// The kernel is latency-bound (a few hundred CTAs, each with a dependent prologue and 2-3 batches of rows), so what
+// matters is how many memory round trips sit one behind the other: the statistics of up to MAXR channels x 4 tiles per
+// thread are requested together and ahead of everything else, gamma / beta ride along, the first batch of x follows,
+// and inside the row loop batch i + 1 is requested before batch i is normalised and stored.
 template <typename T, typename TO, bool SILU>
-__global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ y, const float2* __restrict__ stats,
+__global__ void __launch_bounds__(512) gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ y, const float2* __restrict__ stats,
                                       int stats_ld, int tiles, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, int HW, int C, int groups, int ldx, int ldy,
                                       int rows_per_chunk, float eps) {
@@ -316,53 +320,100 @@ __global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ 
   __shared__ float2 gstat[64];   // (mean, rstd) per group
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int cgs = C / groups, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // the first batch of x loads does not depend on the statistics: issue it before the prologue so that its DRAM / L2
-  // latency overlaps the (dependent, three-barrier) statistics chain
   const int VX = C / 8, RY = blockDim.x / VX;
   const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
   const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
   const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
+  constexpr int MAXR = 4;  // channel rounds of the fast prologue: C <= MAXR * blockDim
+  const bool fast = C <= MAXR * (int)blockDim.x && blockDim.x < 2 * C;
+  float ga[MAXR], be[MAXR];
+  float2 tot[MAXR];
   float v[4][8];
-  if (ry < RY) {
+  if (fast) {
+    // statistics first (they head the dependent chain): rounds x 4 tiles in flight, summed in tile order per channel
+    const float2* sp = stats + (int64_t)n * tiles * stats_ld;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (r0 + ry + u * RY < r1) load8(xb + (int64_t)(r0 + ry + u * RY) * ldx, v[u]);
-  }
-  // per-channel totals of this sample's tile partials.  When the CTA has more threads than channels, G thread groups
-  // split the tiles (a 256^2 map has 512 of them); fixed partition and fixed summation order: deterministic.
-  const int G = blockDim.x >= 2 * C ? blockDim.x / C : 1;
-  for (int idx = threadIdx.x; idx < G * C; idx += blockDim.x) {
-    const int gq = idx / C, c = idx - gq * C;
-    const float2* p = stats + (int64_t)n * tiles * stats_ld + c;
-    float a = 0.f, b = 0.f;
-#pragma unroll 4
-    for (int k = gq; k < tiles; k += G) {
-      const float2 v = p[(int64_t)k * stats_ld];
-      a += v.x;
-      b += v.y;
-    }
-    csum[idx] = make_float2(a, b);
-  }
-  if (G > 1) {
-    __syncthreads();
-    float a = 0.f, b = 0.f;
-    if (threadIdx.x < C) {
-      for (int gq = 0; gq < G; ++gq) {
-        a += csum[gq * C + threadIdx.x].x;
-        b += csum[gq * C + threadIdx.x].y;
+    for (int rr = 0; rr < MAXR; ++rr) tot[rr] = make_float2(0.f, 0.f);
+    for (int k0 = 0; k0 < tiles; k0 += 4) {
+      float2 t[MAXR][4];
+#pragma unroll
+      for (int rr = 0; rr < MAXR; ++rr) {
+        const int c = threadIdx.x + rr * blockDim.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          t[rr][k] = (c < C && k0 + k < tiles) ? sp[(int64_t)(k0 + k) * stats_ld + c] : make_float2(0.f, 0.f);
+      }
+      if (k0 == 0) {
+#pragma unroll
+        for (int rr = 0; rr < MAXR; ++rr) {
+          const int c = threadIdx.x + rr * blockDim.x;
+          ga[rr] = c < C ? gamma[c] : 0.f;
+          be[rr] = c < C ? beta[c] : 0.f;
+        }
+        if (ry < RY) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (r0 + ry + u * RY < r1) load8(xb + (int64_t)(r0 + ry + u * RY) * ldx, v[u]);
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < MAXR; ++rr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tot[rr].x += t[rr][k].x;
+          tot[rr].y += t[rr][k].y;
+        }
       }
     }
-    __syncthreads();
-    if (threadIdx.x < C) csum[threadIdx.x] = make_float2(a, b);
+#pragma unroll
+    for (int rr = 0; rr < MAXR; ++rr) {
+      const int c = threadIdx.x + rr * blockDim.x;
+      if (c < C) csum[c] = tot[rr];
+    }
+  } else {
+    // the first batch of x loads does not depend on the statistics: issue it before the prologue so that its DRAM / L2
+    // latency overlaps the (dependent, three-barrier) statistics chain
+    if (ry < RY) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + ry + u * RY < r1) load8(xb + (int64_t)(r0 + ry + u * RY) * ldx, v[u]);
+    }
+    // per-channel totals of this sample's tile partials.  When the CTA has more threads than channels, G thread groups
+    // split the tiles (a 256^2 map has 512 of them); fixed partition and fixed summation order: deterministic.
+    const int G = blockDim.x >= 2 * C ? blockDim.x / C : 1;
+    for (int idx = threadIdx.x; idx < G * C; idx += blockDim.x) {
+      const int gq = idx / C, c = idx - gq * C;
+      const float2* p = stats + (int64_t)n * tiles * stats_ld + c;
+      float a = 0.f, b = 0.f;
+#pragma unroll 4
+      for (int k = gq; k < tiles; k += G) {
+        const float2 t = p[(int64_t)k * stats_ld];
+        a += t.x;
+        b += t.y;
+      }
+      csum[idx] = make_float2(a, b);
+    }
+    if (G > 1) {
+      __syncthreads();
+      float a = 0.f, b = 0.f;
+      if (threadIdx.x < C) {
+        for (int gq = 0; gq < G; ++gq) {
+          a += csum[gq * C + threadIdx.x].x;
+          b += csum[gq * C + threadIdx.x].y;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < C) csum[threadIdx.x] = make_float2(a, b);
+    }
   }
   __syncthreads();
   const float inv_cnt = 1.0f / ((float)cgs * (float)HW);
   for (int g = warp; g < groups; g += nwarps) {
     float a = 0.f, b = 0.f;
     for (int i = lane; i < cgs; i += 32) {
-      const float2 v = csum[g * cgs + i];
-      a += v.x;
-      b += v.y;
+      const float2 t = csum[g * cgs + i];
+      a += t.x;
+      b += t.y;
     }
     a = warp_sum(a);
     b = warp_sum(b);
@@ -373,11 +424,24 @@ __global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ 
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float2 ms = gstat[c / cgs];
-    const float sc = gamma[c] * ms.y;
-    scale[c] = sc;
-    shift[c] = beta[c] - ms.x * sc;
+  if (fast) {
+#pragma unroll
+    for (int rr = 0; rr < MAXR; ++rr) {
+      const int c = threadIdx.x + rr * blockDim.x;
+      if (c < C) {
+        const float2 ms = gstat[c / cgs];
+        const float sc = ga[rr] * ms.y;
+        scale[c] = sc;
+        shift[c] = be[rr] - ms.x * sc;
+      }
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float2 ms = gstat[c / cgs];
+      const float sc = gamma[c] * ms.y;
+      scale[c] = sc;
+      shift[c] = beta[c] - ms.x * sc;
+    }
   }
   __syncthreads();
   if (ry >= RY) return;
@@ -388,12 +452,12 @@ __global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ 
     sh[j] = shift[vx * 8 + j];
   }
   TO* yb = y + (int64_t)n * HW * ldy + vx * 8;
+  float w[4][8];  // the batch after the one being normalised
   for (int r = r0 + ry; r < r1; r += 4 * RY) {
-    if (r != r0 + ry) {  // (the first batch is already in registers)
+    const int rn = r + 4 * RY;
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (r + u * RY < r1) load8(xb + (int64_t)(r + u * RY) * ldx, v[u]);
-    }
+    for (int u = 0; u < 4; ++u)
+      if (rn + u * RY < r1) load8(xb + (int64_t)(rn + u * RY) * ldx, w[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (r + u * RY < r1) {
@@ -405,6 +469,10 @@ __global__ void gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ 
         store8(yb + (int64_t)(r + u * RY) * ldy, v[u]);
       }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[u][j] = w[u][j];
   }
 }
 
@@ -677,14 +745,21 @@ static int gn_apply_launch(const T* x, TO* y, int N, int HW, int C, int groups, 
   int threads = VX >= 256 ? VX : (256 / VX) * VX;
   threads = ((threads + 31) / 32) * 32;
   const int RY = threads / VX;
-  // ~2 CTAs per SM, each streaming at least 4 * RY rows (one full set of loads in flight per thread)
-  int nchunks = (2 * 148 + N - 1) / N;
+  const size_t smem = (size_t)(2 * C + 2 * (C > threads ? C : threads)) * sizeof(float);  // scale, shift, csum[G][C]
+  MKD_REQUIRE(smem <= 48 * 1024, MKD_E_INVALID, "groupnorm_apply: C=%d too large", C);
+  // ONE wave: as many chunks per sample as the CTAs that can be resident at once allow (a 19th chunk per sample at batch 16
+  // was a second wave of 8 CTAs that doubled the kernel's time), each streaming at least 4 * RY rows
+  int occ = 0;
+  {
+    cudaError_t e = silu ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_apply_stats_kernel<T, TO, true>, threads, smem)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_apply_stats_kernel<T, TO, false>, threads, smem);
+    MKD_REQUIRE(e == cudaSuccess && occ > 0, MKD_E_CUDA, "groupnorm_apply: occupancy query failed");
+  }
+  int nchunks = occ * num_sms() / N;
   if (nchunks > HW / (4 * RY)) nchunks = HW / (4 * RY);
   if (nchunks < 1) nchunks = 1;
   const int rows = (HW + nchunks - 1) / nchunks;
   nchunks = (HW + rows - 1) / rows;
-  const size_t smem = (size_t)(2 * C + 2 * (C > threads ? C : threads)) * sizeof(float);  // scale, shift, csum[G][C]
-  MKD_REQUIRE(smem <= 48 * 1024, MKD_E_INVALID, "groupnorm_apply: C=%d too large", C);
   dim3 grid(nchunks, N);
   if (silu)
     MKD_LAUNCH_OK(launch_pdl(gn_apply_stats_kernel<T, TO, true>, grid, dim3(threads), smem, st, x, y, stats, stats_ld, tiles, gamma, beta, HW, C,
@@ -701,7 +776,7 @@ extern "C" int mkd_groupnorm_apply(const void* x, void* y, int x_dtype, int y_dt
                                    const float* stats, int stats_ld, int tiles_per_sample, mkd_stream_t stream) {
   MKD_REQUIRE(x && y && gamma && beta && stats && N > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64, MKD_E_INVALID,
               "groupnorm_apply: bad args");
-  MKD_REQUIRE(C % groups == 0 && C % 8 == 0 && C <= 8 * 1024, MKD_E_INVALID,
+  MKD_REQUIRE(C % groups == 0 && C % 8 == 0 && C <= 8 * 512, MKD_E_INVALID,
               "groupnorm_apply: C=%d must be a multiple of groups=%d and of 8", C, groups);
   MKD_REQUIRE(N <= 65535 && HW == 128 * tiles_per_sample && stats_ld >= C, MKD_E_INVALID,
               "groupnorm_apply: HW=%d must be 128 * tiles_per_sample=%d, stats_ld=%d >= C", HW, tiles_per_sample, stats_ld);
