@@ -1025,7 +1025,9 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
     const bool can_split = d->workspace && !d->stats && kblocks >= 32;
     pl.nsub = 1;
     if (units2 >= 48 && kblocks >= 16) pl.nsub = 2;
-    else if (units2 > 0 && units1 < 37 && can_split && kblocks >= 64) pl.nsub = 2;
+    // (a single pair of row tiles — the 4x4 level at batch 16 — splits better as 8 narrow units x 9 than as 4 wide x 15:
+    // the fp32 partial epilogue of a 320-wide unit costs more than its 12 k-blocks, and the reducer reads 9 partials, not 15)
+    else if (units2 > 0 && units1 >= 16 && units1 < 37 && can_split && kblocks >= 64) pl.nsub = 2;
     const int units = pl.nsub == 2 ? units2 : units1;
     if (units < 37 && can_split) {
       int s = 74 / units;
