@@ -1,10 +1,9 @@
 // SpatialTransformer attention (self: Nkv = Nq = H*W; cross: Nkv = 77 text tokens), flash-style:
 // the Nq x Nkv score matrix never leaves the SM, softmax statistics are fp32 (upstream _ATTN_PRECISION fp32).
 //
-//   attn_mma_kernel<DP>  bf16 production kernel: 64 queries per CTA (4 warps x 16 rows), K/V streamed through a
-//                        double-buffered cp.async smem ring in tiles of 64 keys, QK^T and PV on the warp-level
-//                        tensor-core path (mma.sync m16n8k16, fp32 accumulate), online softmax in registers.
-//   attn_simt_kernel<T>  one warp per query, used by the fp32 check mode (and any head dim the mma kernel lacks).
+//   attention_tcgen05.cu bf16 production kernels (tcgen05 / TMEM / TMA); this file dispatches to them.
+//   attn_simt_kernel<T>  one warp per query: the fp32 check mode, head dims > 160 (the VAE's 512-wide head), CLIP's causal mask.
+//   attn_mma_kernel<DP>  round-0 warp-level kernel (mma.sync m16n8k16): compiled only into MKD_TRACE=1 builds, for A/B runs.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -61,6 +60,7 @@ __global__ void attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ 
   }
 }
 
+#ifdef MKD_ENABLE_TRACE  // the round-0 warp-level mma.sync kernel: A/B builds only (MKD_ATTN_MMA=1); the shipped library has no such path
 // -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -269,10 +269,13 @@ int launch_mma(const bf16* q, const bf16* k, const bf16* v, bf16* o, int B, int 
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
+#endif  // MKD_ENABLE_TRACE
+#ifdef MKD_ENABLE_TRACE
 bool attn_force_mma() {
   static const int v = debug_switch("MKD_ATTN_MMA", 0);  // trace builds: 1 = the mma.sync kernel for every head dim (A/B runs)
   return v == 1;
 }
+#endif
 }  // namespace
 
 extern "C" int mkd_attention(const void* q, const void* k, const void* v, void* o, int dtype, int B, int heads, int Nq,
@@ -289,16 +292,19 @@ extern "C" int mkd_attention(const void* q, const void* k, const void* v, void* 
   if (dtype == MKD_BF16 && d <= 160) {
     const bf16 *qq = (const bf16*)q, *kk = (const bf16*)k, *vv = (const bf16*)v;
     bf16* oo = (bf16*)o;
-    // production path: tcgen05 / TMEM / TMA flash attention (attention_tcgen05.cu); MKD_ATTN=mma selects the older
-    // warp-level mma.sync kernel below (kept for A/B measurements)
-    if (attention_tcgen05_supported(d, ldq, ldk, ldv) && !attn_force_mma())
-      return attention_tcgen05(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-    if (d <= 16) return launch_mma<16>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-    if (d <= 32) return launch_mma<32>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-    if (d <= 48) return launch_mma<48>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-    if (d <= 64) return launch_mma<64>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-    if (d <= 80) return launch_mma<80>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
-    return launch_mma<160>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+    // the tcgen05 / TMEM / TMA flash attention (attention_tcgen05.cu) takes every head dim admitted above
+#ifdef MKD_ENABLE_TRACE
+    if (attn_force_mma()) {  // A/B builds: the older warp-level mma.sync kernel
+      if (d <= 16) return launch_mma<16>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+      if (d <= 32) return launch_mma<32>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+      if (d <= 48) return launch_mma<48>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+      if (d <= 64) return launch_mma<64>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+      if (d <= 80) return launch_mma<80>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+      return launch_mma<160>(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
+    }
+#endif
+    MKD_REQUIRE(attention_tcgen05_supported(d, ldq, ldk, ldv), MKD_E_INVALID, "attention: head dim %d not supported on the tensor-core kernel", d);
+    return attention_tcgen05(qq, kk, vv, oo, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, scale, st);
   }
   const int warps = 4;
   size_t smem = (size_t)warps * (d + Nkv) * sizeof(float);
