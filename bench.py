@@ -14,7 +14,7 @@ every step), then 50 x [UNet + ControlNet eval -> fused DDIM update].
   roofline  tensor-core roofline of the dominant kernel (tcgen05 implicit-GEMM): algorithmic FLOPs of its launches in
             one UNet+ControlNet eval / their summed CUDA-event durations (single-stream pass, launches queued behind
             a blocker so no host gap is timed), vs the measured sustained bf16 peak; `traffic` = average DRAM bytes per
-            launch of that kernel from the committed ncu pass (profiles/r01_ncu_families.json); `others` = the same
+            launch of that kernel from the committed ncu pass (profiles/r02_ncu_families.json); `others` = the same
             for attention (TFLOP/s) and the norm kernels (GB/s against the measured HBM copy bandwidth)
   cpu_baseline  the oracle (a port: the reference's ldm/cldm dependency is not vendored) on the host cores, bounded sample
 --impl reference: the reference's CPU path = the same oracle, timed on the box's host cores (rank 0 only).

@@ -67,6 +67,44 @@ def test_fused_apply_model_plumbing(faked, pair, B, h):
     assert rel(x0, r0) < 2e-5
 
 
+def test_fused_skip_projection_plumbing(faked, tiny_params, monkeypatch):
+    """ResBlock out conv + 1x1 skip_connection as ONE contraction (mkd_conv_desc.x2): weight rows [3][3][C_out] followed by the
+    C_in columns of the projection, biases summed, the block input routed as the second operand.  The kernel takes the term on
+    yaml-size nets only (K % 160 == 0), so the support query is forced here: this is about the host plumbing."""
+    o = OracleControlLDM(control_params=tiny_params, unet_params=tiny_params).eval()
+    sd = seeded_state_dict(o, 0)
+    cond, x = cond_x(2, 8, seed=5)
+    t = torch.tensor([981, 41])
+    seen = []
+    real = fake_ops.conv2d
+
+    def spy(x2d, w, y2d, **kw):
+        if kw.get("x2") is not None:
+            seen.append((w.shape[0], x2d.shape[1], kw["x2"].shape[1]))
+            assert w.shape[1] == 9 * x2d.shape[1] + kw["x2"].shape[1] and kw.get("residual") is None
+        return real(x2d, w, y2d, **kw)
+
+    monkeypatch.setattr(ops, "conv2d", spy)
+    monkeypatch.setattr(ops, "conv2d_supported", lambda *a, **k: True)
+    m = B200ControlLDM(tiny_params, tiny_params, dtype=torch.bfloat16, device="cpu").load_state_dict(sd)
+    un, cn = m.model.diffusion_model, m.control_model
+    with torch.no_grad():
+        ref = o.apply_model(x, t, cond)
+        fused = m.apply_model(x, t, cond)
+    n_proj = sum(1 for net in (un, cn) for l in net._res_layers() if l[2] != l[3])
+    assert len(seen) == n_proj > 0, (len(seen), n_proj)           # every channel-changing ResBlock took the fused form
+    un.fuse_skip = cn.fuse_skip = False
+    m.invalidate_cond_cache()
+    seen.clear()
+    with torch.no_grad():
+        plain = m.apply_model(x, t, cond)
+    assert not seen
+    assert rel(fused, ref) < 1.5e-2 and rel(plain, ref) < 1.5e-2 and rel(fused, plain) < 1.5e-2, (rel(fused, ref), rel(plain, ref))
+    # fp32 check mode never fuses (the generic kernel has no second term): no c2sk weights are even built
+    m32 = B200ControlLDM(tiny_params, tiny_params, dtype=torch.float32, device="cpu").load_state_dict(sd)
+    assert not any(k.endswith(".c2sk.w") for k in m32.model.diffusion_model.w)
+
+
 def test_bf16_path_plumbing_with_fp32_side_buffers(faked, tiny_params):
     """dtype=bf16 takes the lo/hi (bf16 operand + fp32 trunk copy) code paths; the fakes round on store like the kernels"""
     o = OracleControlLDM(control_params=tiny_params, unet_params=tiny_params).eval()
