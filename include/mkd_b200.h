@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 8
+#define MKD_ABI_VERSION 9
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 
@@ -92,22 +92,26 @@ int mkd_add(const void* a, const void* b, void* y, int dtype, int64_t M, int C, 
  * UNet.out (reached from makeup_diffuse.py:164-168).  Statistics in fp32 over (C/groups * HW) per sample.
  * x_dtype / y_dtype may differ: tensors that are not tensor-core operands (the residual trunk, ResBlock `h`) are
  * kept in fp32 by the bf16 path so that their rounding does not accumulate; norm outputs (GEMM operands) are bf16.
- * workspace: >= mkd_groupnorm_workspace_bytes(N, groups) bytes, fp32-aligned. */
+ * workspace: >= mkd_groupnorm_workspace_bytes(N, groups) bytes, fp32-aligned.
+ * wgroups (ABI v9; 1 = none): weight groups as in mkd_conv_desc.wgroups — with wgroups == 2 the samples n >= N/2 (N even) use
+ * gamma[C .. 2C) / beta[C .. 2C): the same layer of two networks on two stacked batches in one launch.  Same parameter on
+ * mkd_groupnorm_apply and on mkd_layernorm (rows m >= M/2, M even). */
 size_t mkd_groupnorm_workspace_bytes(int N, int groups);
 int mkd_groupnorm(const void* x, void* y, int x_dtype, int y_dtype, int N, int HW, int C, int groups, int ldx,
                   int ldy, const float* gamma, const float* beta, float eps, int silu, void* workspace,
-                  size_t workspace_bytes, mkd_stream_t stream);
+                  size_t workspace_bytes, int wgroups, mkd_stream_t stream);
+
 
 /* GroupNorm as ONE streaming pass, for inputs whose producer (mkd_conv2d with `stats`) already emitted per-tile
  * column sums: stats[((n * tiles_per_sample + t) * stats_ld + c) * 2 + {0,1}], HW == 128 * tiles_per_sample.
  * Same arithmetic as mkd_groupnorm otherwise (fp32 statistics, var = E[x^2] - mean^2 clamped at 0). */
 int mkd_groupnorm_apply(const void* x, void* y, int x_dtype, int y_dtype, int N, int HW, int C, int groups, int ldx,
                         int ldy, const float* gamma, const float* beta, float eps, int silu, const float* stats,
-                        int stats_ld, int tiles_per_sample, mkd_stream_t stream);
+                        int stats_ld, int tiles_per_sample, int wgroups, mkd_stream_t stream);
 
 /* ---- LayerNorm over the last dim (BasicTransformerBlock.norm1/2/3) ---------------------------------------- */
 int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,
-                  const float* gamma, const float* beta, float eps, mkd_stream_t stream);
+                  const float* gamma, const float* beta, float eps, int wgroups, mkd_stream_t stream);
 
 /* ---- row softmax y = softmax(scale * x) over the last dim (fp32 statistics) ----------------------------------------
  * The VAE decoder's mid.attn_1 (upstream AttnBlock: one 512-wide head over all pixels, reached from decode_first_stage,
@@ -174,6 +178,14 @@ typedef struct mkd_conv_desc {
    * issues the two layers separately). */
   const void* x2;
   int C2, ldx2;
+  /* weight groups (ABI v9; 0 or 1 = none, 2 = two groups): the output rows are split in `wgroups` equal, contiguous parts and
+   * part g is computed with weight rows [g*K, (g+1)*K) of `w` and bias[g*K .. (g+1)*K): ONE launch evaluates the same layer
+   * of two networks on two stacked batches — the ControlNet trunk is a copy of the UNet encoder (cldm.ControlNet.__init__
+   * mirrors UNetModel's input_blocks / middle_block), and makeup_diffuse.py:164-168 runs both on the same x_t every step.
+   * `w` holds wgroups*K rows, `bias` wgroups*K values; emb / residual / y / stats are indexed by output row as always.
+   * Only the tensor-core CTA-pair kernel takes it, with whole 256-row tile pairs per part: mkd_conv2d_path() returns
+   * MKD_E_INVALID otherwise and the caller issues one launch per part on row / weight-row slices. */
+  int wgroups;
 } mkd_conv_desc;
 
 int mkd_conv2d(const mkd_conv_desc* d, mkd_stream_t stream);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmkd_b200.so")
 MKD_BF16, MKD_F32 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05, PATH_TCGEN05_SINGLE, PATH_TCGEN05_PAIR = 0, 1, 2, 3, 4
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class ConvDesc(C.Structure):
@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ("stats", C.c_void_p), ("stats_ld", C.c_int),
         ("pad_hi_extra", C.c_int),
         ("x2", C.c_void_p), ("C2", C.c_int), ("ldx2", C.c_int),
+        ("wgroups", C.c_int),
     ]
 
 
@@ -56,10 +57,10 @@ PROTOTYPES = {
     "mkd_geglu": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "mkd_add": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp]),
     "mkd_groupnorm_workspace_bytes": (_sz, [_i, _i]),
-    "mkd_groupnorm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _sz, _vp]),
-    "mkd_groupnorm_apply": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _i, _vp]),
+    "mkd_groupnorm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _sz, _i, _vp]),
+    "mkd_groupnorm_apply": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _i, _i, _vp]),
     "mkd_softmax_rows": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _f, _vp]),
-    "mkd_layernorm": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _vp, _vp, _f, _vp]),
+    "mkd_layernorm": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _vp, _vp, _f, _i, _vp]),
     "mkd_conv2d": (_i, [C.POINTER(ConvDesc), _vp]),
     "mkd_conv2d_path": (_i, [C.POINTER(ConvDesc)]),
     "mkd_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),

@@ -213,6 +213,10 @@ static int validate(const mkd_conv_desc* d) {
                     d->path != MKD_PATH_TCGEN05_SINGLE,
                 MKD_E_INVALID, "conv2d: the x2 term is bf16, stride 1, no upsample / GEGLU, tensor-core CTA-pair kernel only");
   }
+  MKD_REQUIRE(d->wgroups >= 0 && d->wgroups <= 2, MKD_E_INVALID, "conv2d: wgroups must be 0, 1 or 2");
+  if (d->wgroups == 2)
+    MKD_REQUIRE(d->dtype == MKD_BF16 && d->path != MKD_PATH_GENERIC && d->path != MKD_PATH_TCGEN05_SINGLE && d->N % 2 == 0, MKD_E_INVALID,
+                "conv2d: weight groups are bf16, even batch, tensor-core CTA-pair kernel only");
   if (d->act == MKD_ACT_GEGLU) {
     MKD_REQUIRE(d->K % 2 == 0 && d->geglu_block > 0 && (d->K / 2) % d->geglu_block == 0, MKD_E_INVALID,
                 "conv2d: GEGLU needs K even and K/2 %% geglu_block == 0");
@@ -231,7 +235,7 @@ extern "C" int mkd_conv2d_path(const mkd_conv_desc* d) {
   if (rc) return rc;
   if (d->path == MKD_PATH_GENERIC) return MKD_PATH_GENERIC;
   bool ok = mkd::conv2d_tcgen05_supported(d);
-  if (d->x2 && !ok) return MKD_E_INVALID;  // no other kernel takes the second term: the caller issues the two layers separately
+  if ((d->x2 || d->wgroups == 2) && !ok) return MKD_E_INVALID;  // no other kernel takes the second term: the caller issues the two layers separately
   if (d->path >= MKD_PATH_TCGEN05) {  // forced tensor-core kernel (either of the two)
     if (!ok) return MKD_E_INVALID;  // conv2d_tcgen05_supported() left the reason in mkd_last_error()
     return MKD_PATH_TCGEN05;

@@ -68,6 +68,7 @@ __device__ __forceinline__ int fdiv(int n, FastDiv f) { return f.m ? (int)__umul
 struct PairP {
   // main loop
   int kblocks, kb_per_split;
+  int wg_pairs, wg_rows;  // weight groups: row pairs >= wg_pairs use weight rows / bias offset by wg_rows (else wg_pairs = INT_MAX)
   int kb_main;  // k-blocks of the filter-tap walk over `x`; blocks [kb_main, kblocks) read the second 1x1 term `x2` (amap2)
   int conv, cblocks, S, pad, stride;  // stride 2: the activation map walks the input with element strides (1, 2, 2, 1)
   int Wb, Hb, Nb, tiles_w, tiles_h;
@@ -491,7 +492,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       const int tap0 = fdiv(t.kb0, p.d_cblocks);
       int cb = t.kb0 - tap0 * p.cblocks, r = fdiv(tap0, p.d_S);
       int sx = tap0 - r * p.S;
-      const int nb = t.n_unit * (NSUB * UN) + (int)rank * (UN / 2);  // this CTA's half of sub-tile 0's weight rows
+      // this CTA's half of sub-tile 0's weight rows (second weight group: the same rows K further down)
+      const int nb = t.n_unit * (NSUB * UN) + (int)rank * (UN / 2) + (t.m_pair >= p.wg_pairs ? p.wg_rows : 0);
 #pragma unroll 1
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
         if (lane == 0) PAIR_PROG(0, u * 1000 + kb);
@@ -677,7 +679,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant
       if (wt < ACCW / 4 && u_ < p.num_units) {
         const Unit t_ = decode_unit(p, u_);
         const int col = t_.n_unit * ACCW + wt * 4;
-        if (p.bias) v4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (p.bias) v4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + (t_.m_pair >= p.wg_pairs ? p.wg_rows : 0)));
         if (MODE == MODE_PLAIN && p.emb && p.emb_uniform) {
           const int mt = min(2 * t_.m_pair + (int)rank, p.m_tiles - 1);
           const uint2 e = __ldg(reinterpret_cast<const uint2*>(p.emb + (int64_t)fdiv(mt * BM, p.d_ppi) * p.lde + col));
@@ -979,6 +981,7 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
   if (d->x2 && (d->stride != 1 || d->C2 <= 0 || d->C2 % BK || d->ldx2 % 8 || d->ldx2 < d->C2 || !aligned16(d->x2) ||
                 d->act == MKD_ACT_GEGLU))
     return false;
+  if (d->wgroups > 2 || d->wgroups < 0) return false;
   pl.conv = d->R == 3;
   pl.P = d->H / d->stride;
   pl.Q = d->W / d->stride;
@@ -999,6 +1002,8 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
     pl.m_tiles = (pl.M + BM - 1) / BM;
   }
   const int m_pairs = (pl.m_tiles + 1) / 2, kblocks = pl.Ktot / BK;
+  // weight groups: each part of the rows is a whole number of 256-row tile pairs
+  if (d->wgroups == 2 && (pl.M % (4 * BM) != 0 || pl.m_tiles % 4 != 0 || d->N % 2 != 0)) return false;
   // the kernel divides by launch constants with umulhi(n, ceil(2^32 / d)), exact while n * d < 2^32
   {
     const uint64_t lim = 1ull << 32, units_max = (uint64_t)m_pairs * (d->K / 160 + 1) * 16 + 2 * num_sms();
@@ -1107,7 +1112,7 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)pl.Ktot, (cuuint64_t)d->K};
+    cuuint64_t dims[2] = {(cuuint64_t)pl.Ktot, (cuuint64_t)d->K * (d->wgroups == 2 ? 2 : 1)};
     cuuint64_t str[1] = {(cuuint64_t)pl.Ktot * 2};
     cuuint32_t box[2] = {BK, (cuuint32_t)(UN / 2)};
     rc = encode(&bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1117,6 +1122,8 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   PairP p = {};
   p.kblocks = pl.Ktot / BK;
   p.kb_main = d->R * d->S * d->C / BK;
+  p.wg_pairs = d->wgroups == 2 ? (pl.m_tiles + 1) / 4 : 0x7fffffff;
+  p.wg_rows = d->K;
   p.kb_per_split = pl.kb_per_split;
   p.conv = pl.conv;
   p.cblocks = d->C / BK;
@@ -1183,7 +1190,7 @@ int launch(const mkd_conv_desc* d, const PairPlan& pl, cudaStream_t stream) {
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = p.num_units < max_pairs ? p.num_units : max_pairs;
-  l2_prefetch_plan((unsigned long long)d->K * pl.Ktot * 2, 2 * pairs, p.w_bytes, p.w_share);
+  l2_prefetch_plan((unsigned long long)d->K * pl.Ktot * 2 * (d->wgroups == 2 ? 2 : 1), 2 * pairs, p.w_bytes, p.w_share);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);

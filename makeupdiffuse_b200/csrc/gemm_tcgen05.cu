@@ -51,6 +51,7 @@ struct EpiP {
   float* partial;    // split-K workspace or nullptr
   float2* stats;     // optional per-(128-row tile, channel) partial (sum, sum of squares) of the stored values
   int stats_ld;      // float2 elements per tile row of `stats`
+  int wg_row;        // split-K reducer only: rows >= wg_row belong to the second weight group (bias offset by n_rows); else INT_MAX
 };
 
 struct MainP {
@@ -904,8 +905,10 @@ __global__ void splitk_epilogue_kernel(EpiP ep, int splits) {
   const int gw = ep.act == MKD_ACT_GEGLU ? 16 : 8;  // channels per thread
   const int groups = ep.n_rows / gw;
   const int64_t total = (int64_t)ep.M * groups;
+  const float* const bias0 = ep.bias;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / groups), n = (int)(i % groups) * gw;
+    ep.bias = (bias0 && m >= ep.wg_row) ? bias0 + ep.n_rows : bias0;  // second weight group (mkd_conv_desc.wgroups)
     auto gather = [&](int col, float (&v)[16]) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -1226,6 +1229,7 @@ int launch(const mkd_conv_desc* d, const Geometry& g, cudaStream_t stream) {
   ep.y32 = d->y32; ep.ldy32 = d->ldy32; ep.res_f32 = d->residual_dtype == MKD_F32;
   ep.partial = splits > 1 ? (float*)d->workspace : nullptr;
   ep.stats = reinterpret_cast<float2*>(d->stats); ep.stats_ld = d->stats_ld;
+  ep.wg_row = 0x7fffffff;
 
   mp.m_tiles = g.m_tiles;
   mp.n_tiles = n_groups;
@@ -1345,6 +1349,7 @@ int splitk_reduce(const mkd_conv_desc* d, int M, int pix_per_img, int splits, cu
   ep.y32 = d->y32; ep.ldy32 = d->ldy32; ep.res_f32 = d->residual_dtype == MKD_F32;
   ep.partial = (float*)d->workspace;
   ep.stats = nullptr; ep.stats_ld = 0;
+  ep.wg_row = d->wgroups == 2 ? M / 2 : 0x7fffffff;
   int64_t total = (int64_t)M * (d->K / (d->act == MKD_ACT_GEGLU ? 16 : 8));
   int blocks = (int)((total + 127) / 128);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -1360,6 +1365,11 @@ static bool pair_takes_strided(const mkd_conv_desc* d) {
 }
 
 bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
+  if (d->wgroups == 2) {  // weight groups: the CTA-pair kernel or nothing (the caller then launches once per part)
+    if (d->path != MKD_PATH_TCGEN05_SINGLE && !d->upsample && conv2d_pair_supported(d, d->path == MKD_PATH_TCGEN05_PAIR)) return true;
+    set_error("conv2d: weight groups need the CTA-pair kernel, which declined this shape");
+    return false;
+  }
   if (d->x2) {  // second 1x1 term: the CTA-pair kernel or nothing
     if (d->path != MKD_PATH_TCGEN05_SINGLE && d->stride == 1 && !d->upsample && conv2d_pair_supported(d, d->path == MKD_PATH_TCGEN05_PAIR)) return true;
     set_error("conv2d: the x2 term needs the CTA-pair kernel, which declined this shape");
@@ -1378,7 +1388,7 @@ bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
 }
 
 int conv2d_tcgen05(const mkd_conv_desc* d_in, cudaStream_t stream) {
-  if (d_in->x2 || pair_takes_strided(d_in)) return conv2d_pair(d_in, d_in->path == MKD_PATH_TCGEN05_PAIR, stream);
+  if (d_in->wgroups == 2 || d_in->x2 || pair_takes_strided(d_in)) return conv2d_pair(d_in, d_in->path == MKD_PATH_TCGEN05_PAIR, stream);
   Geometry g;
   MKD_REQUIRE(geometry(d_in, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
   mkd_conv_desc dd;

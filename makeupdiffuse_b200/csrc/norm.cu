@@ -77,12 +77,13 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ pa
 template <typename T, typename TO, bool SILU>
 __global__ void gn_apply_kernel(const T* __restrict__ x, TO* __restrict__ y, const float2* __restrict__ partial,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
-                                int groups, int ldx, int ldy, int rows_per_chunk, int nchunks, float eps) {
+                                int groups, int ldx, int ldy, int rows_per_chunk, int nchunks, float eps, long long wsplit) {
   pdl_wait();
   extern __shared__ float sm[];  // scale[C], shift[C]
   float* scale = sm;
   float* shift = sm + C;
   const int n = blockIdx.y, chunk = blockIdx.x;
+  if (n >= wsplit) { gamma += C; beta += C; }  // second weight group (mkd_groupnorm wgroups)
   const int cg = C / groups;
   const float inv_cnt = 1.0f / ((float)cg * (float)HW);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -136,7 +137,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, TO* __restrict__ y, con
 template <typename T, typename TO, bool SILU>
 __global__ void gn_cluster_kernel(const T* __restrict__ x, TO* __restrict__ y, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, int HW, int C, int groups, int ldx, int ldy,
-                                  int rows_per_chunk, float eps) {
+                                  int rows_per_chunk, float eps, long long wsplit) {
   pdl_wait();
   extern __shared__ float sm[];      // phase 1: [2][RY][C] ; phase 2: scale[C], shift[C]
   __shared__ float2 part[64];        // this CTA's (sum, sumsq) per group — read by the whole cluster via DSMEM
@@ -144,6 +145,7 @@ __global__ void gn_cluster_kernel(const T* __restrict__ x, TO* __restrict__ y, c
   const int VX = C / 8, RY = blockDim.x / VX;
   const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  if (n >= wsplit) { gamma += C; beta += C; }  // second weight group (mkd_groupnorm wgroups)
   const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
   const T* xb = x + (int64_t)n * HW * ldx + vx * 8;
   float s[8], q[8];
@@ -242,10 +244,11 @@ constexpr int GG_THREADS = 128, GG_VPT = 5;
 template <typename T, typename TO, bool SILU>
 __global__ void __launch_bounds__(GG_THREADS) gn_group_kernel(const T* __restrict__ x, TO* __restrict__ y,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              int HW, int C, int groups, int ldx, int ldy, float eps) {
+                                                              int HW, int C, int groups, int ldx, int ldy, float eps, long long wsplit) {
   pdl_wait();
   __shared__ float red[2][GG_THREADS / 32];
   const int g = blockIdx.x, n = blockIdx.y;
+  if (n >= wsplit) { gamma += C; beta += C; }  // second weight group (mkd_groupnorm wgroups)
   const int cgs = C / groups, vpr = cgs / 8, nv = HW * vpr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const T* xb = x + (int64_t)n * HW * ldx + g * cgs;
@@ -311,7 +314,7 @@ template <typename T, typename TO, bool SILU>
 __global__ void __launch_bounds__(512) gn_apply_stats_kernel(const T* __restrict__ x, TO* __restrict__ y, const float2* __restrict__ stats,
                                       int stats_ld, int tiles, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, int HW, int C, int groups, int ldx, int ldy,
-                                      int rows_per_chunk, float eps) {
+                                      int rows_per_chunk, float eps, long long wsplit) {
   pdl_wait();
   extern __shared__ float sm[];  // scale[C], shift[C], then float2 csum[C] (dead after the prologue)
   float* scale = sm;
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(512) gn_apply_stats_kernel(const T* __restrict
   float2* csum = reinterpret_cast<float2*>(sm + 2 * C);
   __shared__ float2 gstat[64];   // (mean, rstd) per group
   const int n = blockIdx.y, chunk = blockIdx.x;
+  if (n >= wsplit) { gamma += C; beta += C; }  // second weight group (mkd_groupnorm wgroups)
   const int cgs = C / groups, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int VX = C / 8, RY = blockDim.x / VX;
   const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
@@ -481,10 +485,11 @@ __global__ void __launch_bounds__(512) gn_apply_stats_kernel(const T* __restrict
 constexpr int LN_VPL = 8;
 template <typename T, typename TO>
 __global__ void layernorm_kernel(const T* __restrict__ x, TO* __restrict__ y, int64_t M, int C, int ldx, int ldy,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long wsplit) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= wsplit) { gamma += C; beta += C; }  // second weight group (mkd_layernorm wgroups)
   if (row >= M) return;
   const int nv = C / 8;
   float v[LN_VPL][8];
@@ -532,11 +537,12 @@ __global__ void layernorm_kernel(const T* __restrict__ x, TO* __restrict__ y, in
 template <typename T, typename TO, int LPR>
 __global__ void __launch_bounds__(256) layernorm5_kernel(const T* __restrict__ x, TO* __restrict__ y, int64_t M, int ldx,
                                                          int ldy, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, float eps) {
+                                                         const float* __restrict__ beta, float eps, long long wsplit) {
   pdl_wait();
   constexpr int RPW = 32 / LPR, C = 40 * LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  if (row >= wsplit) { gamma += C; beta += C; }  // second weight group (mkd_layernorm wgroups)
   const bool ok = row < M;  // inactive lanes still take part in the shuffles
   float v[5][8];
   float s = 0.f;
@@ -626,11 +632,11 @@ __global__ void softmax_rows_kernel(const T* __restrict__ x, TO* __restrict__ y,
 
 template <typename T, typename TO>
 static bool layernorm5_launch(const T* x, TO* y, int64_t M, int C, int ldx, int ldy, const float* gamma, const float* beta,
-                              float eps, cudaStream_t st, cudaError_t* err) {
+                              float eps, long long wsplit, cudaStream_t st, cudaError_t* err) {
   const int warps = 8;
   auto go = [&](auto kernel, int rpw) {
     const int64_t rows_per_cta = (int64_t)warps * rpw;
-    *err = launch_pdl(kernel, dim3((unsigned)((M + rows_per_cta - 1) / rows_per_cta)), dim3(warps * 32), 0, st, x, y, M, ldx, ldy, gamma, beta, eps);
+    *err = launch_pdl(kernel, dim3((unsigned)((M + rows_per_cta - 1) / rows_per_cta)), dim3(warps * 32), 0, st, x, y, M, ldx, ldy, gamma, beta, eps, wsplit);
     return true;
   };
   if (C == 320) return go(layernorm5_kernel<T, TO, 8>, 4);
@@ -646,7 +652,7 @@ extern "C" size_t mkd_groupnorm_workspace_bytes(int N, int groups) {
 
 template <typename T, typename TO>
 static int groupnorm_launch(const T* x, TO* y, int N, int HW, int C, int groups, int ldx, int ldy, const float* gamma,
-                            const float* beta, float eps, int silu, float2* partial, cudaStream_t st) {
+                            const float* beta, float eps, int silu, float2* partial, long long wsplit, cudaStream_t st) {
   const int VX = C / 8;
   int threads = VX >= 256 ? VX : (256 / VX) * VX;  // whole number of row lanes
   threads = ((threads + 31) / 32) * 32;
@@ -655,9 +661,9 @@ static int groupnorm_launch(const T* x, TO* y, int N, int HW, int C, int groups,
     // small maps: one CTA per (sample, group), the group lives in registers
     dim3 grid(groups, N);
     if (silu)
-      MKD_LAUNCH_OK(launch_pdl(gn_group_kernel<T, TO, true>, grid, dim3(GG_THREADS), 0, st, x, y, gamma, beta, HW, C, groups, ldx, ldy, eps));
+      MKD_LAUNCH_OK(launch_pdl(gn_group_kernel<T, TO, true>, grid, dim3(GG_THREADS), 0, st, x, y, gamma, beta, HW, C, groups, ldx, ldy, eps, wsplit));
     else
-      MKD_LAUNCH_OK(launch_pdl(gn_group_kernel<T, TO, false>, grid, dim3(GG_THREADS), 0, st, x, y, gamma, beta, HW, C, groups, ldx, ldy, eps));
+      MKD_LAUNCH_OK(launch_pdl(gn_group_kernel<T, TO, false>, grid, dim3(GG_THREADS), 0, st, x, y, gamma, beta, HW, C, groups, ldx, ldy, eps, wsplit));
     MKD_CHECK_LAUNCH();
     return MKD_OK;
   }
@@ -684,8 +690,8 @@ static int groupnorm_launch(const T* x, TO* y, int N, int HW, int C, int groups,
       attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
       cfg.attrs = attr;
       cfg.numAttrs = 2;
-      cudaError_t e = silu ? cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T, TO, true>, x, y, gamma, beta, HW, C, groups, ldx, ldy, rows, eps)
-                           : cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T, TO, false>, x, y, gamma, beta, HW, C, groups, ldx, ldy, rows, eps);
+      cudaError_t e = silu ? cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T, TO, true>, x, y, gamma, beta, HW, C, groups, ldx, ldy, rows, eps, wsplit)
+                           : cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T, TO, false>, x, y, gamma, beta, HW, C, groups, ldx, ldy, rows, eps, wsplit);
       MKD_REQUIRE(e == cudaSuccess, MKD_E_CUDA, "groupnorm: cluster launch failed: %s", cudaGetErrorString(e));
       MKD_CHECK_LAUNCH();
       return MKD_OK;
@@ -706,19 +712,21 @@ static int groupnorm_launch(const T* x, TO* y, int N, int HW, int C, int groups,
   MKD_CHECK_LAUNCH();
   if (silu)
     MKD_LAUNCH_OK(launch_pdl(gn_apply_kernel<T, TO, true>, dim3(grid), dim3(threads), sm2, st, x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
-                                                         rows_per_chunk, nchunks, eps));
+                                                         rows_per_chunk, nchunks, eps, wsplit));
   else
     MKD_LAUNCH_OK(launch_pdl(gn_apply_kernel<T, TO, false>, dim3(grid), dim3(threads), sm2, st, x, y, partial, gamma, beta, HW, C, groups, ldx, ldy,
-                                                          rows_per_chunk, nchunks, eps));
+                                                          rows_per_chunk, nchunks, eps, wsplit));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
 
 extern "C" int mkd_groupnorm(const void* x, void* y, int x_dtype, int y_dtype, int N, int HW, int C, int groups, int ldx,
                              int ldy, const float* gamma, const float* beta, float eps, int silu, void* workspace,
-                             size_t workspace_bytes, mkd_stream_t stream) {
+                             size_t workspace_bytes, int wgroups, mkd_stream_t stream) {
   MKD_REQUIRE(x && y && gamma && beta && workspace && N > 0 && HW > 0 && C > 0 && groups > 0, MKD_E_INVALID,
               "groupnorm: bad args");
+  MKD_REQUIRE(wgroups == 1 || (wgroups == 2 && N % 2 == 0), MKD_E_INVALID, "groupnorm: wgroups must be 1, or 2 with an even batch");
+  const long long wsplit = wgroups == 2 ? N / 2 : (1ll << 62);
   MKD_REQUIRE(C % groups == 0 && C % 8 == 0 && C <= 8 * 1024, MKD_E_INVALID,
               "groupnorm: C=%d must be a multiple of groups=%d and of 8", C, groups);
   MKD_REQUIRE(N <= 65535, MKD_E_INVALID, "groupnorm: N too large");
@@ -729,18 +737,18 @@ extern "C" int mkd_groupnorm(const void* x, void* y, int x_dtype, int y_dtype, i
   cudaStream_t st = (cudaStream_t)stream;
   float2* ws = (float2*)workspace;
   if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
-    return groupnorm_launch<bf16, bf16>((const bf16*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, st);
+    return groupnorm_launch<bf16, bf16>((const bf16*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, wsplit, st);
   if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
-    return groupnorm_launch<float, bf16>((const float*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, st);
+    return groupnorm_launch<float, bf16>((const float*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, wsplit, st);
   if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
-    return groupnorm_launch<float, float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, st);
+    return groupnorm_launch<float, float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, ws, wsplit, st);
   MKD_REQUIRE(false, MKD_E_INVALID, "groupnorm: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
 }
 
 template <typename T, typename TO>
 static int gn_apply_launch(const T* x, TO* y, int N, int HW, int C, int groups, int ldx, int ldy, const float* gamma,
                            const float* beta, float eps, int silu, const float2* stats, int stats_ld, int tiles,
-                           cudaStream_t st) {
+                           long long wsplit, cudaStream_t st) {
   const int VX = C / 8;
   int threads = VX >= 256 ? VX : (256 / VX) * VX;
   threads = ((threads + 31) / 32) * 32;
@@ -763,19 +771,21 @@ static int gn_apply_launch(const T* x, TO* y, int N, int HW, int C, int groups, 
   dim3 grid(nchunks, N);
   if (silu)
     MKD_LAUNCH_OK(launch_pdl(gn_apply_stats_kernel<T, TO, true>, grid, dim3(threads), smem, st, x, y, stats, stats_ld, tiles, gamma, beta, HW, C,
-                             groups, ldx, ldy, rows, eps));
+                             groups, ldx, ldy, rows, eps, wsplit));
   else
     MKD_LAUNCH_OK(launch_pdl(gn_apply_stats_kernel<T, TO, false>, grid, dim3(threads), smem, st, x, y, stats, stats_ld, tiles, gamma, beta, HW, C,
-                             groups, ldx, ldy, rows, eps));
+                             groups, ldx, ldy, rows, eps, wsplit));
   MKD_CHECK_LAUNCH();
   return MKD_OK;
 }
 
 extern "C" int mkd_groupnorm_apply(const void* x, void* y, int x_dtype, int y_dtype, int N, int HW, int C, int groups,
                                    int ldx, int ldy, const float* gamma, const float* beta, float eps, int silu,
-                                   const float* stats, int stats_ld, int tiles_per_sample, mkd_stream_t stream) {
+                                   const float* stats, int stats_ld, int tiles_per_sample, int wgroups, mkd_stream_t stream) {
   MKD_REQUIRE(x && y && gamma && beta && stats && N > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64, MKD_E_INVALID,
               "groupnorm_apply: bad args");
+  MKD_REQUIRE(wgroups == 1 || (wgroups == 2 && N % 2 == 0), MKD_E_INVALID, "groupnorm_apply: wgroups must be 1, or 2 with an even batch");
+  const long long wsplit = wgroups == 2 ? N / 2 : (1ll << 62);
   MKD_REQUIRE(C % groups == 0 && C % 8 == 0 && C <= 8 * 512, MKD_E_INVALID,
               "groupnorm_apply: C=%d must be a multiple of groups=%d and of 8", C, groups);
   MKD_REQUIRE(N <= 65535 && HW == 128 * tiles_per_sample && stats_ld >= C, MKD_E_INVALID,
@@ -786,11 +796,11 @@ extern "C" int mkd_groupnorm_apply(const void* x, void* y, int x_dtype, int y_dt
   cudaStream_t st = (cudaStream_t)stream;
   const float2* sp = reinterpret_cast<const float2*>(stats);
   if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
-    return gn_apply_launch<bf16, bf16>((const bf16*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, st);
+    return gn_apply_launch<bf16, bf16>((const bf16*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, wsplit, st);
   if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
-    return gn_apply_launch<float, bf16>((const float*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, st);
+    return gn_apply_launch<float, bf16>((const float*)x, (bf16*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, wsplit, st);
   if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
-    return gn_apply_launch<float, float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, st);
+    return gn_apply_launch<float, float>((const float*)x, (float*)y, N, HW, C, groups, ldx, ldy, gamma, beta, eps, silu, sp, stats_ld, tiles_per_sample, wsplit, st);
   MKD_REQUIRE(false, MKD_E_INVALID, "groupnorm_apply: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
 }
 
@@ -818,8 +828,10 @@ extern "C" int mkd_softmax_rows(const void* x, void* y, int x_dtype, int y_dtype
 }
 
 extern "C" int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, int64_t M, int C, int ldx, int ldy,
-                             const float* gamma, const float* beta, float eps, mkd_stream_t stream) {
+                             const float* gamma, const float* beta, float eps, int wgroups, mkd_stream_t stream) {
   MKD_REQUIRE(x && y && gamma && beta && M > 0 && C > 0, MKD_E_INVALID, "layernorm: bad args");
+  MKD_REQUIRE(wgroups == 1 || (wgroups == 2 && M % 2 == 0), MKD_E_INVALID, "layernorm: wgroups must be 1, or 2 with an even row count");
+  const long long wsplit = wgroups == 2 ? M / 2 : (1ll << 62);
   MKD_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_VPL, MKD_E_INVALID, "layernorm: C=%d must be a multiple of 8, <= %d", C,
               8 * 32 * LN_VPL);
   MKD_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta),
@@ -831,11 +843,11 @@ extern "C" int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, i
     cudaError_t le = cudaSuccess;
     bool took = false;
     if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
-      took = layernorm5_launch((const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps, st, &le);
+      took = layernorm5_launch((const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps, wsplit, st, &le);
     else if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
-      took = layernorm5_launch((const float*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps, st, &le);
+      took = layernorm5_launch((const float*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps, wsplit, st, &le);
     else if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
-      took = layernorm5_launch((const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps, st, &le);
+      took = layernorm5_launch((const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps, wsplit, st, &le);
     if (took) {
       MKD_LAUNCH_OK(le);
       MKD_CHECK_LAUNCH();
@@ -843,11 +855,11 @@ extern "C" int mkd_layernorm(const void* x, void* y, int x_dtype, int y_dtype, i
     }
   }
   if (x_dtype == MKD_BF16 && y_dtype == MKD_BF16)
-    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<bf16, bf16>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps));
+    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<bf16, bf16>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const bf16*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps, wsplit));
   else if (x_dtype == MKD_F32 && y_dtype == MKD_BF16)
-    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<float, bf16>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const float*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps));
+    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<float, bf16>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const float*)x, (bf16*)y, M, C, ldx, ldy, gamma, beta, eps, wsplit));
   else if (x_dtype == MKD_F32 && y_dtype == MKD_F32)
-    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<float, float>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps));
+    MKD_LAUNCH_OK(launch_pdl(layernorm_kernel<float, float>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, (const float*)x, (float*)y, M, C, ldx, ldy, gamma, beta, eps, wsplit));
   else
     MKD_REQUIRE(false, MKD_E_INVALID, "layernorm: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
   MKD_CHECK_LAUNCH();

@@ -146,18 +146,20 @@ def groupnorm_workspace_bytes(N, groups=32) -> int:
 
 
 @_timed("groupnorm", lambda x, y, *a, **k: _nb(x, y))
-def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
+def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32, wgroups=1):
+    """wgroups = 2: gamma / beta hold [2, C]; samples n >= N/2 use the second row (two networks' layer in one launch)"""
     px, ldx = _rows(x2d)
     py, ldy = _rows(y2d)
     M, Cc = x2d.shape
     assert M % N == 0 and y2d.shape == x2d.shape and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    assert gamma.numel() == wgroups * Cc and beta.numel() == wgroups * Cc and gamma.is_contiguous() and beta.is_contiguous()
     L.check(L.load().mkd_groupnorm(px, py, _dt(x2d), _dt(y2d), N, M // N, Cc, groups, ldx, ldy, gamma.data_ptr(), beta.data_ptr(),
                                    float(eps), int(bool(silu)), workspace.data_ptr(),
-                                   workspace.numel() * workspace.element_size(), _stream()), "groupnorm")
+                                   workspace.numel() * workspace.element_size(), wgroups, _stream()), "groupnorm")
 
 
 @_timed("groupnorm_apply", lambda x, y, *a, **k: _nb(x, y))
-def groupnorm_apply(x2d, y2d, N, gamma, beta, eps, silu, stats, groups=32):
+def groupnorm_apply(x2d, y2d, N, gamma, beta, eps, silu, stats, groups=32, wgroups=1):
     """GroupNorm whose statistics were emitted by the producing conv2d(..., stats=): ``stats`` is a
     [N * HW / 128, C, 2] fp32 view (row pitch may exceed C when it is a channel slice of a concat's statistics)."""
     px, ldx = _rows(x2d)
@@ -166,19 +168,21 @@ def groupnorm_apply(x2d, y2d, N, gamma, beta, eps, silu, stats, groups=32):
     assert M % N == 0 and (M // N) % 128 == 0 and y2d.shape == x2d.shape
     assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[1:] == (Cc, 2) and stats.stride(2) == 1
     assert stats.stride(1) == 2 and stats.shape[0] == M // 128 and stats.stride(0) % 2 == 0
+    assert gamma.numel() == wgroups * Cc and beta.numel() == wgroups * Cc and gamma.is_contiguous() and beta.is_contiguous()
     L.check(L.load().mkd_groupnorm_apply(px, py, _dt(x2d), _dt(y2d), N, M // N, Cc, groups, ldx, ldy, gamma.data_ptr(),
                                          beta.data_ptr(), float(eps), int(bool(silu)), stats.data_ptr(),
-                                         stats.stride(0) // 2, (M // N) // 128, _stream()), "groupnorm_apply")
+                                         stats.stride(0) // 2, (M // N) // 128, wgroups, _stream()), "groupnorm_apply")
 
 
 @_timed("layernorm", lambda x, y, *a, **k: _nb(x, y))
-def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
+def layernorm(x2d, y2d, gamma, beta, eps=1e-5, wgroups=1):
     px, ldx = _rows(x2d)
     py, ldy = _rows(y2d)
     M, Cc = x2d.shape
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    assert gamma.numel() == wgroups * Cc and beta.numel() == wgroups * Cc and gamma.is_contiguous() and beta.is_contiguous()
     L.check(L.load().mkd_layernorm(px, py, _dt(x2d), _dt(y2d), M, Cc, ldx, ldy, gamma.data_ptr(), beta.data_ptr(), float(eps),
-                                   _stream()), "layernorm")
+                                   wgroups, _stream()), "layernorm")
 
 
 @_timed("softmax_rows", lambda x, y, *a, **k: _nb(x, y))
@@ -193,15 +197,16 @@ def softmax_rows(x2d, y2d, scale=1.0):
 
 def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None,
                    residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None,
-                   y32=None, stats=None, pad_hi_extra=0, x2=None) -> L.ConvDesc:
+                   y32=None, stats=None, pad_hi_extra=0, x2=None, wgroups=1) -> L.ConvDesc:
     """y2d: output in the activation dtype (or None); y32: optional fp32 copy of the same result.
     x2: optional second input [N*H*W, C2] of a fused 1x1 term (mkd_conv_desc.x2): w is then [K, R*S*C + C2]."""
     px, ldx = _rows(x2d)
     Cc = x2d.shape[1]
-    K = w.shape[0]
+    K = w.shape[0] // wgroups  # wgroups = 2: w holds the rows of two networks' layer, bias both biases (mkd_conv_desc.wgroups)
     C2 = 0 if x2 is None else x2.shape[1]
     assert x2d.shape[0] == N * H * W, (x2d.shape, N, H, W)
-    assert w.is_contiguous() and w.numel() == K * (R * S * Cc + C2) and w.dtype == x2d.dtype
+    assert w.is_contiguous() and w.numel() == wgroups * K * (R * S * Cc + C2) and w.dtype == x2d.dtype
+    assert bias is None or bias.numel() == wgroups * K
     d = L.ConvDesc()
     d.dtype = _dt(x2d)
     d.residual_dtype = d.dtype
@@ -241,6 +246,7 @@ def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=
         assert x2.dtype == x2d.dtype and x2.shape[0] == x2d.shape[0] and stride == 1 and not upsample
         d.x2, d.ldx2 = _rows(x2)
         d.C2 = C2
+    d.wgroups = wgroups
     return d
 
 
@@ -259,6 +265,34 @@ def conv2d(x2d, w, y2d, **kw):
     Q = (Wi + 2 * d.pad + d.pad_hi_extra - d.S) // d.stride + 1
     PROFILE.append({"op": "conv2d", "path": path, "flops": 2.0 * d.N * P * Q * d.K * (d.R * d.S * d.C + d.C2), "M": d.N * P * Q, "K": d.K,
                     "C": d.C, "C2": d.C2, "R": d.R, "stride": d.stride, "up": d.upsample, "e0": e0, "e1": e1, "desc": d})
+
+
+def conv2d_grouped(x2d, w, y2d, *, N, **kw):
+    """The same layer of TWO networks on two stacked batches in one launch (mkd_conv_desc.wgroups = 2): rows [0, M/2) of every
+    row-indexed tensor (x, y, y32, residual, x2; emb and stats by image / tile) belong to network 0, the rest to network 1;
+    ``w`` / ``bias`` hold network 0's rows followed by network 1's.  Shapes the CTA-pair kernel declines (parts that are not
+    whole 256-row tile pairs, tiny problems) run as one launch per part on slices."""
+    d = make_conv_desc(x2d, w, y2d, N=N, wgroups=2, **kw)
+    if L.load().mkd_conv2d_path(C.byref(d)) >= 0:
+        conv2d(x2d, w, y2d, N=N, wgroups=2, **kw)
+        return
+    assert N % 2 == 0 and w.shape[0] % 2 == 0
+    K = w.shape[0] // 2
+    out = y2d if y2d is not None else kw.get("y32")
+    rows = {"x": x2d.shape[0] // 2, "out": out.shape[0] // 2}
+
+    def part(t, g, n):
+        return None if t is None else t[g * n:(g + 1) * n]
+    for g in (0, 1):
+        k2 = dict(kw)
+        k2["bias"] = part(kw.get("bias"), g, K)
+        for name in ("residual", "y32"):
+            k2[name] = part(kw.get(name), g, rows["out"])
+        k2["emb"] = part(kw.get("emb"), g, N // 2)
+        k2["x2"] = part(kw.get("x2"), g, rows["x"])
+        if kw.get("stats") is not None:
+            k2["stats"] = part(kw["stats"], g, kw["stats"].shape[0] // 2)
+        conv2d(part(x2d, g, rows["x"]), w[g * K:(g + 1) * K], part(y2d, g, rows["out"]), N=N // 2, **k2)
 
 
 def conv2d_path(x2d, w, y2d, **kw) -> int:

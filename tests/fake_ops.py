@@ -65,7 +65,15 @@ def add(a2d, b2d, y2d):
     y2d.copy_(a2d.float() + b2d.float())
 
 
-def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
+def _by_parts(fn, x2d, y2d, N, gamma, beta, eps, silu, workspace, groups):
+    h, C = x2d.shape[0] // 2, x2d.shape[1]
+    for g in (0, 1):
+        fn(x2d[g * h:(g + 1) * h], y2d[g * h:(g + 1) * h], N // 2, gamma.reshape(2, C)[g], beta.reshape(2, C)[g], eps, silu, workspace, groups)
+
+
+def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32, wgroups=1):
+    if wgroups == 2:
+        return _by_parts(groupnorm, x2d, y2d, N, gamma, beta, eps, silu, workspace, groups)
     M, C = x2d.shape
     xr = x2d.float().reshape(N, M // N, C).permute(0, 2, 1)
     r = F.group_norm(xr, groups, gamma, beta, eps)
@@ -74,7 +82,13 @@ def groupnorm(x2d, y2d, N, gamma, beta, eps, silu, workspace, groups=32):
     y2d.copy_(r.permute(0, 2, 1).reshape(M, C))
 
 
-def groupnorm_apply(x2d, y2d, N, gamma, beta, eps, silu, stats, groups=32):
+def groupnorm_apply(x2d, y2d, N, gamma, beta, eps, silu, stats, groups=32, wgroups=1):
+    if wgroups == 2:
+        h, C = x2d.shape[0] // 2, x2d.shape[1]
+        for g in (0, 1):
+            groupnorm_apply(x2d[g * h:(g + 1) * h], y2d[g * h:(g + 1) * h], N // 2, gamma.reshape(2, C)[g], beta.reshape(2, C)[g], eps, silu,
+                            stats[g * (stats.shape[0] // 2):(g + 1) * (stats.shape[0] // 2)], groups)
+        return
     """mkd_groupnorm_apply: statistics come from the producer's per-tile (sum, sumsq) partials, not from x"""
     M, C = x2d.shape
     tiles = (M // N) // 128
@@ -98,13 +112,22 @@ def softmax_rows(x2d, y2d, scale=1.0):
     y2d.copy_(torch.softmax(x2d.float() * scale, -1))
 
 
-def layernorm(x2d, y2d, gamma, beta, eps=1e-5):
+def layernorm(x2d, y2d, gamma, beta, eps=1e-5, wgroups=1):
+    if wgroups == 2:
+        h, C = x2d.shape[0] // 2, x2d.shape[1]
+        for g in (0, 1):
+            layernorm(x2d[g * h:(g + 1) * h], y2d[g * h:(g + 1) * h], gamma.reshape(2, C)[g], beta.reshape(2, C)[g], eps)
+        return
     y2d.copy_(F.layer_norm(x2d.float(), (x2d.shape[1],), gamma, beta, eps))
 
 
 def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None, residual=None,
            alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None, y32=None, stats=None,
-           pad_hi_extra=0, x2=None):
+           pad_hi_extra=0, x2=None, wgroups=1):
+    if wgroups == 2:
+        return conv2d_grouped(x2d, w, y2d, N=N, H=H, W=W, R=R, S=S, stride=stride, pad=pad, upsample=upsample, bias=bias, emb=emb,
+                              residual=residual, alpha=alpha, act=act, geglu_block=geglu_block, path=path, workspace=workspace,
+                              y32=y32, stats=stats, pad_hi_extra=pad_hi_extra, x2=x2)
     C = x2d.shape[1]
     K = w.shape[0]
     C2 = 0 if x2 is None else x2.shape[1]
@@ -148,6 +171,26 @@ def conv2d(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, b
             out.copy_(acc)
 
 
+def conv2d_grouped(x2d, w, y2d, *, N, **kw):
+    """contract of mkd_conv_desc.wgroups = 2: part g of the rows with weight rows / biases [g K, (g + 1) K)"""
+    K = w.shape[0] // 2
+    out = y2d if y2d is not None else kw.get("y32")
+    rx, ro = x2d.shape[0] // 2, out.shape[0] // 2
+
+    def part(t, g, n):
+        return None if t is None else t[g * n:(g + 1) * n]
+    for g in (0, 1):
+        k2 = dict(kw)
+        k2["bias"] = part(kw.get("bias"), g, K)
+        for name in ("residual", "y32"):
+            k2[name] = part(kw.get(name), g, ro)
+        k2["emb"] = part(kw.get("emb"), g, N // 2)
+        k2["x2"] = part(kw.get("x2"), g, rx)
+        if kw.get("stats") is not None:
+            k2["stats"] = part(kw["stats"], g, kw["stats"].shape[0] // 2)
+        conv2d(part(x2d, g, rx), w[g * K:(g + 1) * K], part(y2d, g, ro), N=N // 2, **k2)
+
+
 def conv2d_supported(x2d, w, y2d, **kw):
     """the contract of the x2 term: stride 1, C2 % 64 == 0, K % 160 == 0 (the CTA-pair kernel's tiles)"""
     x2 = kw.get("x2")
@@ -186,4 +229,4 @@ def image_grid_u8(images, nrow, padding=2, clamp=True, rescale=True):
 
 
 ALL = ["image_grid_u8", "attention_causal", "embed_tokens", "device_ok", "groupnorm_workspace_bytes", "ddim_update", "nchw_to_nhwc", "nhwc_to_nchw", "timestep_embedding",
-       "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "softmax_rows", "conv2d", "conv2d_supported", "attention"]
+       "silu", "geglu", "add", "groupnorm", "groupnorm_apply", "layernorm", "softmax_rows", "conv2d", "conv2d_supported", "conv2d_grouped", "attention"]

@@ -511,3 +511,93 @@ def test_attention(dt, B, heads, Nq, Nkv, d):
     sp = lambda t, n: t.float().reshape(B, n, heads, d).permute(0, 2, 1, 3)  # noqa: E731
     ref = F.scaled_dot_product_attention(sp(q, Nq), sp(k, Nkv), sp(v, Nkv)).permute(0, 2, 1, 3).reshape(B * Nq, C)
     assert rel(o, ref) < (1e-2 if dt == BF else 2e-5)
+
+
+# ---- weight groups (mkd_conv_desc.wgroups / the norms' wgroups): the same layer of two networks on two stacked batches --------
+WG_CASES = [
+    dict(N=32, H=32, W=32, C=320, K=320, R=3, emb=True, y32="both", stats=True),      # ResBlock conv1, 32x32 level
+    dict(N=32, H=32, W=32, C=320, K=320, R=1, res32=True, y32="only"),                # attention out-projection into the fp32 stream
+    dict(N=32, H=16, W=16, C=640, K=5120, R=1, act="geglu"),                          # FF1 GEGLU
+    dict(N=32, H=4, W=4, C=1280, K=1280, R=3, emb=True, y32="only", workspace=True),  # 4x4 level: split-K + reducer
+    dict(N=32, H=16, W=16, C=640, K=640, R=3, C2=320, y32="both", stats=True),        # out conv + fused skip projection
+    dict(N=32, H=32, W=32, C=320, K=320, R=3, stride=2, y32="both"),                  # Downsample in place
+    dict(N=32, H=8, W=8, C=1280, K=3840, R=1),                                        # q/k/v at the 8x8 level
+    dict(N=2, H=16, W=16, C=640, K=640, R=1, fallback=True),                          # too few units for the pair kernel: two launches
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_conv_weight_groups(case):
+    """conv2d_grouped == the two networks' launches on their own halves (same kernel, so the same arithmetic up to the split-K
+    plan), and the grouped launch really is ONE launch where the kernel takes it"""
+    N, H, W, C, K, R = (case[k] for k in "NHWCKR")
+    stride, C2 = case.get("stride", 1), case.get("C2", 0)
+    geglu = case.get("act") == "geglu"
+    M, Mo = N * H * W, N * (H // stride) * (W // stride)
+    Ko = K // 2 if geglu else K
+    x = rnd(M, C, dt=BF, seed=1)
+    w = (rnd(2 * K, R * R * C + C2, seed=2) / math.sqrt(C * R * R + C2)).to(BF)
+    b = 0.5 * rnd(2 * K, seed=3)
+    kw = dict(H=H, W=W, R=R, S=R, stride=stride, pad=R // 2, bias=b)
+    if case.get("emb"):
+        kw["emb"] = rnd(N, K, dt=BF, seed=4)
+    if C2:
+        kw["x2"] = rnd(M, C2, dt=BF, seed=5)
+    if case.get("workspace"):
+        kw["workspace"] = torch.empty(64 << 20, dtype=torch.uint8, device=DEV)
+    if geglu:
+        kw.update(act=L.ACT_GEGLU, geglu_block=128)
+    res = rnd(Mo, Ko, dt=F32, seed=6) if case.get("res32") else None
+    outs = []
+    for grouped in (True, False):
+        y = None if case.get("y32") == "only" else torch.zeros(Mo, Ko, device=DEV, dtype=BF)
+        y32 = torch.zeros(Mo, Ko, device=DEV) if case.get("y32") else None
+        st = torch.zeros(Mo // 128, Ko, 2, device=DEV) if case.get("stats") else None
+        k2 = dict(kw, y32=y32, stats=st, residual=None if res is None else res.clone())
+        n0 = L.load().mkd_launch_count()
+        if grouped:
+            ops.conv2d_grouped(x, w, y, N=N, **k2)
+        else:
+            for g in (0, 1):
+                part = lambda t, n: None if t is None else t[g * n:(g + 1) * n]  # noqa: E731
+                k3 = dict(k2, bias=part(b, K), emb=part(k2.get("emb"), N // 2), x2=part(k2.get("x2"), M // 2), y32=part(y32, Mo // 2),
+                          residual=part(k2["residual"], Mo // 2), stats=part(st, Mo // 256))
+                ops.conv2d(part(x, M // 2), w[g * K:(g + 1) * K], part(y, Mo // 2), N=N // 2, **k3)
+        launches = L.load().mkd_launch_count() - n0
+        outs.append((y, y32, st, launches))
+    (y1, y321, st1, l1), (y0, y320, st0, l0) = outs
+    if not case.get("fallback"):
+        assert l1 * 2 == l0, (l1, l0)       # one launch (+ one reducer) instead of two (+ two)
+    else:
+        assert l1 == l0
+    for a, r in ((y1, y0), (y321, y320)):
+        if a is not None:
+            assert rel(a, r.float()) < (3e-3 if case.get("workspace") else 1e-6), rel(a, r.float())
+            assert float(r.float().abs().max()) > 0
+    if st1 is not None:
+        assert rel(st1, st0) < 1e-5
+
+
+@pytest.mark.parametrize("N,HW,C", [(32, 1024, 320), (32, 256, 640), (32, 64, 1280), (32, 16, 2560), (4, 100, 128)])
+def test_norm_weight_groups(N, HW, C):
+    """GroupNorm (all three kernels), GroupNorm-apply and LayerNorm with wgroups = 2 == the two halves with their own gamma / beta,
+    bit for bit"""
+    x = rnd(N * HW, C, dt=F32, seed=1) * 1.5 + 0.2
+    g2, b2 = 1 + 0.2 * rnd(2, C, seed=2), 0.1 * rnd(2, C, seed=3)
+    ws = torch.empty(ops.groupnorm_workspace_bytes(N) // 4, device=DEV)
+    h = N * HW // 2
+
+    def both(fn):
+        a, r = torch.empty(N * HW, C, device=DEV, dtype=BF), torch.empty(N * HW, C, device=DEV, dtype=BF)
+        fn(x, a, g2, b2, 2, N)
+        for g in (0, 1):
+            fn(x[g * h:(g + 1) * h], r[g * h:(g + 1) * h], g2[g].contiguous(), b2[g].contiguous(), 1, N // 2)
+        assert torch.equal(a, r)
+    both(lambda xx, yy, ga, be, wg, n: ops.groupnorm(xx, yy, n, ga, be, 1e-5, True, ws, wgroups=wg))
+    if C <= 1280:
+        both(lambda xx, yy, ga, be, wg, n: ops.layernorm(xx, yy, ga, be, wgroups=wg))
+    if HW % 128 == 0:
+        t = x.reshape(N * HW // 128, 128, C)
+        st = torch.stack([t.sum(1), (t * t).sum(1)], -1).contiguous()
+        both(lambda xx, yy, ga, be, wg, n: ops.groupnorm_apply(xx, yy, n, ga, be, 1e-5, True,
+                                                               st[:xx.shape[0] // 128] if xx.data_ptr() == x.data_ptr() else st[h // 128:], wgroups=wg))
