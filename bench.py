@@ -139,6 +139,8 @@ def workload_config(args, world):
                            + (" fused into the last DDIM-update kernel (peer stores)" if getattr(args, "fused_gather", False)
                               and world > 1 else " (NCCL)" if world > 1 else ""),
             "cuda_graph": not args.no_graph,
+            "trunks": "UNet encoder and ControlNet trunk as two networks on two streams" if getattr(args, "no_grouped", False)
+                      else "UNet encoder + ControlNet trunk as one stacked network (two weight groups per launch)",
             "l2": "per-step working set (2.44 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -195,6 +197,8 @@ def main():
                          "20-step DDIM, sharded over the GPUs")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-grouped", action="store_true",
+                    help="A/B: UNet encoder and ControlNet trunk as two networks on two streams instead of one stacked network")
     ap.add_argument("--fused-gather", action="store_true",
                     help="N > 1: all-gather the final latents with the last DDIM-update kernel's own peer stores "
                          "(symmetric memory over NVLink) instead of the NCCL collective")
@@ -246,6 +250,7 @@ def main():
 
     model = B200ControlLDM(dtype=torch.bfloat16, device=dev)
     model.load_state_dict(synthetic_state_dict(model, 0, dev))
+    model.grouped = not args.no_grouped
     sampler = B200DDIMSampler(model, use_cuda_graph=not args.no_graph)
     if args.decode:
         from makeupdiffuse_b200 import B200FirstStageDecoder

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .nets import B200ControlNet, B200ControlledUnet
+from .nets import B200ControlNet, B200ControlledUnet, B200GroupedTrunk
 
 
 class _Wrapper:
@@ -54,6 +54,10 @@ class B200ControlLDM:
         # ControlNet trunk on a second stream, concurrent with the UNet encoder (set False to serialise: profiling, A/B runs)
         self.concurrent = True
         self._side = None
+        # UNet encoder + ControlNet trunk as one stacked network (nets.B200GroupedTrunk): each layer of the two structurally
+        # identical trunks is one launch over both batches.  False: two networks, two streams (A/B runs)
+        self.grouped = True
+        self._trunk = None
 
     @property
     def device(self):
@@ -75,7 +79,13 @@ class B200ControlLDM:
         self.model.diffusion_model.load_state_dict(un, strict=strict, prefix="model.diffusion_model.", device=self._device)
         self._cond_cache.clear()
         self._weights_epoch += 1
+        self._trunk = None  # stacked copies of the trunk weights: rebuilt from the new ones on first use
         return self
+
+    def _grouped_trunk(self):
+        if self._trunk is None:
+            self._trunk = B200GroupedTrunk(self.model.diffusion_model, self.control_model)
+        return self._trunk
 
     # ---- step-invariant conditioning ------------------------------------------------------------------------
     # The hoisted tensors (hint features, cross-attention K/V) are reused while the cond is THE SAME tensors holding the
@@ -102,7 +112,8 @@ class B200ControlLDM:
         un, cn = self.model.diffusion_model, self.control_model
         key = (tuple(self._tkey(t) for t in ctx_list), None if cat_list is None else tuple(self._tkey(t) for t in cat_list))
         hit = self._cond_cache.get("k")
-        if hit is not None and hit[0] == key and hit[4] == (un.arena_epoch, cn.arena_epoch):
+        if hit is not None and hit[0] == key and hit[4] == (un.arena_epoch, cn.arena_epoch) and \
+                (not self.grouped or cat_list is None or "kv2" in hit[1]):
             return hit[1]
         ctx = ctx_list[0] if len(ctx_list) == 1 else torch.cat(ctx_list, 1)
         prep = {"kv_unet": un.context_kv(ctx)}
@@ -110,6 +121,8 @@ class B200ControlLDM:
             hint = cat_list[0] if len(cat_list) == 1 else torch.cat(cat_list, 1)
             prep["kv_cn"] = cn.context_kv(ctx)
             prep["hint"] = cn.hint_features(hint)
+            if self.grouped:
+                prep["kv2"], prep["hint2"] = self._grouped_trunk().stack_cond(prep["kv_unet"], prep["kv_cn"], prep["hint"])
         # keep the source tensors alive so data_ptr-based keys cannot be recycled
         self._cond_cache["k"] = (key, prep, ctx_list, cat_list, (un.arena_epoch, cn.arena_epoch))
         return prep
@@ -122,9 +135,13 @@ class B200ControlLDM:
         prep = self._prepare(cond)
         t = t.to(torch.int64).contiguous()
         use_cn = cond["c_concat"] is not None
+        grouped = use_cn and self.grouped
         two_streams = use_cn and self.concurrent and x_noisy.is_cuda
         pending = None
-        if two_streams:
+        if grouped:
+            # both trunks as one stacked network on this stream; only the injecting zero-convs go to the side stream below
+            slots, pending = self._grouped_trunk().run(x_noisy, prep["hint2"], t, prep["kv2"], N, H, W)
+        elif two_streams:
             # The ControlNet trunk depends only on (x, t, hint, ctx): fork it onto a second stream so its many small,
             # latency-bound kernels fill the SMs the UNet encoder's leave idle.  Inside a CUDA-graph capture this
             # becomes a parallel branch of the graph.
@@ -137,14 +154,17 @@ class B200ControlLDM:
             with torch.cuda.stream(self._side):
                 pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W)
                 join.record(self._side)
-        xin = un._x_in(x_noisy)
-        slots = un.encode(xin, t, prep["kv_unet"], N, H, W)
+        if not grouped:
+            xin = un._x_in(x_noisy)
+            slots = un.encode(xin, t, prep["kv_unet"], N, H, W)
         before_block = None
         if use_cn:
             nb = len(un.input_blocks)
             inject = [None] * nb + [slots[nb]] if self.only_mid_control else slots
             inject_st = un.skip_slot_stats(N, H, W)
             if two_streams:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=x_noisy.device)
                 # The 13 injecting zero-convs stay on the side stream, issued in the order the decoder consumes the
                 # slots (middle output first, then hs.pop() order) with one event each: the decoder's deep, SM-starved
                 # blocks start after the first two and overlap the rest.
@@ -170,7 +190,8 @@ class B200ControlLDM:
                     if i == nb - 1:
                         main.wait_event(tail)  # joins the side stream whatever was injected
             else:
-                pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W)
+                if not grouped:
+                    pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W)
                 cn.zero_convs(pending, N, inject=inject, scales=self.control_scales, inject_st=inject_st)
             un.note_slots_rewritten([j for j, s in enumerate(inject) if s is not None], with_stats=True)
         e = un.decode(prep["kv_unet"], N, H, W, before_block=before_block)

@@ -98,6 +98,7 @@ class _Net(nn.Module):
         # bumped whenever context_kv() / hint_features() refill their (shared, static) arena buffers: a holder of earlier
         # results — B200ControlLDM's cond cache — compares epochs to learn that the buffers now hold another cond's data
         self.arena_epoch = 0
+        self._wg = 1  # weight groups of every launch (2 in B200GroupedTrunk: two networks' layer on two stacked batches)
         self._channel_mult, self._nrb = tuple(channel_mult), num_res_blocks
         self.w: dict[str, torch.Tensor] = {}
         self._bufs: dict = {}
@@ -276,9 +277,9 @@ class _Net(nn.Module):
     def _gn(self, x, y, N, gamma, beta, eps, silu):
         """x: Act (or (tensor, stats) via Act); GroupNorm(+SiLU) of x into the bf16 operand buffer y"""
         if x.st is not None:
-            ops.groupnorm_apply(x.src(), y, N, gamma, beta, eps, silu, x.st)
+            ops.groupnorm_apply(x.src(), y, N, gamma, beta, eps, silu, x.st, wgroups=self._wg)
         else:
-            ops.groupnorm(x.src(), y, N, gamma, beta, eps, silu, self._gn_ws(N))
+            ops.groupnorm(x.src(), y, N, gamma, beta, eps, silu, self._gn_ws(N), wgroups=self._wg)
 
     # ---- building blocks ---------------------------------------------------------------------------------------
     def _conv(self, x, wkey, y, N, H, W, R=1, **kw):
@@ -287,8 +288,14 @@ class _Net(nn.Module):
             # the library materialises the im2col matrix (stride 2) / the x2-upsampled input in the workspace
             rows = N * (H // 2) * (W // 2) * 9 if kw.get("stride", 1) == 2 else N * 4 * H * W
             self._grow_ws(rows * x.shape[1] * 2 + _SPLITK_WS_BYTES)
-        ops.conv2d(x, self.w[wkey + ".w"], y, N=N, H=H, W=W, R=R, S=R, pad=R // 2 if "pad" not in kw else kw.pop("pad"),
-                   bias=self.w.get(wkey + ".b"), workspace=self._ws, **kw)
+        self._launch(x, self.w[wkey + ".w"], y, N=N, H=H, W=W, R=R, S=R, pad=R // 2 if "pad" not in kw else kw.pop("pad"),
+                     bias=self.w.get(wkey + ".b"), workspace=self._ws, **kw)
+
+    def _launch(self, x, w, y, **kw):
+        if self._wg == 2:
+            ops.conv2d_grouped(x, w, y, **kw)
+        else:
+            ops.conv2d(x, w, y, **kw)
 
     def _grow_ws(self, need):
         """large batches outgrow the default workspace; a replaced buffer stays alive (captured graphs of other shapes
@@ -298,17 +305,19 @@ class _Net(nn.Module):
             self._ws = torch.empty(-(-need // 4), dtype=torch.float32, device=self._device)
 
     def _linear(self, x, wkey, y, **kw):
-        ops.conv2d(x, self.w[wkey + ".w"], y, N=1, H=1, W=x.shape[0], bias=self.w.get(wkey + ".b"), workspace=self._ws, **kw)
+        self._launch(x, self.w[wkey + ".w"], y, N=self._wg, H=1, W=x.shape[0] // self._wg, bias=self.w.get(wkey + ".b"),
+                     workspace=self._ws, **kw)
 
-    def _time_embedding(self, t, B):
-        """emb = time_embed(timestep_embedding(t)); returns silu(emb) @ W_all + b_all for every ResBlock at once."""
+    def _time_embedding(self, t, B, out=None):
+        """emb = time_embed(timestep_embedding(t)); returns silu(emb) @ W_all + b_all for every ResBlock at once
+        (into ``out``, a [B, _emb_total] view, when given)."""
         te = self._buf("t_emb", B, self.mc)
         ops.timestep_embedding(t, te)
         e1 = self._buf("te1", B, self.ted)
         self._linear(te, "te0", e1, act=L.ACT_SILU)
         e2 = self._buf("te2", B, self.ted)
         self._linear(e1, "te2", e2, act=L.ACT_SILU)  # every consumer (ResBlock.emb_layers) starts with SiLU: fused here
-        ea = self._buf("emb_all", B, self._emb_total)
+        ea = self._buf("emb_all", B, self._emb_total) if out is None else out
         self._linear(e2, "emb_all", ea)
         return ea
 
@@ -361,8 +370,15 @@ class _Net(nn.Module):
         ck = (key, N, H, W, y.lo is None, y.hi is None, y.st is None)
         ok = self._fuse_ok.get(ck)
         if ok is None:
-            ok = ops.conv2d_supported(t2, self.w[key + ".c2sk.w"], y.lo, N=N, H=H, W=W, R=3, S=3, pad=1, x2=x_lo,
-                                      bias=self.w[key + ".c2sk.b"], workspace=self._ws, y32=y.hi, stats=y.st)
+            w, b = self.w[key + ".c2sk.w"], self.w[key + ".c2sk.b"]
+            ok = ops.conv2d_supported(t2, w, y.lo, N=N, H=H, W=W, R=3, S=3, pad=1, x2=x_lo, bias=b, workspace=self._ws,
+                                      y32=y.hi, stats=y.st, wgroups=self._wg)
+            if not ok and self._wg == 2:
+                # the grouped launch is declined (parts that are not whole tile pairs): ops.conv2d_grouped then issues one launch
+                # per network, each of which may still take the second term
+                half = lambda v: None if v is None else v[:v.shape[0] // 2]  # noqa: E731
+                ok = ops.conv2d_supported(half(t2), half(w), half(y.lo), N=N // 2, H=H, W=W, R=3, S=3, pad=1, x2=half(x_lo),
+                                          bias=half(b), workspace=self._ws, y32=half(y.hi), stats=half(y.st))
             self._fuse_ok[ck] = ok
         return ok
 
@@ -380,7 +396,7 @@ class _Net(nn.Module):
         self._conv(n, key + ".pi", o_lo, N, H, W, R=1, y32=o_hi)
         ln = self._buf("st_ln", M, ch)
         # self-attention
-        ops.layernorm(xs, ln, self.w[key + ".norm1.g"], self.w[key + ".norm1.b"])
+        ops.layernorm(xs, ln, self.w[key + ".norm1.g"], self.w[key + ".norm1.b"], wgroups=self._wg)
         qkv = self._buf("st_qkv", M, 3 * ch)
         self._linear(ln, key + ".qkv", qkv)
         att = self._buf("st_att", M, ch)
@@ -388,7 +404,7 @@ class _Net(nn.Module):
                       d=hd, scale=scale)
         self._linear(att, key + ".o1", o_lo, residual=xs, y32=o_hi)
         # cross-attention (K/V of the step-invariant context are precomputed: ctx_kv[key] = [N*L, 2*ch])
-        ops.layernorm(xs, ln, self.w[key + ".norm2.g"], self.w[key + ".norm2.b"])
+        ops.layernorm(xs, ln, self.w[key + ".norm2.g"], self.w[key + ".norm2.b"], wgroups=self._wg)
         q2 = self._buf("st_q2", M, ch)
         self._linear(ln, key + ".q2", q2)
         kv = ctx_kv[key]
@@ -396,7 +412,7 @@ class _Net(nn.Module):
         ops.attention(q2, kv[:, :ch], kv[:, ch:], att, B=N, heads=self.heads, Nq=H * W, Nkv=Lc, d=hd, scale=scale)
         self._linear(att, key + ".o2", o_lo, residual=xs, y32=o_hi)
         # GEGLU feed-forward (gate fused into the first GEMM's epilogue)
-        ops.layernorm(xs, ln, self.w[key + ".norm3.g"], self.w[key + ".norm3.b"])
+        ops.layernorm(xs, ln, self.w[key + ".norm3.g"], self.w[key + ".norm3.b"], wgroups=self._wg)
         inner = 4 * ch
         ff = self._buf("st_ff", M, inner)
         self._linear(ln, key + ".ff1", ff, act=L.ACT_GEGLU, geglu_block=_geglu_block(inner))
@@ -676,39 +692,48 @@ class B200ControlledUnet(_Net):
         self._put("out.2.w", self._krsc(g("out.2.weight")), True); self._put("out.2.b", g("out.2.bias"))
 
     # the decoder's concat buffers: cat_i = [ h (C_h) | hs[11-i] (C_skip) ]
-    def _cat(self, i, N, H, W):
+    # row_groups = 2 (set by B200GroupedTrunk): every concat buffer (and its statistics) is allocated with twice the rows.
+    # The decoder and the reference call forms use the first half as before; the grouped trunk writes the stacked
+    # (UNet | ControlNet) block outputs through the full-height views (full=True), so the UNet half lands in its slot with
+    # no copy and the ControlNet half sits below it, where its zero-conv reads it.
+    row_groups = 1
+
+    def _cat(self, i, N, H, W, full=False):
         nb = len(self.input_blocks)
         ds = self.block_ds[nb - 1 - i]
         ch, ich = self.cat_split[i]
-        return self._buf(f"cat{i}", N * (H // ds) * (W // ds), ch + ich), ch, ds
+        rows = N * (H // ds) * (W // ds)
+        buf = self._buf(f"cat{i}", self.row_groups * rows, ch + ich)
+        return (buf if full else buf[:rows]), ch, ds
 
-    def skip_slots(self, N, H, W):
+    def skip_slots(self, N, H, W, full=False):
         """views the 12 encoder outputs live in + the view of the middle-block output (13 injection targets,
         ordered like ControlNet's outputs)"""
         nb = len(self.input_blocks)
         slots = []
         for j in range(nb):
-            cat, ch, _ = self._cat(nb - 1 - j, N, H, W)
+            cat, ch, _ = self._cat(nb - 1 - j, N, H, W, full)
             slots.append(cat[:, ch:])
-        cat0, ch0, _ = self._cat(0, N, H, W)
+        cat0, ch0, _ = self._cat(0, N, H, W, full)
         slots.append(cat0[:, :ch0])
         return slots
 
-    def _cat_stats(self, i, N, H, W):
+    def _cat_stats(self, i, N, H, W, full=False):
         """GroupNorm statistics of concat buffer i ([tiles, C_h + C_skip, 2]) or None when the level has no whole tiles"""
         cat, _, ds = self._cat(i, N, H, W)
         if not self._stats_ok(N, H // ds, W // ds):
             return None
-        return self._stats(f"cat{i}", cat.shape[0], cat.shape[1])
+        st = self._stats(f"cat{i}", self.row_groups * cat.shape[0], cat.shape[1])
+        return st if full else st[:cat.shape[0] // 128]
 
-    def skip_slot_stats(self, N, H, W):
+    def skip_slot_stats(self, N, H, W, full=False):
         """statistics views matching skip_slots(): the channel slice of the concat statistics each slot owns"""
         nb = len(self.input_blocks)
         out = []
         for j in range(nb):
-            st = self._cat_stats(nb - 1 - j, N, H, W)
+            st = self._cat_stats(nb - 1 - j, N, H, W, full)
             out.append(None if st is None else st[:, self.cat_split[nb - 1 - j][0]:, :])
-        st0 = self._cat_stats(0, N, H, W)
+        st0 = self._cat_stats(0, N, H, W, full)
         out.append(None if st0 is None else st0[:, :self.cat_split[0][0], :])
         return out
 
@@ -782,3 +807,94 @@ class B200ControlledUnet(_Net):
         out = torch.empty(N, self.out_channels, H, W, dtype=torch.float32, device=e.device)
         ops.nhwc_to_nchw(e, out)
         return out
+
+
+class B200GroupedTrunk(_Net):
+    """``input_blocks`` + ``middle_block`` of the UNet AND of its ControlNet copy as ONE network over a stacked batch.
+
+    The ControlNet trunk is a structural copy of the UNet encoder (upstream cldm.py: same blocks, own weights), and both read the
+    same (x_t, t, context): ``apply_model`` (makeup_diffuse.py:164-168) evaluates the same layer shapes twice per step.  Here every
+    layer is launched once with ``mkd_conv_desc.wgroups = 2`` / ``wgroups`` of the norm kernels: rows [0, M) of each activation
+    belong to the UNet, rows [M, 2M) to the ControlNet; each weight tensor holds the UNet's rows followed by the ControlNet's.
+    Twice the work units per launch at the under-filled 16x16 / 8x8 / 4x4 levels, half the trunk's launches.  Shapes the grouped
+    kernel declines run as one launch per network on the row halves (ops.conv2d_grouped), so results never depend on the path.
+
+    Outputs: block j of the stacked trunk writes through the full-height view of the decoder's concat slot j
+    (B200ControlledUnet.row_groups = 2): the UNet half IS ``hs[j]`` in place, the ControlNet half below it is what
+    ``zero_convs.j`` reads."""
+
+    def __init__(self, un: "B200ControlledUnet", cn: "B200ControlNet"):
+        super().__init__(un.in_channels, un.mc, un._attn_res, un._nrb, un._channel_mult, un.heads, 1, un.context_dim, un.dtype)
+        assert un._loaded and cn._loaded and self.block_chans == cn.block_chans == un.block_chans[:len(self.block_chans)]
+        self.un, self.cn = un, cn
+        self._device = un._device
+        self._wg = 2
+        for k, wc in cn.w.items():
+            if k.startswith(("input_blocks.", "middle_block.")):
+                wu = un.w[k]
+                assert wu.shape == wc.shape and wu.dtype == wc.dtype, k
+                self.w[k] = torch.cat([wu, wc], 0)
+        self._emb_off = {l[1]: cn._emb_off[l[1]] for l in self._res_layers()}
+        assert all(un._emb_off[k] == o for k, o in self._emb_off.items())
+        self._emb_total = un._emb_total
+        self._ws = torch.empty(_SPLITK_WS_BYTES // 4, dtype=torch.float32, device=self._device)
+        un.row_groups = 2
+        self.fused_gn_stats, self.fuse_skip = un.fused_gn_stats, un.fuse_skip
+        self._loaded = True
+
+    def stack_x(self, x):
+        """x_t twice: conv_in's stacked NHWC operand (both networks read the same latent)"""
+        B, Cc, H, W = x.shape
+        M = B * H * W
+        cols = 64 if self._hi else (Cc + 7) // 8 * 8
+        key = ("x_in2", 2 * M, cols)
+        if key not in self._bufs:
+            self._bufs[key] = torch.zeros(2 * M, cols, dtype=self.dtype, device=self._device)  # pad columns stay 0
+        buf = self._bufs[key]
+        xf = x.float().contiguous()
+        ops.nchw_to_nhwc(xf, buf[:M, :Cc])
+        ops.nchw_to_nhwc(xf, buf[M:, :Cc])
+        return buf if self._hi else buf[:, :Cc]
+
+    def stack_cond(self, kv_un, kv_cn, hint):
+        """per-cond (step-invariant) operands in stacked form: cross-attention K/V of both networks, and the residual of the
+        stacked conv_in — zeros for the UNet rows, ``input_hint_block(hint)`` for the ControlNet rows (cldm.py: h += guided_hint)"""
+        kv2 = {}
+        for key, kc in kv_cn.items():
+            ku = kv_un[key]
+            b = self._buf("kv2_" + key, 2 * ku.shape[0], ku.shape[1])
+            b[:ku.shape[0]].copy_(ku)
+            b[ku.shape[0]:].copy_(kc)
+            kv2[key] = b
+        h2 = self._buf("hint2", 2 * hint.shape[0], hint.shape[1])
+        h2[:hint.shape[0]].zero_()
+        h2[hint.shape[0]:].copy_(hint)
+        return kv2, h2
+
+    def run(self, x, hint2, t, kv2, N, H, W):
+        """both trunks; leaves the UNet ready for decode() (skip slots, statistics flags, time embedding) and returns
+        (slots, the ControlNet's 13 pending zero-conv calls) like encode() + run_trunk() did"""
+        un, cn = self.un, self.cn
+        self.fused_gn_stats, self.fuse_skip = un.fused_gn_stats, un.fuse_skip  # the A/B switches follow the UNet's
+        ea2 = self._buf("emb_all2", 2 * N, un._emb_total)
+        un._time_embedding(t, N, out=ea2[:N])
+        cn._time_embedding(t, N, out=ea2[N:, :cn._emb_total])
+        un._emb_cur = ea2[:N]
+        slots, slots2 = un.skip_slots(N, H, W), un.skip_slots(N, H, W, full=True)
+        un._slot_st, st2 = un.skip_slot_stats(N, H, W), un.skip_slot_stats(N, H, W, full=True)
+        un._slot_ok = [False] * len(slots)
+        pending = []
+        cur, h, w = Act(self.stack_x(x)), H, W
+        for j, blk in enumerate(self.input_blocks):
+            hi = self._buf(f"enc{j}_32", slots2[j].shape[0], slots2[j].shape[1], torch.float32) \
+                if self._hi and self._next_needs_hi(j) else None
+            y = Act(slots2[j], hi, st2[j])
+            h, w = self._run_block(blk, cur, y, ea2, kv2, 2 * N, h, w, conv_in_residual=hint2 if j == 0 else None)
+            un._slot_ok[j] = y.st is not None
+            pending.append((f"zero_convs.{j}.0", slots2[j][slots[j].shape[0]:], j, h, w))
+            cur = y
+        y = Act(slots2[-1], None, st2[-1])
+        self._run_block(self.middle, cur, y, ea2, kv2, 2 * N, h, w)
+        un._slot_ok[-1] = y.st is not None
+        pending.append(("middle_block_out.0", slots2[-1][slots[-1].shape[0]:], len(self.input_blocks), h, w))
+        return slots, pending

@@ -170,7 +170,7 @@ class B200DDIMSampler:
                getattr(m, "only_mid_control", False), tuple(getattr(m, "control_scales", ())),
                # a graph holds raw pointers and the launch structure of the moment it was captured: reloaded weights
                # (new tensors), another stream layout or another GroupNorm path need a new capture
-               getattr(m, "_weights_epoch", 0), getattr(m, "concurrent", None),
+               getattr(m, "_weights_epoch", 0), getattr(m, "concurrent", None), getattr(m, "grouped", None),
                tuple(getattr(n, "fused_gn_stats", None) for n in nets))
         if g is None or g["key"] != key:
             sx, st = x.clone(), t.clone()

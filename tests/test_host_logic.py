@@ -84,15 +84,32 @@ def test_fused_skip_projection_plumbing(faked, tiny_params, monkeypatch):
             assert w.shape[1] == 9 * x2d.shape[1] + kw["x2"].shape[1] and kw.get("residual") is None
         return real(x2d, w, y2d, **kw)
 
+    real_g = fake_ops.conv2d_grouped
+
+    def spy_grouped(x2d, w, y2d, **kw):  # the stacked (UNet | ControlNet) trunk: one call covers the layer of both networks
+        if kw.get("x2") is not None:
+            seen.append((w.shape[0] // 2, x2d.shape[1], kw["x2"].shape[1]))
+            assert w.shape[1] == 9 * x2d.shape[1] + kw["x2"].shape[1] and kw.get("residual") is None
+        return real_g(x2d, w, y2d, **kw)
+
     monkeypatch.setattr(ops, "conv2d", spy)
+    monkeypatch.setattr(ops, "conv2d_grouped", spy_grouped)
     monkeypatch.setattr(ops, "conv2d_supported", lambda *a, **k: True)
     m = B200ControlLDM(tiny_params, tiny_params, dtype=torch.bfloat16, device="cpu").load_state_dict(sd)
     un, cn = m.model.diffusion_model, m.control_model
     with torch.no_grad():
         ref = o.apply_model(x, t, cond)
         fused = m.apply_model(x, t, cond)
-    n_proj = sum(1 for net in (un, cn) for l in net._res_layers() if l[2] != l[3])
-    assert len(seen) == n_proj > 0, (len(seen), n_proj)           # every channel-changing ResBlock took the fused form
+    n_un = sum(1 for l in un._res_layers() if l[2] != l[3])
+    n_cn = sum(1 for l in cn._res_layers() if l[2] != l[3])
+    assert len(seen) == n_un > 0, (len(seen), n_un)               # every channel-changing ResBlock took the fused form
+    m.grouped = False                                             # two separate trunks: the ControlNet's layers are own launches
+    m.invalidate_cond_cache()
+    seen.clear()
+    with torch.no_grad():
+        assert rel(m.apply_model(x, t, cond), fused) < 1e-6
+    assert len(seen) == n_un + n_cn
+    m.grouped = True
     un.fuse_skip = cn.fuse_skip = False
     m.invalidate_cond_cache()
     seen.clear()
@@ -323,3 +340,66 @@ def test_non_power_of_two_maps_use_the_two_phase_groupnorm(faked, tiny_params):
     t = torch.tensor([501])
     with torch.no_grad():
         assert rel(m.apply_model(x, t, cond), o.apply_model(x, t, cond)) < 1.5e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_grouped_trunk_matches_two_networks(faked, tiny_params, monkeypatch, dtype):
+    """UNet encoder + ControlNet trunk as ONE stacked network (nets.B200GroupedTrunk, mkd_conv_desc.wgroups = 2) against the two
+    separate networks: same eps (the fakes compute part by part, so equality is exact), half the trunk's conv / norm calls, the
+    UNet half of each block output lands in the decoder's concat slot in place, control scales / only_mid_control / a doubled
+    CFG batch / the reference's module-level call forms afterwards all keep working."""
+    o = OracleControlLDM(control_params=tiny_params, unet_params=tiny_params).eval()
+    sd = seeded_state_dict(o, 0)
+    m = B200ControlLDM(tiny_params, tiny_params, dtype=dtype, device="cpu").load_state_dict(sd)
+    cond, x = cond_x(2, 8, seed=11)
+    t = torch.tensor([981, 41])
+    calls = {"conv2d": 0, "conv2d_grouped": 0, "layernorm": 0}
+    for name in calls:
+        def counted(*a, _f=getattr(fake_ops, name), _n=name, **k):
+            calls[_n] += 1
+            return _f(*a, **k)
+        monkeypatch.setattr(ops, name, counted)
+    with torch.no_grad():
+        ref = o.apply_model(x, t, cond)
+        assert m.grouped
+        g = m.apply_model(x, t, cond)
+        n_grouped, n_ln_grouped = dict(calls), calls["layernorm"]
+        assert n_grouped["conv2d_grouped"] > 0
+        m.grouped = False
+        m.invalidate_cond_cache()
+        for k in calls:
+            calls[k] = 0
+        s = m.apply_model(x, t, cond)
+        assert calls["conv2d_grouped"] == 0
+        # every trunk layer of the ControlNet rode along with the UNet's: that many conv launches fewer
+        assert calls["conv2d"] - n_grouped["conv2d"] == 2 * n_grouped["conv2d_grouped"]
+        assert calls["layernorm"] > n_ln_grouped
+        assert torch.equal(g, s)
+        assert rel(g, ref) < (2e-5 if dtype == torch.float32 else 1.5e-2)
+        m.grouped = True
+        m.invalidate_cond_cache()
+        # control scales and only_mid_control act on the injecting zero-convs, which are unchanged
+        m.control_scales = [0.5 + 0.1 * i for i in range(13)]
+        o.control_scales = list(m.control_scales)
+        assert rel(m.apply_model(x, t, cond), o.apply_model(x, t, cond)) < (2e-5 if dtype == torch.float32 else 1.5e-2)
+        m.only_mid_control = o.only_mid_control = True
+        assert rel(m.apply_model(x, t, cond), o.apply_model(x, t, cond)) < (2e-5 if dtype == torch.float32 else 1.5e-2)
+        m.only_mid_control = o.only_mid_control = False
+        m.control_scales = o.control_scales = [1.0] * 13
+        # doubled batch (CFG rows) and a cond without hint (plain UNet path) through the same objects
+        c2 = {"c_crossattn": [torch.cat([cond["c_crossattn"][0]] * 2)], "c_concat": [torch.cat([cond["c_concat"][0]] * 2)]}
+        x2, t2 = torch.cat([x, x + 0.5]), torch.cat([t, t])
+        assert rel(m.apply_model(x2, t2, c2), o.apply_model(x2, t2, c2)) < (2e-5 if dtype == torch.float32 else 1.5e-2)
+        nc = {"c_crossattn": cond["c_crossattn"], "c_concat": None}
+        assert rel(m.apply_model(x, t, nc), o.apply_model(x, t, nc)) < (2e-5 if dtype == torch.float32 else 1.5e-2)
+        # module-level call forms on networks whose concat buffers are now double height
+        ctx, hint = cond["c_crossattn"][0], cond["c_concat"][0]
+        ctl = m.control_model(x=x, hint=hint, timesteps=t, context=ctx)
+        e = m.model.diffusion_model(x=x, timesteps=t, context=ctx, control=ctl, only_mid_control=False)
+        assert rel(e, ref) < (2e-5 if dtype == torch.float32 else 1.5e-2)
+        # and the fused path again after them (arena epochs invalidate the hoisted cond tensors)
+        assert torch.equal(m.apply_model(x, t, cond), g)
+    # reloading weights rebuilds the stacked copies
+    tr = m._grouped_trunk()
+    m.load_state_dict(sd)
+    assert m._trunk is None and m._grouped_trunk() is not tr
