@@ -139,8 +139,6 @@ def workload_config(args, world):
                            + (" fused into the last DDIM-update kernel (peer stores)" if getattr(args, "fused_gather", False)
                               and world > 1 else " (NCCL)" if world > 1 else ""),
             "cuda_graph": not args.no_graph,
-            "trunks": "UNet encoder and ControlNet trunk as two networks on two streams" if getattr(args, "no_grouped", False)
-                      else "UNet encoder + ControlNet trunk as one stacked network (two weight groups per launch)",
             "l2": "per-step working set (2.44 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -250,7 +248,9 @@ def main():
 
     model = B200ControlLDM(dtype=torch.bfloat16, device=dev)
     model.load_state_dict(synthetic_state_dict(model, 0, dev))
-    model.grouped = not args.no_grouped
+    if args.no_grouped:
+        model.grouped = False
+    args.stacked = bool(model._use_grouped(rows, h, h))
     sampler = B200DDIMSampler(model, use_cuda_graph=not args.no_graph)
     if args.decode:
         from makeupdiffuse_b200 import B200FirstStageDecoder
@@ -513,6 +513,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(args, world),
+                "trunks": "UNet encoder + ControlNet trunk as one stacked network (two weight groups per launch)" if args.stacked
+                          else "UNet encoder and ControlNet trunk as two networks on two streams",
                 "ms_per_unet_controlnet_step": ms_model_step,
                 "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},

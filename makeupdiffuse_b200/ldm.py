@@ -55,8 +55,10 @@ class B200ControlLDM:
         self.concurrent = True
         self._side = None
         # UNet encoder + ControlNet trunk as one stacked network (nets.B200GroupedTrunk): each layer of the two structurally
-        # identical trunks is one launch over both batches.  False: two networks, two streams (A/B runs)
-        self.grouped = True
+        # identical trunks is one launch over both batches.  "auto": when every level's rows per network are whole 256-row tile
+        # pairs (what the grouped kernel takes) on the bf16 path; True / False force one form (tests, A/B runs).  Results do
+        # not depend on it.
+        self.grouped = "auto"
         self._trunk = None
 
     @property
@@ -81,6 +83,15 @@ class B200ControlLDM:
         self._weights_epoch += 1
         self._trunk = None  # stacked copies of the trunk weights: rebuilt from the new ones on first use
         return self
+
+    def _stack_cond(self, prep):
+        prep["kv2"], prep["hint2"] = self._grouped_trunk().stack_cond(prep["kv_unet"], prep["kv_cn"], prep["hint"])
+
+    def _use_grouped(self, N, H, W):
+        if self.grouped != "auto":
+            return bool(self.grouped)
+        ds = self.model.diffusion_model._ds  # the deepest level decides: its row count is the smallest
+        return self.dtype != torch.float32 and (N * (H // ds) * (W // ds)) % 256 == 0
 
     def _grouped_trunk(self):
         if self._trunk is None:
@@ -107,13 +118,14 @@ class B200ControlLDM:
         """forget the hoisted per-cond tensors: the next apply_model recomputes the hint block and the K/V projections"""
         self._cond_cache.clear()
 
-    def _prepare(self, cond):
+    def _prepare(self, cond, grouped=False):
         ctx_list, cat_list = cond["c_crossattn"], cond["c_concat"]
         un, cn = self.model.diffusion_model, self.control_model
         key = (tuple(self._tkey(t) for t in ctx_list), None if cat_list is None else tuple(self._tkey(t) for t in cat_list))
         hit = self._cond_cache.get("k")
-        if hit is not None and hit[0] == key and hit[4] == (un.arena_epoch, cn.arena_epoch) and \
-                (not self.grouped or cat_list is None or "kv2" in hit[1]):
+        if hit is not None and hit[0] == key and hit[4] == (un.arena_epoch, cn.arena_epoch):
+            if grouped and "kv2" not in hit[1]:
+                self._stack_cond(hit[1])
             return hit[1]
         ctx = ctx_list[0] if len(ctx_list) == 1 else torch.cat(ctx_list, 1)
         prep = {"kv_unet": un.context_kv(ctx)}
@@ -121,8 +133,8 @@ class B200ControlLDM:
             hint = cat_list[0] if len(cat_list) == 1 else torch.cat(cat_list, 1)
             prep["kv_cn"] = cn.context_kv(ctx)
             prep["hint"] = cn.hint_features(hint)
-            if self.grouped:
-                prep["kv2"], prep["hint2"] = self._grouped_trunk().stack_cond(prep["kv_unet"], prep["kv_cn"], prep["hint"])
+            if grouped:
+                self._stack_cond(prep)
         # keep the source tensors alive so data_ptr-based keys cannot be recycled
         self._cond_cache["k"] = (key, prep, ctx_list, cat_list, (un.arena_epoch, cn.arena_epoch))
         return prep
@@ -132,15 +144,18 @@ class B200ControlLDM:
         assert isinstance(cond, dict)
         un, cn = self.model.diffusion_model, self.control_model
         N, _, H, W = x_noisy.shape
-        prep = self._prepare(cond)
-        t = t.to(torch.int64).contiguous()
         use_cn = cond["c_concat"] is not None
-        grouped = use_cn and self.grouped
+        grouped = use_cn and self._use_grouped(N, H, W)
+        prep = self._prepare(cond, grouped)
+        t = t.to(torch.int64).contiguous()
         two_streams = use_cn and self.concurrent and x_noisy.is_cuda
         pending = None
         if grouped:
             # both trunks as one stacked network on this stream; only the injecting zero-convs go to the side stream below
-            slots, pending = self._grouped_trunk().run(x_noisy, prep["hint2"], t, prep["kv2"], N, H, W)
+            if two_streams and self._side is None:
+                self._side = torch.cuda.Stream(device=x_noisy.device)
+            slots, pending = self._grouped_trunk().run(x_noisy, prep["hint2"], t, prep["kv2"], N, H, W,
+                                                       side=self._side if two_streams else None)
         elif two_streams:
             # The ControlNet trunk depends only on (x, t, hint, ctx): fork it onto a second stream so its many small,
             # latency-bound kernels fill the SMs the UNet encoder's leave idle.  Inside a CUDA-graph capture this

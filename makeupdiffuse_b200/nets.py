@@ -871,14 +871,27 @@ class B200GroupedTrunk(_Net):
         h2[hint.shape[0]:].copy_(hint)
         return kv2, h2
 
-    def run(self, x, hint2, t, kv2, N, H, W):
+    def run(self, x, hint2, t, kv2, N, H, W, side=None):
         """both trunks; leaves the UNet ready for decode() (skip slots, statistics flags, time embedding) and returns
-        (slots, the ControlNet's 13 pending zero-conv calls) like encode() + run_trunk() did"""
+        (slots, the ControlNet's 13 pending zero-conv calls) like encode() + run_trunk() did.
+        side: optional second stream — the two time-embedding MLPs (eight skinny launches that depend on t only) run there
+        while this stream lays out x_t and runs the stacked conv_in; the first ResBlock waits for them."""
         un, cn = self.un, self.cn
         self.fused_gn_stats, self.fuse_skip = un.fused_gn_stats, un.fuse_skip  # the A/B switches follow the UNet's
         ea2 = self._buf("emb_all2", 2 * N, un._emb_total)
-        un._time_embedding(t, N, out=ea2[:N])
-        cn._time_embedding(t, N, out=ea2[N:, :cn._emb_total])
+        emb_done = None
+        if side is not None:
+            main = torch.cuda.current_stream()
+            fork, emb_done = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                un._time_embedding(t, N, out=ea2[:N])
+                cn._time_embedding(t, N, out=ea2[N:, :cn._emb_total])
+                emb_done.record(side)
+        else:
+            un._time_embedding(t, N, out=ea2[:N])
+            cn._time_embedding(t, N, out=ea2[N:, :cn._emb_total])
         un._emb_cur = ea2[:N]
         slots, slots2 = un.skip_slots(N, H, W), un.skip_slots(N, H, W, full=True)
         un._slot_st, st2 = un.skip_slot_stats(N, H, W), un.skip_slot_stats(N, H, W, full=True)
@@ -893,6 +906,8 @@ class B200GroupedTrunk(_Net):
             un._slot_ok[j] = y.st is not None
             pending.append((f"zero_convs.{j}.0", slots2[j][slots[j].shape[0]:], j, h, w))
             cur = y
+            if j == 0 and emb_done is not None:
+                main.wait_event(emb_done)  # block 0 is conv_in alone: every later block reads the embeddings
         y = Act(slots2[-1], None, st2[-1])
         self._run_block(self.middle, cur, y, ea2, kv2, 2 * N, h, w)
         un._slot_ok[-1] = y.st is not None

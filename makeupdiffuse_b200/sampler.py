@@ -182,7 +182,13 @@ class B200DDIMSampler:
                 out = self.model.apply_model(sx, st, c)
             g = self._graph = {"key": key, "graph": graph, "x": sx, "t": st, "out": out,
                                "launches": _lib.load().mkd_launch_count() - n0}
-        prepare(c)  # no-op when the cond is unchanged; otherwise recomputes the hoisted tensors eagerly
+        # no-op when the cond is unchanged; otherwise recomputes the hoisted tensors eagerly (in the stacked form too when the
+        # captured evaluation runs the two trunks as one network)
+        ug = getattr(m, "_use_grouped", None)
+        if ug is not None:
+            prepare(c, c["c_concat"] is not None and ug(x.shape[0], x.shape[2], x.shape[3]))
+        else:
+            prepare(c)
         g["x"].copy_(x)
         g["t"].copy_(t)
         g["graph"].replay()

@@ -96,6 +96,7 @@ def test_fused_skip_projection_plumbing(faked, tiny_params, monkeypatch):
     monkeypatch.setattr(ops, "conv2d_grouped", spy_grouped)
     monkeypatch.setattr(ops, "conv2d_supported", lambda *a, **k: True)
     m = B200ControlLDM(tiny_params, tiny_params, dtype=torch.bfloat16, device="cpu").load_state_dict(sd)
+    m.grouped = True
     un, cn = m.model.diffusion_model, m.control_model
     with torch.no_grad():
         ref = o.apply_model(x, t, cond)
@@ -361,7 +362,8 @@ def test_grouped_trunk_matches_two_networks(faked, tiny_params, monkeypatch, dty
         monkeypatch.setattr(ops, name, counted)
     with torch.no_grad():
         ref = o.apply_model(x, t, cond)
-        assert m.grouped
+        assert m.grouped == "auto" and not m._use_grouped(2, 8, 8) and not m._use_grouped(16, 32, 32) == (dtype == torch.float32)
+        m.grouped = True
         g = m.apply_model(x, t, cond)
         n_grouped, n_ln_grouped = dict(calls), calls["layernorm"]
         assert n_grouped["conv2d_grouped"] > 0
