@@ -195,6 +195,9 @@ def main():
                          "20-step DDIM, sharded over the GPUs")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grouped", action="store_true",
+                    help="A/B: force the stacked trunk where the default ('auto') would not pick it (levels whose rows per network are "
+                         "not whole tile pairs then run one launch per network)")
     ap.add_argument("--no-grouped", action="store_true",
                     help="A/B: UNet encoder and ControlNet trunk as two networks on two streams instead of one stacked network")
     ap.add_argument("--fused-gather", action="store_true",
@@ -248,8 +251,8 @@ def main():
 
     model = B200ControlLDM(dtype=torch.bfloat16, device=dev)
     model.load_state_dict(synthetic_state_dict(model, 0, dev))
-    if args.no_grouped:
-        model.grouped = False
+    if args.no_grouped or args.grouped:
+        model.grouped = bool(args.grouped)
     args.stacked = bool(model._use_grouped(rows, h, h))
     sampler = B200DDIMSampler(model, use_cuda_graph=not args.no_graph)
     if args.decode:
@@ -391,6 +394,9 @@ def main():
             px = torch.cat([px] * 2)
         t = torch.full((rows,), 501, device=dev, dtype=torch.long)
         was_concurrent, model.concurrent = model.concurrent, False  # one stream: a launch's events bracket it alone
+        # as inside the sampler's loop: the timestep embeddings come from the per-loop table (B200ControlLDM.set_step)
+        model.precompute_time_embeddings([501])
+        model.set_step(501, rows)
         model.apply_model(px, t, cond)
         torch.cuda.synchronize()
         ops.PROFILE = []
@@ -402,6 +408,7 @@ def main():
         torch.cuda.synchronize()
         serial_ms = s0.elapsed_time(s1)
         model.concurrent = was_concurrent
+        model.set_step(None)
         prof, ops.PROFILE = ops.PROFILE, None
         other, attn_prof = {}, []
         all_prof = prof

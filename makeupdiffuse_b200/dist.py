@@ -62,12 +62,16 @@ def sample_sharded(sampler, S, batch_global, shape, cond_local, x_T_local, rank=
     mine = gathered[lo:hi]
     sampler.make_schedule(ddim_num_steps=S, ddim_eta=kw.pop("eta", 0.0), verbose=False)
     steps = np.flip(sampler.ddim_timesteps)
-    if hasattr(sampler, "begin_loop"):
-        sampler.begin_loop()  # this loop reads its cond afresh (B200DDIMSampler.begin_loop)
+    own = hasattr(sampler, "begin_loop")
+    if own:
+        sampler.begin_loop(steps)  # this loop reads its cond afresh, timestep embeddings of all steps at once (B200DDIMSampler)
+        kw = dict(kw)
     x = x_T_local
     for i, step in enumerate(steps):
         ts = torch.full((b,), int(step), device=x.device, dtype=torch.long)
         last = i == len(steps) - 1
+        if own:
+            kw["t_value"] = int(step)
         x, _ = sampler.denoising_step(x, cond_local, ts, index=len(steps) - i - 1, out=mine if last else None,
                                       peer_ptrs=peer_ptrs if last else None, **kw)
     if fused:

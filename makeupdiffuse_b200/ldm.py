@@ -60,6 +60,10 @@ class B200ControlLDM:
         # not depend on it.
         self.grouped = "auto"
         self._trunk = None
+        # ResBlock timestep embeddings of a whole sampling loop, computed ahead of it (precompute_time_embeddings / set_step)
+        self._emb_table = None
+        self._emb_bufs = {}
+        self._emb_rows = None
 
     @property
     def device(self):
@@ -83,6 +87,39 @@ class B200ControlLDM:
         self._weights_epoch += 1
         self._trunk = None  # stacked copies of the trunk weights: rebuilt from the new ones on first use
         return self
+
+    # ---- timestep embeddings of a sampling loop ---------------------------------------------------------------------
+    # emb = emb_layers(time_embed(timestep_embedding(t))) depends on t alone.  A DDIM loop knows its timesteps up front and
+    # uses ONE t for the whole batch (cddim.py:86-89 / upstream ddim_sampling: ts = torch.full((b,), step)), so the sampler
+    # asks for all S of them at once — two MLP chains over S rows instead of S x 2 chains over the batch, each streaming
+    # ~85 MB of weights for 16 rows — and selects one row per step.  apply_model(x, t, cond) without a selected step
+    # computes the embeddings from its t argument as before.
+    def precompute_time_embeddings(self, values):
+        vals = tuple(int(v) for v in values)
+        tb = self._emb_table
+        if tb is not None and tb["vals"] == vals and tb["epoch"] == self._weights_epoch:
+            return
+        un, cn = self.model.diffusion_model, self.control_model
+        tv = torch.tensor(vals, dtype=torch.int64, device=self._device)
+        tab = torch.zeros(len(vals), 2, un._emb_total, dtype=self.dtype, device=self._device)
+        un._time_embedding(tv, len(vals), out=tab[:, 0])
+        cn._time_embedding(tv, len(vals), out=tab[:, 1, :cn._emb_total])
+        self._emb_table = {"vals": vals, "row": {v: i for i, v in enumerate(vals)}, "tab": tab, "epoch": self._weights_epoch}
+
+    def set_step(self, t_value, rows=None):
+        """select the precomputed embeddings of timestep ``t_value`` for the next apply_model calls on ``rows`` batch rows
+        (all at that timestep); ``None`` returns to computing them from the ``t`` argument.  Returns whether a row is selected."""
+        self._emb_rows = None
+        tb = self._emb_table
+        if t_value is None or tb is None or tb["epoch"] != self._weights_epoch or int(t_value) not in tb["row"]:
+            return False
+        tot = tb["tab"].shape[2]
+        buf = self._emb_bufs.get(rows)
+        if buf is None:
+            buf = self._emb_bufs[rows] = torch.empty(2 * rows, tot, dtype=self.dtype, device=self._device)
+        buf.view(2, rows, tot).copy_(tb["tab"][tb["row"][int(t_value)]][:, None, :].expand(2, rows, tot))
+        self._emb_rows = rows
+        return True
 
     def _stack_cond(self, prep):
         prep["kv2"], prep["hint2"] = self._grouped_trunk().stack_cond(prep["kv_unet"], prep["kv_cn"], prep["hint"])
@@ -148,6 +185,9 @@ class B200ControlLDM:
         grouped = use_cn and self._use_grouped(N, H, W)
         prep = self._prepare(cond, grouped)
         t = t.to(torch.int64).contiguous()
+        emb2 = self._emb_bufs[N] if self._emb_rows == N else None  # [UNet rows | ControlNet rows] of the selected step
+        emb_un = None if emb2 is None else emb2[:N]
+        emb_cn = None if emb2 is None else emb2[N:, :cn._emb_total]
         two_streams = use_cn and self.concurrent and x_noisy.is_cuda
         pending = None
         if grouped:
@@ -155,7 +195,7 @@ class B200ControlLDM:
             if two_streams and self._side is None:
                 self._side = torch.cuda.Stream(device=x_noisy.device)
             slots, pending = self._grouped_trunk().run(x_noisy, prep["hint2"], t, prep["kv2"], N, H, W,
-                                                       side=self._side if two_streams else None)
+                                                       side=self._side if two_streams else None, emb2=emb2)
         elif two_streams:
             # The ControlNet trunk depends only on (x, t, hint, ctx): fork it onto a second stream so its many small,
             # latency-bound kernels fill the SMs the UNet encoder's leave idle.  Inside a CUDA-graph capture this
@@ -167,11 +207,11 @@ class B200ControlLDM:
             fork.record(main)
             self._side.wait_event(fork)
             with torch.cuda.stream(self._side):
-                pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W)
+                pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W, emb=emb_cn)
                 join.record(self._side)
         if not grouped:
             xin = un._x_in(x_noisy)
-            slots = un.encode(xin, t, prep["kv_unet"], N, H, W)
+            slots = un.encode(xin, t, prep["kv_unet"], N, H, W, emb=emb_un)
         before_block = None
         if use_cn:
             nb = len(un.input_blocks)
@@ -206,7 +246,7 @@ class B200ControlLDM:
                         main.wait_event(tail)  # joins the side stream whatever was injected
             else:
                 if not grouped:
-                    pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W)
+                    pending = cn.run_trunk(cn._x_in(x_noisy), prep["hint"], t, prep["kv_cn"], N, H, W, emb=emb_cn)
                 cn.zero_convs(pending, N, inject=inject, scales=self.control_scales, inject_st=inject_st)
             un.note_slots_rewritten([j for j, s in enumerate(inject) if s is not None], with_stats=True)
         e = un.decode(prep["kv_unet"], N, H, W, before_block=before_block)

@@ -592,11 +592,12 @@ class B200ControlNet(_Net):
             cur, H, W = out, Ho, Wo
         return cur[:, :self.mc]
 
-    def run_trunk(self, x_nhwc, guided_hint, t, ctx_kv, N, H, W):
+    def run_trunk(self, x_nhwc, guided_hint, t, ctx_kv, N, H, W, emb=None):
         """time embedding + input blocks + middle block.  Returns the 13 pending zero-conv calls
         [(weight key, input view, index, h, w)]: the trunk touches no UNet buffer, so it can run on a second stream
-        concurrently with the UNet encoder; the zero-convs (which may inject into UNet skip slots) come after the join."""
-        emb_all = self._time_embedding(t, N)
+        concurrently with the UNet encoder; the zero-convs (which may inject into UNet skip slots) come after the join.
+        emb: the ResBlock embeddings [N, _emb_total] when the caller already holds them (B200ControlLDM.set_step)."""
+        emb_all = self._time_embedding(t, N) if emb is None else emb
         pending = []
         cur, h, w = Act(x_nhwc), H, W
         for j, blk in enumerate(self.input_blocks):
@@ -743,8 +744,8 @@ class B200ControlledUnet(_Net):
         for j in js:
             self._slot_ok[j] = bool(with_stats) and self._slot_st[j] is not None
 
-    def encode(self, x_nhwc, t, ctx_kv, N, H, W):
-        self._emb_cur = self._time_embedding(t, N)
+    def encode(self, x_nhwc, t, ctx_kv, N, H, W, emb=None):
+        self._emb_cur = self._time_embedding(t, N) if emb is None else emb
         slots = self.skip_slots(N, H, W)
         self._slot_st = self.skip_slot_stats(N, H, W)
         self._slot_ok = [False] * len(slots)
@@ -871,16 +872,19 @@ class B200GroupedTrunk(_Net):
         h2[hint.shape[0]:].copy_(hint)
         return kv2, h2
 
-    def run(self, x, hint2, t, kv2, N, H, W, side=None):
+    def run(self, x, hint2, t, kv2, N, H, W, side=None, emb2=None):
         """both trunks; leaves the UNet ready for decode() (skip slots, statistics flags, time embedding) and returns
         (slots, the ControlNet's 13 pending zero-conv calls) like encode() + run_trunk() did.
         side: optional second stream — the two time-embedding MLPs (eight skinny launches that depend on t only) run there
-        while this stream lays out x_t and runs the stacked conv_in; the first ResBlock waits for them."""
+        while this stream lays out x_t and runs the stacked conv_in; the first ResBlock waits for them.
+        emb2: the stacked embeddings [2N, un._emb_total] when the caller already holds them (B200ControlLDM.set_step)."""
         un, cn = self.un, self.cn
         self.fused_gn_stats, self.fuse_skip = un.fused_gn_stats, un.fuse_skip  # the A/B switches follow the UNet's
-        ea2 = self._buf("emb_all2", 2 * N, un._emb_total)
+        ea2 = self._buf("emb_all2", 2 * N, un._emb_total) if emb2 is None else emb2
         emb_done = None
-        if side is not None:
+        if emb2 is not None:
+            pass
+        elif side is not None:
             main = torch.cuda.current_stream()
             fork, emb_done = torch.cuda.Event(), torch.cuda.Event()
             fork.record(main)

@@ -104,10 +104,10 @@ class B200DDIMSampler:
                       dynamic_threshold=None, **kwargs):
         dev = self.model.device
         b = shape[0]
-        self.begin_loop()
+        steps = np.flip(self.ddim_timesteps)
+        self.begin_loop(steps)
         img = torch.randn(shape, device=dev) if x_T is None else x_T
         inter = {"x_inter": [img], "pred_x0": [img]}
-        steps = np.flip(self.ddim_timesteps)
         total = steps.shape[0]
         for i, step in enumerate(steps):
             index = total - i - 1
@@ -118,7 +118,8 @@ class B200DDIMSampler:
                 img, cond, ts, index=index, quantize_denoised=quantize_denoised, temperature=temperature,
                 noise_dropout=noise_dropout, score_corrector=score_corrector, corrector_kwargs=corrector_kwargs,
                 unconditional_guidance_scale=unconditional_guidance_scale,
-                unconditional_conditioning=unconditional_conditioning, dynamic_threshold=dynamic_threshold)
+                unconditional_conditioning=unconditional_conditioning, dynamic_threshold=dynamic_threshold,
+                t_value=int(step))
             if callback:
                 callback(i)
             if img_callback:
@@ -128,15 +129,20 @@ class B200DDIMSampler:
                 inter["pred_x0"].append(pred_x0)
         return img, inter
 
-    def begin_loop(self):
+    def begin_loop(self, steps=None):
         """A sampling loop starts: whatever was hoisted for an earlier cond (the model's hint features and K/V, the
         doubled CFG cond) is dropped, so the loop reads its conditioning tensors as they are NOW — also when the caller
         refilled the same tensors in a way torch's version counter does not see.  Loops driven from outside
-        (makeupdiffuse_b200.dist.sample_sharded, a caller's own loop over denoising_step) call this themselves."""
+        (makeupdiffuse_b200.dist.sample_sharded, a caller's own loop over denoising_step) call this themselves.
+        steps: the loop's timesteps, when known: the model computes the timestep embeddings of all of them at once, and
+        denoising_step(..., t_value=step) selects one per step."""
         self._cfg_cache = None
         inv = getattr(self.model, "invalidate_cond_cache", None)
         if inv is not None:
             inv()
+        pre = getattr(self.model, "precompute_time_embeddings", None)
+        if pre is not None and steps is not None and len(steps):
+            pre([int(v) for v in steps])
 
     def p_sample_ddim(self, *a, **k):
         with torch.no_grad():
@@ -154,9 +160,21 @@ class B200DDIMSampler:
             return self.reconstruct(x_latent, cond, t_start, **kw)
 
     # ---- the model call, optionally as a CUDA-graph replay -------------------------------------------------------
-    def _eps(self, x, t, c):
+    def _eps(self, x, t, c, t_value=None):
         """model.apply_model(x, t, c); with use_cuda_graph the ~10^3 kernel launches of one UNet+ControlNet step are
-        captured once per (cond, batch shape) and replayed (launch-bound otherwise: SURVEY.md §7 hard part 6)."""
+        captured once per (cond, batch shape) and replayed (launch-bound otherwise: SURVEY.md §7 hard part 6).
+        t_value: the loop's timestep as a host int when every row of ``t`` holds it (the sampler's own loops): the model
+        then takes the ResBlock timestep embeddings from the table computed at the start of the loop (begin_loop(steps))
+        instead of running the two embedding MLPs again."""
+        set_step = getattr(self.model, "set_step", None)
+        if set_step is None or t_value is None:
+            return self._eps_call(x, t, c, False)
+        try:
+            return self._eps_call(x, t, c, set_step(t_value, x.shape[0]))
+        finally:
+            set_step(None)
+
+    def _eps_call(self, x, t, c, emb_selected):
         prepare = getattr(self.model, "_prepare", None)
         if not (self.use_cuda_graph and x.is_cuda and prepare is not None):
             return self.model.apply_model(x, t, c)
@@ -170,7 +188,7 @@ class B200DDIMSampler:
                getattr(m, "only_mid_control", False), tuple(getattr(m, "control_scales", ())),
                # a graph holds raw pointers and the launch structure of the moment it was captured: reloaded weights
                # (new tensors), another stream layout or another GroupNorm path need a new capture
-               getattr(m, "_weights_epoch", 0), getattr(m, "concurrent", None), getattr(m, "grouped", None),
+               getattr(m, "_weights_epoch", 0), getattr(m, "concurrent", None), getattr(m, "grouped", None), emb_selected,
                tuple(getattr(n, "fused_gn_stats", None) for n in nets))
         if g is None or g["key"] != key:
             sx, st = x.clone(), t.clone()
@@ -199,11 +217,12 @@ class B200DDIMSampler:
     def denoising_step(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
                        temperature=1.0, noise_dropout=0.0, score_corrector=None, corrector_kwargs=None,
                        unconditional_guidance_scale=1.0, unconditional_conditioning=None, dynamic_threshold=None,
-                       out=None, peer_ptrs=None):
+                       out=None, peer_ptrs=None, t_value=None):
         """``out`` (extension, optional): tensor that receives x_prev — e.g. this rank's slice of an all-gather
         buffer, so the last update of a sharded run lands directly where the collective reads it.
         ``peer_ptrs`` (extension, optional): device pointers of that same slice inside EVERY rank's gather buffer (peer
-        memory); the update kernel then stores x_prev to all of them — the all-gather fused into the kernel."""
+        memory); the update kernel then stores x_prev to all of them — the all-gather fused into the kernel.
+        ``t_value`` (extension, optional): the timestep as a host int when every row of ``t`` holds it (see _eps)."""
         m = self.model
         if m.parameterization != "eps":
             raise NotImplementedError("B200 path implements the yaml's parameterization: eps (yaml:50)")
@@ -215,12 +234,12 @@ class B200DDIMSampler:
         x = x.float().contiguous()
         cfg = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.0)
         if not cfg:
-            e = self._eps(x, t, c)
+            e = self._eps(x, t, c, t_value)
         else:
             cc = self._cfg_cache  # the doubled cond is step-invariant: build it once, not 50 times
             if cc is None or cc[0] is not c or cc[1] is not unconditional_conditioning:
                 cc = self._cfg_cache = (c, unconditional_conditioning, _cat_uncond_first(unconditional_conditioning, c))
-            e = self._eps(torch.cat([x] * 2), torch.cat([t] * 2), cc[2])
+            e = self._eps(torch.cat([x] * 2), torch.cat([t] * 2), cc[2], t_value)
         if use_original_steps:
             if self._coef_orig is None:
                 # cddim.py:54 reads the sigma table off the MODEL; without that attribute the reference raises
@@ -253,13 +272,13 @@ class B200DDIMSampler:
         steps = np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps
         steps = steps[:t_start]
         total = steps.shape[0]
-        self.begin_loop()
+        self.begin_loop(steps)
         x = x_latent
         for i, step in enumerate(np.flip(steps)):
             ts = torch.full((x_latent.shape[0],), int(step), device=x_latent.device, dtype=torch.long)
             x, _ = self.denoising_step(x, cond, ts, index=total - i - 1, use_original_steps=use_original_steps,
                                        unconditional_guidance_scale=unconditional_guidance_scale,
-                                       unconditional_conditioning=unconditional_conditioning)
+                                       unconditional_conditioning=unconditional_conditioning, t_value=int(step))
             if callback:
                 callback(i)
         return x

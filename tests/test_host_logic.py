@@ -405,3 +405,49 @@ def test_grouped_trunk_matches_two_networks(faked, tiny_params, monkeypatch, dty
     tr = m._grouped_trunk()
     m.load_state_dict(sd)
     assert m._trunk is None and m._grouped_trunk() is not tr
+
+
+def test_timestep_embedding_table(faked, pair, monkeypatch):
+    """The sampler's loops compute the ResBlock timestep embeddings of all their steps at once (two MLP chains over S rows)
+    and select one row per step; apply_model without a selected step still derives them from its t argument.  Same eps either
+    way, the embedding kernels leave the per-step call, a reload of the weights or an unknown timestep falls back."""
+    o, m = pair
+    cond, x = cond_x(2, 8, seed=13)
+    n_te = {"n": 0}
+    real = fake_ops.timestep_embedding
+
+    def counted(t, out, *a, **k):
+        n_te["n"] += 1
+        return real(t, out, *a, **k)
+
+    monkeypatch.setattr(ops, "timestep_embedding", counted)
+    for grouped in (False, True):
+        m.grouped = grouped
+        m.invalidate_cond_cache()
+        t = torch.tensor([601, 601])
+        plain = m.apply_model(x, t, cond).clone()
+        m.precompute_time_embeddings([981, 601, 201])
+        n0 = n_te["n"]
+        assert m.set_step(601, 2)
+        assert rel(m.apply_model(x, t, cond), plain) < 1e-5 and n_te["n"] == n0       # no embedding kernels in the step
+        x4, t4 = torch.cat([x, x]), torch.cat([t, t])
+        c4 = {k: [torch.cat([v[0], v[0]])] for k, v in cond.items()}
+        e4 = m.apply_model(x4, t4, c4)                                                # other row count: computed from t
+        assert n_te["n"] == n0 + 2 and rel(e4[:2], plain) < 1e-5
+        assert not m.set_step(777, 2)                                                 # not a step of this loop
+        m.set_step(None)
+        n0 = n_te["n"]
+        assert torch.equal(m.apply_model(x, t, cond), plain) and n_te["n"] == n0 + 2
+    m.grouped = "auto"
+    m.invalidate_cond_cache()
+    # the sampler's loop: one table per loop, none of the 6 steps runs the embedding MLPs
+    s = B200DDIMSampler(m)
+    n0 = n_te["n"]
+    a, _ = s.sample(6, 2, (4, 8, 8), cond, eta=0.0, x_T=x, verbose=False)
+    assert n_te["n"] == n0 + 2
+    b, _ = MKDDIMSampler(o).sample(6, 2, (4, 8, 8), cond, eta=0.0, x_T=x, verbose=False)
+    assert rel(a, b) < 1e-4
+    # a caller's own loop over denoising_step without t_value keeps the per-step computation
+    n0 = n_te["n"]
+    s.denoising_step(x, cond, torch.tensor([981, 981]), index=5)
+    assert n_te["n"] == n0 + 2
