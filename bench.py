@@ -476,7 +476,7 @@ def main():
             others["attention"] = {"bound": "tensor", "kernel": "attn_tcgen05_kernel", "achieved": att_flops / (att["ms"] / 1e3) / 1e12,
                                    "unit": "TFLOP/s", "launches_per_eval": att["n"], "kernel_ms_per_eval": att["ms"],
                                    "note": "4*B*heads*Nq*Nkv*d FLOPs; exp2 / latency bound at head dim 40 (XU pipe 41 %), "
-                                           "46 launches of which 32 are sub-10-us maps"}
+                                           f"{att['n']} launches per evaluation, most of them sub-10-us maps (16x16 and deeper levels, 77-key cross-attention)"}
         for k in ("groupnorm", "groupnorm_apply", "layernorm"):
             if k in other and other[k]["ms"]:
                 gbs = other[k]["bytes"] / (other[k]["ms"] / 1e3) / 1e9

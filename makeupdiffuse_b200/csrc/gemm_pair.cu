@@ -1041,8 +1041,11 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
       while (s > 1 && (size_t)s * pl.M * d->K * sizeof(float) > d->workspace_bytes) --s;
       if (s > 1) pl.splits = s;
     }
-    // too few units to be worth a cluster launch: leave tiny problems to the single-CTA kernel (more, smaller tiles)
-    if (!forced && units * pl.splits < 24) return false;
+    // too few units to be worth a cluster launch: leave tiny problems to the single-CTA kernel (more, smaller tiles) —
+    // except with weight groups, where declining means TWO single-CTA launches back to back: the k-block rate does not depend on
+    // the tile size, so one pair launch over both networks' rows takes the time of one of them (the middle block's K = C GEMMs at
+    // batch 16: 2 x 8 units)
+    if (!forced && d->wgroups != 2 && units * pl.splits < 24) return false;
   }
   pl.kb_per_split = (kblocks + pl.splits - 1) / pl.splits;
   pl.splits = (kblocks + pl.kb_per_split - 1) / pl.kb_per_split;

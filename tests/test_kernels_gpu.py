@@ -522,7 +522,10 @@ WG_CASES = [
     dict(N=32, H=16, W=16, C=640, K=640, R=3, C2=320, y32="both", stats=True),        # out conv + fused skip projection
     dict(N=32, H=32, W=32, C=320, K=320, R=3, stride=2, y32="both"),                  # Downsample in place
     dict(N=32, H=8, W=8, C=1280, K=3840, R=1),                                        # q/k/v at the 8x8 level
-    dict(N=2, H=16, W=16, C=640, K=640, R=1, fallback=True),                          # too few units for the pair kernel: two launches
+    dict(N=2, H=16, W=16, C=640, K=640, R=1),                                         # 2 x 4 units: still one launch (not two single-CTA ones)
+    dict(N=32, H=4, W=4, C=1280, K=1280, R=1, res32=True, y32="only"),                # middle block's attention out-projection: 2 x 8 units
+    dict(N=32, H=4, W=4, C=1280, K=1280, R=1, y32="both"),                            # middle block's proj_in
+    dict(N=2, H=8, W=8, C=640, K=640, R=1, fallback=True),                            # parts that are not whole tile pairs: two launches
 ]
 
 
