@@ -9,8 +9,10 @@ masks and landmarks belongs to the teacher pipeline, which stays out of scope â€
   ``img_name = '<src>&<ref>'``);
 * ``log_results`` â€” ``diffusion_makeup.py:360-411``: x_p -> ``get_z`` -> reconstruction, control_src / control_ref,
   ground_truth, one-step x_0 prediction at a random t >= t_min ("sample_ddmp"), DDIM samples, guided DDIM samples, and
-  the ``test_pairs`` bookkeeping (``:376-381``).  The text panel ``conditioning`` (``log_txt_as_img``, needs a font
-  file) is not produced;
+  the ``test_pairs`` bookkeeping (``:376-381``), and the text panel ``conditioning`` (``:372``, upstream
+  ``ldm.util.log_txt_as_img``: the image names drawn on a white 256 x 256 canvas â€” ``txt_panels`` below; upstream loads
+  ``font/DejaVuSans.ttf`` from the ControlNet checkout, here a TTF path can be passed and PIL's built-in font is the default,
+  so the glyph pixels may differ while key, shape, value range and line wrapping are the reference's);
 * ``sample_log`` â€” upstream ``ControlLDM.sample_log`` as called at ``:393-408`` (shape from ``c_concat``);
 * ``test_step`` / ``save_local`` â€” ``:332-358``: clamp, ``make_grid(nrow = number of panels)``, rescale, HWC, uint8 and
   PNG.  The grid / rescale / uint8 conversion is one CUDA pass (``mkd_image_grid_u8``), byte-identical to the
@@ -53,6 +55,26 @@ def write_test_pairs(path, test_pairs):
             f.write("%s %s %s\n" % (p[0], p[1], p[2]))
 
 
+def txt_panels(wh, captions, size=10, font_path=None):
+    """upstream ``ldm.util.log_txt_as_img`` as called at diffusion_makeup.py:372 with ((256, 256), img_names, size=16): one white
+    RGB canvas of ``wh`` = (width, height) per caption, the caption in black from the top-left corner, wrapped every
+    ``int(40 * width / 256)`` characters; returns [B, 3, H, W] fp32 in [-1, 1] on the host (pure host-side drawing)."""
+    import numpy as np
+    from PIL import Image, ImageDraw, ImageFont
+    font = ImageFont.truetype(font_path, size=size) if font_path else ImageFont.load_default(size=size)
+    nc = int(40 * (wh[0] / 256))
+    out = []
+    for cap in captions:
+        canvas = Image.new("RGB", tuple(wh), color="white")
+        lines = "\n".join(cap[i:i + nc] for i in range(0, len(cap), nc))
+        try:
+            ImageDraw.Draw(canvas).text((0, 0), lines, fill="black", font=font)
+        except UnicodeEncodeError:  # upstream skips captions its font cannot encode and keeps the blank canvas
+            pass
+        out.append(np.array(canvas).transpose(2, 0, 1) / 127.5 - 1.0)
+    return torch.tensor(np.stack(out), dtype=torch.float32)
+
+
 def sample_log(model, cond, batch_size, ddim, ddim_steps, sampler=None, **kwargs):
     """upstream ControlLDM.sample_log: DDIM over shape (4, h / 8, w / 8) taken from the hint"""
     assert ddim, "the reference only samples with DDIM (ddim_steps is set in its configs)"
@@ -63,7 +85,7 @@ def sample_log(model, cond, batch_size, ddim, ddim_steps, sampler=None, **kwargs
 
 @torch.no_grad()
 def log_results(model, batch, batch_idx=0, *, ddim_steps=50, ddim_eta=0.0, sample=True, unconditional_guidance_scale=9.0,
-                t_min=0, test_pairs=None, sampler=None, generator=None):
+                t_min=0, test_pairs=None, sampler=None, generator=None, font_path=None):
     """diffusion_makeup.py:360-411.  ``batch``: 'pgt_sr' [B,3,H,W] in [-1,1] (the teacher output x_p), 'src_img' /
     'ref_img' [B,3,H,W] in [0,1], 'c_crossattn' [B,77,768] or 'tokens' [B,77] or 'txt' (list of prompts), optional
     'img_name'.  Returns the reference's dict of image batches (device tensors in about [-1, 1])."""
@@ -81,6 +103,8 @@ def log_results(model, batch, batch_idx=0, *, ddim_steps=50, ddim_eta=0.0, sampl
     src, ref = torch.chunk(c_cat, 2, dim=1)
     log["control_src"] = src * 2.0 - 1.0
     log["control_ref"] = ref * 2.0 - 1.0
+    if "img_name" in batch:  # diffusion_makeup.py:372 (the reference's batches always carry img_name)
+        log["conditioning"] = txt_panels((256, 256), batch["img_name"], size=16, font_path=font_path).to(dev)
     log["ground_truth"] = pgt_sr
     if test_pairs is not None and "img_name" in batch:
         test_pairs.extend(test_pair_rows(batch_idx, batch["img_name"]))

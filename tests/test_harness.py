@@ -40,6 +40,23 @@ def test_save_local_writes_reference_grids(tmp_path, monkeypatch):
         assert grids[k][0, 0, 0] == 127  # pad_value 0 -> (0 + 1) / 2 * 255 truncated
 
 
+def test_conditioning_text_panels():
+    """log["conditioning"] (diffusion_makeup.py:372; upstream ldm.util.log_txt_as_img): white canvases with the image names in
+    black from the top-left corner, wrapped every int(40 * width / 256) characters, [B, 3, H, W] in [-1, 1]"""
+    names = ["xfsy_0106&vFG112", "", "a" * 95]
+    t = harness.txt_panels((256, 256), names, size=16)
+    assert t.shape == (3, 3, 256, 256) and t.dtype == torch.float32
+    assert float(t.max()) == 1.0 and float(t.min()) == -1.0
+    assert bool((t[1] == 1.0).all())                               # empty caption: blank white canvas
+    ink = lambda x: (x[0] < 0.0).nonzero()                          # noqa: E731  (dark pixels of the first channel: [row, col])
+    one, three = ink(t[0]), ink(t[2])
+    assert 0 < one.shape[0] and int(one[:, 0].max()) < 24           # one line of 16-px text at the top
+    assert int(three[:, 0].max()) > 2 * int(one[:, 0].max())        # 95 characters wrap into 3 lines of 40
+    assert int(three[:, 0].max()) < 80 and int(one[:, 1].min()) < 8  # starts at the left edge
+    w = harness.txt_panels((128, 64), ["b" * 45], size=10)          # other canvas: wrap width scales with the canvas width (20)
+    assert w.shape == (1, 3, 64, 128) and int(ink(w[0])[:, 0].max()) > 20
+
+
 def reference_grid(x, nrow, padding, clamp, rescale):
     return fake_ops.image_grid_u8(x, nrow, padding, clamp, rescale).numpy()
 
@@ -90,8 +107,9 @@ def test_log_results_end_to_end_against_oracle(tmp_path):
     log = harness.log_results(m, batch, 2, ddim_steps=S, unconditional_guidance_scale=scale, t_min=t_min, test_pairs=pairs,
                               sampler=B200DDIMSampler(m, use_cuda_graph=False), generator=gg)
     assert pairs == [["0002-1", "non-makeup/a.png", "makeup/b.png"], ["0002-2", "non-makeup/c.png", "makeup/d.png"]]
-    assert list(log) == ["reconstruction", "control_src", "control_ref", "ground_truth", "sample_ddmp", "samples",
-                         "samples_cfg_scale_9.00"]
+    assert list(log) == ["reconstruction", "control_src", "control_ref", "conditioning", "ground_truth", "sample_ddmp", "samples",
+                         "samples_cfg_scale_9.00"]  # the reference's panels in the reference's order (diffusion_makeup.py:369-408)
+    assert log["conditioning"].shape == (B, 3, 256, 256) and float(log["conditioning"].min()) == -1.0
     # the same flow on the oracle, same random draws in the same order (zn, t, noise; x_T of each DDIM run)
     gg = torch.Generator(device="cuda").manual_seed(11)
     dev = "cuda"
@@ -131,6 +149,6 @@ def test_log_results_end_to_end_against_oracle(tmp_path):
             assert e < 1e-3
     assert log["samples"].shape == (B, 3, hw, hw) and torch.isfinite(log["samples_cfg_scale_9.00"]).all()
     grids = harness.save_local(log, 2, str(tmp_path))
-    assert len(grids) == 7 and os.path.exists(tmp_path / "samples_0002.png")
+    assert len(grids) == 8 and os.path.exists(tmp_path / "samples_0002.png") and os.path.exists(tmp_path / "conditioning_0002.png")
     for k, v in log.items():
-        assert np.array_equal(grids[k], reference_grid(v.float().cpu(), 7, 2, True, True))
+        assert np.array_equal(grids[k], reference_grid(v.float().cpu(), 8, 2, True, True))
