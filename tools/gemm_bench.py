@@ -57,15 +57,27 @@ SHAPES = {
     "conv1280_c2": (16, 8, 8, 1280, 1280, 3, "res32"),
     "conv2560_8x8": (16, 8, 8, 2560, 1280, 3, "emb32"),
     "skip_1x1": (16, 16, 16, 320, 640, 1, "y32"),
+    # the stacked trunk's launches (names g2_*): the same layer of the UNet encoder and the ControlNet trunk on two stacked
+    # batches of 16, mkd_conv_desc.wgroups = 2 (twice the rows of the shapes above, two weight sets)
+    "g2_conv320_c1": (32, 32, 32, 320, 320, 3, "emb32st"),
+    "g2_conv320_c2": (32, 32, 32, 320, 320, 3, "res32st"),
+    "g2_sq320_res32": (32, 32, 32, 320, 320, 1, "res32"),
+    "g2_conv640": (32, 16, 16, 640, 640, 3, "emb32"),
+    "g2_sq640_res32": (32, 16, 16, 640, 640, 1, "res32"),
+    "g2_conv1280": (32, 8, 8, 1280, 1280, 3, "emb32"),
+    "g2_sq1280_res32": (32, 8, 8, 1280, 1280, 1, "res32"),
+    "g2_conv1280_4x4": (32, 4, 4, 1280, 1280, 3, "emb32"),
+    "g2_sq1280_m512": (32, 4, 4, 1280, 1280, 1, "res32"),
 }
 for name, (N, H, W, C, K, R, epi) in SHAPES.items():
     if a.only and a.only not in name:
         continue
     M = N * H * W
+    wg = 2 if name.startswith("g2_") else 1
     x = torch.randn(M, C, device=DEV).bfloat16()
-    w = (torch.randn(K, R, R, C, device=DEV) / math.sqrt(C * R * R)).bfloat16()
-    bias = torch.randn(K, device=DEV)
-    kw = dict(N=N, H=H, W=W, R=R, S=R, pad=R // 2, bias=bias, workspace=ws)
+    w = (torch.randn(wg * K, R, R, C, device=DEV) / math.sqrt(C * R * R)).bfloat16()
+    bias = torch.randn(wg * K, device=DEV)
+    kw = dict(N=N, H=H, W=W, R=R, S=R, pad=R // 2, bias=bias, workspace=ws, wgroups=wg)
     Ko = K
     if epi == "plain":
         y = torch.empty(M, K, device=DEV, dtype=torch.bfloat16)
