@@ -68,6 +68,9 @@ SHAPES = {
     "g2_sq1280_res32": (32, 8, 8, 1280, 1280, 1, "res32"),
     "g2_conv1280_4x4": (32, 4, 4, 1280, 1280, 3, "emb32"),
     "g2_sq1280_m512": (32, 4, 4, 1280, 1280, 1, "res32"),
+    "g2_conv2560_4x4": (32, 4, 4, 2560, 1280, 3, "emb32"),
+    "m512_conv1280": (8, 8, 8, 1280, 1280, 3, "emb32"),    # 512 rows, one network (8x8 level of configs[3]'s 8 rows per GPU)
+    "m512_conv2560": (8, 8, 8, 2560, 1280, 3, "emb32"),
 }
 for name, (N, H, W, C, K, R, epi) in SHAPES.items():
     if a.only and a.only not in name:
