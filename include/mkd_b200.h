@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MKD_ABI_VERSION 9
+#define MKD_ABI_VERSION 10
 
 typedef void* mkd_stream_t; /* cudaStream_t */
 
@@ -186,6 +186,20 @@ typedef struct mkd_conv_desc {
    * Only the tensor-core CTA-pair kernel takes it, with whole 256-row tile pairs per part: mkd_conv2d_path() returns
    * MKD_E_INVALID otherwise and the caller issues one launch per part on row / weight-row slices. */
   int wgroups;
+  /* GroupNorm tail (ABI v10; gn_y == NULL: none).  Where the library runs the layer as split-K partials + reducer (the 8x8 / 4x4
+   * levels at small batch), the reducer — which already reads every output value once — also normalises it: one thread block
+   * per (image, group) sums the partials, applies bias / emb / alpha / residual, stores y / y32 as usual, reduces mean and
+   * variance of the group in fp32 and writes
+   *     gn_y[m, k] = (silu?)( (v[m, k] - mean[n, g]) * rstd[n, g] * gn_gamma[k] + gn_beta[k] )        (activation dtype)
+   * i.e. the GroupNorm32(+SiLU) that follows the conv in a ResBlock (upstream ldm ResBlock.out_layers[0:2]) without its own launch
+   * and without re-reading the conv output.  With wgroups == 2, gn_gamma / gn_beta hold [2, K] like mkd_groupnorm's.
+   * act must be NONE, (K / gn_groups) % 8 == 0, pixels per image * K / gn_groups / 8 <= 512.  Only launches that split K carry
+   * it: mkd_conv2d_path() returns MKD_E_INVALID otherwise and the caller runs mkd_groupnorm after the conv. */
+  void* gn_y;
+  int gn_ld, gn_groups, gn_silu;
+  float gn_eps;
+  const float* gn_gamma;
+  const float* gn_beta;
 } mkd_conv_desc;
 
 int mkd_conv2d(const mkd_conv_desc* d, mkd_stream_t stream);

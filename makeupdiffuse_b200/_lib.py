@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmkd_b200.so")
 MKD_BF16, MKD_F32 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05, PATH_TCGEN05_SINGLE, PATH_TCGEN05_PAIR = 0, 1, 2, 3, 4
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class ConvDesc(C.Structure):
@@ -36,6 +36,8 @@ class ConvDesc(C.Structure):
         ("pad_hi_extra", C.c_int),
         ("x2", C.c_void_p), ("C2", C.c_int), ("ldx2", C.c_int),
         ("wgroups", C.c_int),
+        ("gn_y", C.c_void_p), ("gn_ld", C.c_int), ("gn_groups", C.c_int), ("gn_silu", C.c_int), ("gn_eps", C.c_float),
+        ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p),
     ]
 
 

@@ -217,6 +217,12 @@ static int validate(const mkd_conv_desc* d) {
   if (d->wgroups == 2)
     MKD_REQUIRE(d->dtype == MKD_BF16 && d->path != MKD_PATH_GENERIC && d->path != MKD_PATH_TCGEN05_SINGLE && d->N % 2 == 0, MKD_E_INVALID,
                 "conv2d: weight groups are bf16, even batch, tensor-core CTA-pair kernel only");
+  if (d->gn_y) {
+    MKD_REQUIRE(d->dtype == MKD_BF16 && d->act == MKD_ACT_NONE && d->gn_groups > 0 && d->K % d->gn_groups == 0 &&
+                    (d->K / d->gn_groups) % 8 == 0 && d->gn_gamma && d->gn_beta && d->gn_ld >= d->K && d->path != MKD_PATH_GENERIC &&
+                    d->path != MKD_PATH_TCGEN05_SINGLE && d->stride == 1 && !d->upsample && !d->stats,
+                MKD_E_INVALID, "conv2d: the GroupNorm tail is bf16, act NONE, whole vectors of 8 channels per group, stride 1, CTA-pair kernel only");
+  }
   if (d->act == MKD_ACT_GEGLU) {
     MKD_REQUIRE(d->K % 2 == 0 && d->geglu_block > 0 && (d->K / 2) % d->geglu_block == 0, MKD_E_INVALID,
                 "conv2d: GEGLU needs K even and K/2 %% geglu_block == 0");
@@ -235,7 +241,7 @@ extern "C" int mkd_conv2d_path(const mkd_conv_desc* d) {
   if (rc) return rc;
   if (d->path == MKD_PATH_GENERIC) return MKD_PATH_GENERIC;
   bool ok = mkd::conv2d_tcgen05_supported(d);
-  if ((d->x2 || d->wgroups == 2) && !ok) return MKD_E_INVALID;  // no other kernel takes the second term: the caller issues the two layers separately
+  if ((d->x2 || d->wgroups == 2 || d->gn_y) && !ok) return MKD_E_INVALID;  // no other kernel takes the second term: the caller issues the two layers separately
   if (d->path >= MKD_PATH_TCGEN05) {  // forced tensor-core kernel (either of the two)
     if (!ok) return MKD_E_INVALID;  // conv2d_tcgen05_supported() left the reason in mkd_last_error()
     return MKD_PATH_TCGEN05;

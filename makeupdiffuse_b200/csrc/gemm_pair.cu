@@ -1049,6 +1049,8 @@ bool plan(const mkd_conv_desc* d, PairPlan& pl, bool forced) {
   }
   pl.kb_per_split = (kblocks + pl.splits - 1) / pl.splits;
   pl.splits = (kblocks + pl.kb_per_split - 1) / pl.kb_per_split;
+  // GroupNorm tail (mkd_conv_desc.gn_y): rides in the split-K reducer, one block per (image, group), one vector of 8 channels per thread
+  if (d->gn_y && (pl.splits <= 1 || pl.geglu || (int64_t)pl.P * pl.Q * (d->K / d->gn_groups / 8) > 512)) return false;
   // shared memory: ring stages + panel slots
   const bool partial = pl.splits > 1;
   const bool any32 = partial || d->y32 || (d->residual && d->residual_dtype == MKD_F32);

@@ -965,6 +965,101 @@ __global__ void splitk_epilogue_kernel(EpiP ep, int splits) {
   }
 }
 
+// split-K reducer with a GroupNorm tail (mkd_conv_desc.gn_y): one block per (image, group); thread i owns row i / vpr of the image
+// and channels [8 (i % vpr), +8) of the group.  The reduced value gets the ordinary epilogue (stores y / y32), then the block
+// reduces (sum, sum of squares) in fp32 and every thread normalises the 8 values it still holds.
+struct GnTail {
+  bf16* y;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int ld, groups, silu;
+  int wsplit;  // images >= wsplit read the second gamma / beta set (weight groups), else INT_MAX
+};
+__global__ void __launch_bounds__(512) splitk_gn_kernel(EpiP ep, int splits, GnTail gn) {
+  pdl_wait();
+  __shared__ float red[2][32];
+  const int n = blockIdx.x / gn.groups, g = blockIdx.x - n * gn.groups;
+  const int cg = ep.n_rows / gn.groups, vpr = cg / 8;
+  const int items = ep.pix_per_img * vpr;
+  const int i = threadIdx.x;
+  const bool live = i < items;
+  const int row = live ? i / vpr : 0;
+  const int m = n * ep.pix_per_img + row, col = g * cg + (live ? i - row * vpr : 0) * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  float s = 0.f, ss = 0.f;
+  if (live) {
+    if (ep.bias && m >= ep.wg_row) ep.bias += ep.n_rows;  // second weight group (mkd_conv_desc.wgroups)
+    // same order of additions as splitk_epilogue_kernel (s = 0, 1, ...), loads of up to 8 splits in flight
+    for (int s0 = 0; s0 < splits; s0 += 8) {
+      float4 t[8][2];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (s0 + q < splits) {
+          const float4* p = reinterpret_cast<const float4*>(ep.partial + ((int64_t)(s0 + q) * ep.M + m) * ep.n_rows + col);
+          t[q][0] = p[0];
+          t[q][1] = p[1];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (s0 + q < splits) {
+          v[0] += t[q][0].x; v[1] += t[q][0].y; v[2] += t[q][0].z; v[3] += t[q][0].w;
+          v[4] += t[q][1].x; v[5] += t[q][1].y; v[6] += t[q][1].z; v[7] += t[q][1].w;
+        }
+      }
+    }
+    epilogue_vec8(ep, m, col, v);  // bias / emb / alpha / residual, y / y32 stores; v now holds the layer's output
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s += v[j];
+      ss += v[j] * v[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) {
+    red[0][warp] = s;
+    red[1][warp] = ss;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    s = lane < nw ? red[0][lane] : 0.f;
+    ss = lane < nw ? red[1][lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+      red[0][0] = s;
+      red[1][0] = ss;
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  const float cnt = (float)(ep.pix_per_img * cg);
+  const float mean = red[0][0] / cnt;
+  const float var = fmaxf(red[1][0] / cnt - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + gn.eps);
+  const int wo = n >= gn.wsplit ? ep.n_rows : 0;
+  float ga[8], be[8], r[8];
+  load8(gn.gamma + wo + col, ga);
+  load8(gn.beta + wo + col, be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float t = (v[j] - mean) * rstd * ga[j] + be[j];
+    r[j] = gn.silu ? silu_f(t) : t;
+  }
+  store8(gn.y + (int64_t)m * gn.ld + col, r);
+}
+
 // Nearest-neighbour x2 upsample, NHWC bf16, 8 channels per thread: out[n, 2h+dy, 2w+dx, :] = in[n, h, w, :].
 // (Upsample blocks: the 3x3 conv that follows then runs on the tensor cores like any other.)
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int ldx) {
@@ -1350,6 +1445,18 @@ int splitk_reduce(const mkd_conv_desc* d, int M, int pix_per_img, int splits, cu
   ep.partial = (float*)d->workspace;
   ep.stats = nullptr; ep.stats_ld = 0;
   ep.wg_row = d->wgroups == 2 ? M / 2 : 0x7fffffff;
+  if (d->gn_y) {  // GroupNorm tail: one block per (image, group), one vector of 8 channels per thread (gemm_pair.cu's plan checked the sizes)
+    GnTail gn;
+    gn.y = (bf16*)d->gn_y; gn.gamma = d->gn_gamma; gn.beta = d->gn_beta; gn.eps = d->gn_eps;
+    gn.ld = d->gn_ld; gn.groups = d->gn_groups; gn.silu = d->gn_silu;
+    const int images = M / pix_per_img;
+    gn.wsplit = d->wgroups == 2 ? images / 2 : 0x7fffffff;
+    const int items = pix_per_img * (d->K / d->gn_groups / 8);
+    MKD_REQUIRE(items <= 512 && M % pix_per_img == 0, MKD_E_INVALID, "splitk_reduce: GroupNorm tail needs <= 512 vectors per (image, group)");
+    MKD_LAUNCH_OK(launch_pdl(splitk_gn_kernel, dim3(images * d->gn_groups), dim3((items + 31) / 32 * 32), 0, stream, ep, splits, gn));
+    MKD_CHECK_LAUNCH();
+    return MKD_OK;
+  }
   int64_t total = (int64_t)M * (d->K / (d->act == MKD_ACT_GEGLU ? 16 : 8));
   int blocks = (int)((total + 127) / 128);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -1370,6 +1477,11 @@ bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
     set_error("conv2d: weight groups need the CTA-pair kernel, which declined this shape");
     return false;
   }
+  if (d->gn_y && !d->x2) {  // GroupNorm tail: rides in the CTA-pair kernel's split-K reducer or nowhere
+    if (d->path != MKD_PATH_TCGEN05_SINGLE && d->stride == 1 && !d->upsample && conv2d_pair_supported(d, d->path == MKD_PATH_TCGEN05_PAIR)) return true;
+    set_error("conv2d: the GroupNorm tail needs a split-K launch of the CTA-pair kernel, which this shape is not");
+    return false;
+  }
   if (d->x2) {  // second 1x1 term: the CTA-pair kernel or nothing
     if (d->path != MKD_PATH_TCGEN05_SINGLE && d->stride == 1 && !d->upsample && conv2d_pair_supported(d, d->path == MKD_PATH_TCGEN05_PAIR)) return true;
     set_error("conv2d: the x2 term needs the CTA-pair kernel, which declined this shape");
@@ -1388,7 +1500,7 @@ bool conv2d_tcgen05_supported(const mkd_conv_desc* d) {
 }
 
 int conv2d_tcgen05(const mkd_conv_desc* d_in, cudaStream_t stream) {
-  if (d_in->wgroups == 2 || d_in->x2 || pair_takes_strided(d_in)) return conv2d_pair(d_in, d_in->path == MKD_PATH_TCGEN05_PAIR, stream);
+  if (d_in->wgroups == 2 || d_in->x2 || d_in->gn_y || pair_takes_strided(d_in)) return conv2d_pair(d_in, d_in->path == MKD_PATH_TCGEN05_PAIR, stream);
   Geometry g;
   MKD_REQUIRE(geometry(d_in, g), MKD_E_INVALID, "gemm_tcgen05: unsupported shape");
   mkd_conv_desc dd;

@@ -94,6 +94,7 @@ class _Net(nn.Module):
         self._attn_res = tuple(attention_resolutions)
         self.fused_gn_stats = True  # False: always the two-phase GroupNorm (A/B runs)
         self.fuse_skip = True       # False: ResBlock skip projections always as their own GEMM (A/B runs)
+        self.fuse_gn_tail = True    # False: out_layers' GroupNorm always as its own launch (A/B runs)
         self._fuse_ok: dict = {}
         # bumped whenever context_kv() / hint_features() refill their (shared, static) arena buffers: a holder of earlier
         # results — B200ControlLDM's cond cache — compares epochs to learn that the buffers now hold another cond's data
@@ -347,9 +348,15 @@ class _Net(nn.Module):
         h_lo, h_hi = self._side("res_h", M, cout)
         h_st = self._stats("res_h", M, cout) if self._stats_ok(N, H, W) else None
         e = emb_all[:, self._emb_off[key]:self._emb_off[key] + cout]
-        self._conv(t1, key + ".c1", h_lo, N, H, W, R=3, emb=e, y32=h_hi, stats=h_st)
         t2 = self._buf("gn_b", M, cout)
-        self._gn(Act(h_lo, h_hi, h_st), t2, N, self.w[key + ".gn2.g"], self.w[key + ".gn2.b"], 1e-5, True)
+        gn2 = dict(y=t2, gamma=self.w[key + ".gn2.g"], beta=self.w[key + ".gn2.b"], eps=1e-5, silu=True)
+        if h_st is None and self._gn_tail_ok(key + ".c1", t1, h_lo, h_hi, e, N, H, W, gn2):
+            # deep levels: conv1 runs as split-K partials + reducer, and the reducer normalises what it has just summed — out_layers'
+            # GroupNorm + SiLU without a launch of its own (mkd_conv_desc.gn_y)
+            self._conv(t1, key + ".c1", h_lo, N, H, W, R=3, emb=e, y32=h_hi, gn=gn2)
+        else:
+            self._conv(t1, key + ".c1", h_lo, N, H, W, R=3, emb=e, y32=h_hi, stats=h_st)
+            self._gn(Act(h_lo, h_hi, h_st), t2, N, gn2["gamma"], gn2["beta"], 1e-5, True)
         if cin != cout and self._skip_fuses(key, t2, x.lo, y, N, H, W):
             # h = conv2(...) + skip_connection(x): the 1x1 projection rides as extra k-blocks of the 3x3 conv's GEMM
             self._conv(t2, key + ".c2sk", y.lo, N, H, W, R=3, x2=x.lo, y32=y.hi, stats=y.st)
@@ -361,6 +368,24 @@ class _Net(nn.Module):
         else:
             sk = x.src()
         self._conv(t2, key + ".c2", y.lo, N, H, W, R=3, residual=sk, y32=y.hi, stats=y.st)
+
+    def _gn_tail_ok(self, wkey, x, y_lo, y_hi, emb, N, H, W, gn):
+        """does this conv take the GroupNorm that follows it as a tail of its split-K reducer?  (bf16 path, launches the library
+        runs as split-K: the 8x8 / 4x4 levels at small batch; asked once per (layer, shape))"""
+        if not (self._hi and self.fuse_gn_tail):
+            return False
+        ck = ("gn_tail", wkey, N, H, W, y_lo is None, y_hi is None)
+        ok = self._fuse_ok.get(ck)
+        if ok is None:
+            w, b = self.w[wkey + ".w"], self.w.get(wkey + ".b")
+            kw = dict(H=H, W=W, R=3, S=3, pad=1, workspace=self._ws)
+            ok = ops.conv2d_supported(x, w, y_lo, N=N, bias=b, emb=emb, y32=y_hi, gn=gn, wgroups=self._wg, **kw)
+            if not ok and self._wg == 2:  # (declined as one grouped launch: ops.conv2d_grouped runs one launch per network)
+                half = lambda v: None if v is None else v[:v.shape[0] // 2]  # noqa: E731
+                ok = ops.conv2d_supported(half(x), half(w), half(y_lo), N=N // 2, bias=half(b), emb=half(emb), y32=half(y_hi),
+                                          gn=dict(gn, y=half(gn["y"]), gamma=half(gn["gamma"]), beta=half(gn["beta"])), **kw)
+            self._fuse_ok[ck] = ok
+        return ok
 
     def _skip_fuses(self, key, t2, x_lo, y, N, H, W):
         """can this ResBlock's out conv take its skip projection as a second term?  (bf16 path, CTA-pair kernel shapes;
@@ -840,7 +865,7 @@ class B200GroupedTrunk(_Net):
         self._emb_total = un._emb_total
         self._ws = torch.empty(_SPLITK_WS_BYTES // 4, dtype=torch.float32, device=self._device)
         un.row_groups = 2
-        self.fused_gn_stats, self.fuse_skip = un.fused_gn_stats, un.fuse_skip
+        self.fused_gn_stats, self.fuse_skip, self.fuse_gn_tail = un.fused_gn_stats, un.fuse_skip, un.fuse_gn_tail
         self._loaded = True
 
     def stack_x(self, x):
@@ -879,7 +904,7 @@ class B200GroupedTrunk(_Net):
         while this stream lays out x_t and runs the stacked conv_in; the first ResBlock waits for them.
         emb2: the stacked embeddings [2N, un._emb_total] when the caller already holds them (B200ControlLDM.set_step)."""
         un, cn = self.un, self.cn
-        self.fused_gn_stats, self.fuse_skip = un.fused_gn_stats, un.fuse_skip  # the A/B switches follow the UNet's
+        self.fused_gn_stats, self.fuse_skip, self.fuse_gn_tail = un.fused_gn_stats, un.fuse_skip, un.fuse_gn_tail  # A/B switches follow the UNet's
         ea2 = self._buf("emb_all2", 2 * N, un._emb_total) if emb2 is None else emb2
         emb_done = None
         if emb2 is not None:

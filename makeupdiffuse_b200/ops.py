@@ -197,9 +197,11 @@ def softmax_rows(x2d, y2d, scale=1.0):
 
 def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=False, bias=None, emb=None,
                    residual=None, alpha=1.0, act=L.ACT_NONE, geglu_block=0, path=L.PATH_AUTO, workspace=None,
-                   y32=None, stats=None, pad_hi_extra=0, x2=None, wgroups=1) -> L.ConvDesc:
+                   y32=None, stats=None, pad_hi_extra=0, x2=None, wgroups=1, gn=None) -> L.ConvDesc:
     """y2d: output in the activation dtype (or None); y32: optional fp32 copy of the same result.
-    x2: optional second input [N*H*W, C2] of a fused 1x1 term (mkd_conv_desc.x2): w is then [K, R*S*C + C2]."""
+    x2: optional second input [N*H*W, C2] of a fused 1x1 term (mkd_conv_desc.x2): w is then [K, R*S*C + C2].
+    gn: optional GroupNorm tail (mkd_conv_desc.gn_y): dict(y=, gamma=, beta=, eps=, silu=, groups=32) — the GroupNorm(+SiLU) of
+    the layer's output written to ``y`` by the split-K reducer; only launches that split K take it (conv2d_supported)."""
     px, ldx = _rows(x2d)
     Cc = x2d.shape[1]
     K = w.shape[0] // wgroups  # wgroups = 2: w holds the rows of two networks' layer, bias both biases (mkd_conv_desc.wgroups)
@@ -247,6 +249,13 @@ def make_conv_desc(x2d, w, y2d, *, N, H, W, R=1, S=1, stride=1, pad=0, upsample=
         d.x2, d.ldx2 = _rows(x2)
         d.C2 = C2
     d.wgroups = wgroups
+    if gn is not None:
+        gy, ga, be = gn["y"], gn["gamma"], gn["beta"]
+        assert gy.dtype == x2d.dtype and gy.shape[1] == K and ga.dtype == torch.float32 and be.dtype == torch.float32
+        assert ga.numel() == wgroups * K and be.numel() == wgroups * K and ga.is_contiguous() and be.is_contiguous()
+        d.gn_y, d.gn_ld = _rows(gy)
+        d.gn_gamma, d.gn_beta = ga.data_ptr(), be.data_ptr()
+        d.gn_eps, d.gn_silu, d.gn_groups = float(gn["eps"]), int(bool(gn["silu"])), int(gn.get("groups", 32))
     return d
 
 
@@ -292,6 +301,8 @@ def conv2d_grouped(x2d, w, y2d, *, N, **kw):
         k2["x2"] = part(kw.get("x2"), g, rows["x"])
         if kw.get("stats") is not None:
             k2["stats"] = part(kw["stats"], g, kw["stats"].shape[0] // 2)
+        if kw.get("gn") is not None:
+            k2["gn"] = dict(kw["gn"], y=part(kw["gn"]["y"], g, rows["out"]), gamma=part(kw["gn"]["gamma"], g, K), beta=part(kw["gn"]["beta"], g, K))
         conv2d(part(x2d, g, rows["x"]), w[g * K:(g + 1) * K], part(y2d, g, rows["out"]), N=N // 2, **k2)
 
 

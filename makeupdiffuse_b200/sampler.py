@@ -189,7 +189,7 @@ class B200DDIMSampler:
                # a graph holds raw pointers and the launch structure of the moment it was captured: reloaded weights
                # (new tensors), another stream layout or another GroupNorm path need a new capture
                getattr(m, "_weights_epoch", 0), getattr(m, "concurrent", None), getattr(m, "grouped", None), emb_selected,
-               tuple(getattr(n, "fused_gn_stats", None) for n in nets))
+               tuple((getattr(n, "fused_gn_stats", None), getattr(n, "fuse_gn_tail", None)) for n in nets))
         if g is None or g["key"] != key:
             sx, st = x.clone(), t.clone()
             self.model.apply_model(sx, st, c)  # warm-up: allocates every static buffer, fills the cond cache

@@ -451,3 +451,67 @@ def test_timestep_embedding_table(faked, pair, monkeypatch):
     n0 = n_te["n"]
     s.denoising_step(x, cond, torch.tensor([981, 981]), index=5)
     assert n_te["n"] == n0 + 2
+
+
+def test_groupnorm_tail_plumbing(faked, tiny_params, monkeypatch):
+    """out_layers' GroupNorm + SiLU as a tail of conv1's split-K reducer (mkd_conv_desc.gn_y): the kernel takes it only where it
+    splits K (yaml-size networks, deep levels), so the support query is forced here — this is about the host plumbing: conv1
+    carries gamma / beta / eps / SiLU and the destination, the separate GroupNorm call disappears, eps is unchanged, stacked
+    trunk and two-network form alike."""
+    o = OracleControlLDM(control_params=tiny_params, unet_params=tiny_params).eval()
+    sd = seeded_state_dict(o, 0)
+    cond, x = cond_x(2, 8, seed=17)
+    t = torch.tensor([981, 41])
+    m = B200ControlLDM(tiny_params, tiny_params, dtype=torch.bfloat16, device="cpu").load_state_dict(sd)
+    un, cn = m.model.diffusion_model, m.control_model
+    calls = {"gn": 0, "tail": 0}
+    real_gn, real_conv, real_grouped = fake_ops.groupnorm, fake_ops.conv2d, fake_ops.conv2d_grouped
+
+    def gn_spy(*a, **k):
+        calls["gn"] += 1
+        return real_gn(*a, **k)
+
+    def conv_spy(x2d, w, y2d, **kw):
+        if kw.get("gn") is not None:
+            calls["tail"] += 1
+            assert kw["gn"]["silu"] and kw["gn"]["eps"] == 1e-5 and kw["gn"]["y"].shape == (x2d.shape[0], w.shape[0])
+        return real_conv(x2d, w, y2d, **kw)
+
+    def grouped_spy(x2d, w, y2d, **kw):
+        if kw.get("gn") is not None:
+            calls["tail"] += 1
+            assert kw["gn"]["gamma"].numel() == w.shape[0]          # both networks' gamma, like the stacked weights
+        return real_grouped(x2d, w, y2d, **kw)
+
+    monkeypatch.setattr(ops, "groupnorm", gn_spy)
+    monkeypatch.setattr(ops, "conv2d", conv_spy)
+    monkeypatch.setattr(ops, "conv2d_grouped", grouped_spy)
+    un.fused_gn_stats = cn.fused_gn_stats = False                    # every GroupNorm is a plain launch: countable
+    with torch.no_grad():
+        ref = o.apply_model(x, t, cond)
+        for grouped in (False, True):
+            m.grouped = grouped
+            m.invalidate_cond_cache()
+            calls.update(gn=0, tail=0)
+            plain = m.apply_model(x, t, cond).clone()
+            n_gn = calls["gn"]
+            assert calls["tail"] == 0
+            monkeypatch.setattr(ops, "conv2d_supported", lambda *a, **k: k.get("gn") is not None)
+            for net in (un, cn) + ((m._grouped_trunk(),) if grouped else ()):
+                net._fuse_ok.clear()
+            calls.update(gn=0, tail=0)
+            fused = m.apply_model(x, t, cond)
+            n_res = len(un._res_layers()) + (0 if grouped else len(cn._res_layers()))   # stacked: one call covers both networks' layer
+            assert calls["tail"] == n_res and calls["gn"] == n_gn - n_res   # one GroupNorm call fewer per conv1 call
+            assert rel(fused, plain) < 1e-6 and rel(fused, ref) < 1.5e-2
+            monkeypatch.setattr(ops, "conv2d_supported", fake_ops.conv2d_supported)
+            for net in (un, cn) + ((m._grouped_trunk(),) if grouped else ()):
+                net._fuse_ok.clear()
+        un.fuse_gn_tail = False                                          # the A/B switch
+        monkeypatch.setattr(ops, "conv2d_supported", lambda *a, **k: k.get("gn") is not None)
+        un._fuse_ok.clear()
+        calls.update(gn=0, tail=0)
+        m.grouped = False
+        m.invalidate_cond_cache()
+        m.apply_model(x, t, cond)
+        assert calls["tail"] == len(cn._res_layers())

@@ -581,6 +581,65 @@ def test_conv_weight_groups(case):
         assert rel(st1, st0) < 1e-5
 
 
+GN_TAIL_CASES = [
+    dict(N=16, H=4, W=4, C=1280, K=1280, emb=True, y32="only"),                 # decoder ResBlock conv1 at the 4x4 level (9 splits)
+    dict(N=16, H=8, W=8, C=2560, K=1280, emb=True, y32="only"),                 # ... at the 8x8 level (2 splits), 64 x 5 vectors per block
+    dict(N=32, H=4, W=4, C=1280, K=1280, emb=True, y32="only", wgroups=2),      # stacked trunk: gamma / beta per network
+    dict(N=16, H=8, W=8, C=1280, K=1280, C2=2560, y32="both", silu=False, eps=1e-6),  # out conv + skip projection -> SpatialTransformer norm
+    dict(N=16, H=32, W=32, C=320, K=320, emb=True, y32="only", declined=True),   # no split-K at this level: the caller keeps its GroupNorm launch
+]
+
+
+@pytest.mark.parametrize("case", GN_TAIL_CASES)
+def test_conv_groupnorm_tail(case):
+    """mkd_conv_desc.gn_y: the split-K reducer also writes GroupNorm(+SiLU) of the layer's output == the conv followed by
+    mkd_groupnorm on its fp32 output; y / y32 unchanged; one launch fewer; shapes that do not split are declined"""
+    N, H, W, C, K = (case[k] for k in "NHWCK")
+    wg, C2 = case.get("wgroups", 1), case.get("C2", 0)
+    M = N * H * W
+    x = rnd(M, C, dt=BF, seed=1)
+    w = (rnd(wg * K, 9 * C + C2, seed=2) / math.sqrt(9 * C + C2)).to(BF)
+    b = 0.5 * rnd(wg * K, seed=3)
+    gamma, beta = 1.0 + 0.3 * rnd(wg * K, seed=7), 0.2 * rnd(wg * K, seed=8)
+    kw = dict(N=N, H=H, W=W, R=3, S=3, pad=1, bias=b, workspace=torch.empty(64 << 20, dtype=torch.uint8, device=DEV), wgroups=wg)
+    if case.get("emb"):
+        kw["emb"] = rnd(N, K, dt=BF, seed=4)
+    if C2:
+        kw["x2"] = rnd(M, C2, dt=BF, seed=5)
+    silu, eps = case.get("silu", True), case.get("eps", 1e-5)
+
+    def outs():
+        return (torch.zeros(M, K, device=DEV, dtype=BF) if case["y32"] == "both" else None), torch.zeros(M, K, device=DEV)
+    y, y32 = outs()
+    g = torch.zeros(M, K, device=DEV, dtype=BF)
+    gn = dict(y=g, gamma=gamma, beta=beta, eps=eps, silu=silu)
+    ok = ops.conv2d_supported(x, w, y, y32=y32, gn=gn, **kw)
+    assert ok == (not case.get("declined"))
+    if not ok:
+        with pytest.raises(RuntimeError):
+            ops.conv2d(x, w, y, y32=y32, gn=gn, **kw)
+        return
+    n0 = L.load().mkd_launch_count()
+    ops.conv2d(x, w, y, y32=y32, gn=gn, **kw)
+    fused_launches = L.load().mkd_launch_count() - n0
+    yr, y32r = outs()
+    gr = torch.zeros(M, K, device=DEV, dtype=BF)
+    n0 = L.load().mkd_launch_count()
+    ops.conv2d(x, w, yr, y32=y32r, **kw)
+    ops.groupnorm(y32r, gr, N, gamma, beta, eps, silu, torch.empty(ops.groupnorm_workspace_bytes(N), dtype=torch.uint8, device=DEV), wgroups=wg)
+    assert L.load().mkd_launch_count() - n0 > fused_launches == 2          # GEMM + reducer; the GroupNorm launch(es) are gone
+    assert torch.equal(y32, y32r) and (y is None or torch.equal(y, yr))    # the layer's own outputs: same sums in the same order
+    assert float(gr.float().abs().max()) > 0.5
+    assert rel(g, gr.float()) < 4e-3, rel(g, gr.float())                    # both round to bf16 once; statistics in fp32 either way
+    # against torch on the fp32 output
+    ref = torch.empty_like(y32r)
+    for p in range(wg):
+        rows = slice(p * M // wg, (p + 1) * M // wg)
+        t = F.group_norm(y32r[rows].reshape(N // wg, H * W, K).permute(0, 2, 1), 32, gamma[p * K:(p + 1) * K], beta[p * K:(p + 1) * K], eps)
+        ref[rows] = (F.silu(t) if silu else t).permute(0, 2, 1).reshape(-1, K)
+    assert rel(g, ref) < 4e-3, rel(g, ref)
+
+
 @pytest.mark.parametrize("N,HW,C", [(32, 1024, 320), (32, 256, 640), (32, 64, 1280), (32, 16, 2560), (4, 100, 128)])
 def test_norm_weight_groups(N, HW, C):
     """GroupNorm (all three kernels), GroupNorm-apply and LayerNorm with wgroups = 2 == the two halves with their own gamma / beta,
