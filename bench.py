@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--grouped", action="store_true",
                     help="A/B: force the stacked trunk where the default ('auto') would not pick it (levels whose rows per network are "
                          "not whole tile pairs then run one launch per network)")
+    ap.add_argument("--no-gn-tail", action="store_true", help="A/B: out_layers' GroupNorm always as its own launch (no mkd_conv_desc.gn_y)")
     ap.add_argument("--no-grouped", action="store_true",
                     help="A/B: UNet encoder and ControlNet trunk as two networks on two streams instead of one stacked network")
     ap.add_argument("--fused-gather", action="store_true",
@@ -251,6 +252,8 @@ def main():
 
     model = B200ControlLDM(dtype=torch.bfloat16, device=dev)
     model.load_state_dict(synthetic_state_dict(model, 0, dev))
+    if args.no_gn_tail:
+        model.model.diffusion_model.fuse_gn_tail = model.control_model.fuse_gn_tail = False
     if args.no_grouped or args.grouped:
         model.grouped = bool(args.grouped)
     args.stacked = bool(model._use_grouped(rows, h, h))

@@ -380,10 +380,8 @@ class _Net(nn.Module):
             w, b = self.w[wkey + ".w"], self.w.get(wkey + ".b")
             kw = dict(H=H, W=W, R=3, S=3, pad=1, workspace=self._ws)
             ok = ops.conv2d_supported(x, w, y_lo, N=N, bias=b, emb=emb, y32=y_hi, gn=gn, wgroups=self._wg, **kw)
-            if not ok and self._wg == 2:  # (declined as one grouped launch: ops.conv2d_grouped runs one launch per network)
-                half = lambda v: None if v is None else v[:v.shape[0] // 2]  # noqa: E731
-                ok = ops.conv2d_supported(half(x), half(w), half(y_lo), N=N // 2, bias=half(b), emb=half(emb), y32=half(y_hi),
-                                          gn=dict(gn, y=half(gn["y"]), gamma=half(gn["gamma"]), beta=half(gn["beta"])), **kw)
+            # (stacked trunk: only as ONE grouped launch — where that does not split K, two split-K launches per network with tails
+            #  would replace one grouped launch + one GroupNorm launch: measured slower at the 8x8 level)
             self._fuse_ok[ck] = ok
         return ok
 
