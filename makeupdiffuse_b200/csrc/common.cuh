@@ -112,8 +112,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel drains, then block in
 // griddepcontrol.wait until that kernel has completed and flushed.  One UNet+ControlNet step is ~500 dependent
 // launches of 5-50 us.  Rule that keeps it correct transitively: EVERY kernel waits, on every path, before it reads or
-// writes global memory.  Measured on B200 (bench.py, batch 16): 10.20 ms/step with PDL vs 9.94 ms without, so the
-// attribute is OFF by default (MKD_PDL=1 enables it); without it griddepcontrol.* are no-ops.
+// writes global memory.  ON by default since round 2 (6.97 -> 6.74 ms per step; it had measured slightly negative in round 1,
+// before the launch count fell and the GEMM prologues grew a cluster rendezvous); without the attribute griddepcontrol.* are no-ops.
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
