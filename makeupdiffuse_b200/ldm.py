@@ -50,7 +50,7 @@ class B200ControlLDM:
         self.sqrt_recip_alphas_cumprod = f32(np.sqrt(1.0 / ac))
         self.sqrt_recipm1_alphas_cumprod = f32(np.sqrt(1.0 / ac - 1))
         self._cond_cache = {}
-        self._weights_epoch = 0  # bumped by load_state_dict: captured CUDA graphs hold the old weight pointers
+        self._trunk_epoch = None
         # ControlNet trunk on a second stream, concurrent with the UNet encoder (set False to serialise: profiling, A/B runs)
         self.concurrent = True
         self._side = None
@@ -84,9 +84,14 @@ class B200ControlLDM:
         self.control_model.load_state_dict(cn, strict=strict, prefix="control_model.", device=self._device)
         self.model.diffusion_model.load_state_dict(un, strict=strict, prefix="model.diffusion_model.", device=self._device)
         self._cond_cache.clear()
-        self._weights_epoch += 1
-        self._trunk = None  # stacked copies of the trunk weights: rebuilt from the new ones on first use
         return self
+
+    @property
+    def _weights_epoch(self):
+        """changes whenever either network (re)loads weights — through this object or through the network's own load_state_dict
+        (INTEGRATION level 1).  Captured CUDA graphs hold the old weight pointers, the stacked trunk copies of them and the
+        timestep-embedding table values computed from them: all three are keyed on it."""
+        return (getattr(self.model.diffusion_model, "load_epoch", 0), getattr(self.control_model, "load_epoch", 0))
 
     # ---- timestep embeddings of a sampling loop ---------------------------------------------------------------------
     # emb = emb_layers(time_embed(timestep_embedding(t))) depends on t alone.  A DDIM loop knows its timesteps up front and
@@ -131,8 +136,10 @@ class B200ControlLDM:
         return self.dtype != torch.float32 and (N * (H // ds) * (W // ds)) % 256 == 0
 
     def _grouped_trunk(self):
-        if self._trunk is None:
+        if self._trunk is None or self._trunk_epoch != self._weights_epoch:  # stacked COPIES of the trunk weights: rebuilt after a reload
+            self._trunk = None
             self._trunk = B200GroupedTrunk(self.model.diffusion_model, self.control_model)
+            self._trunk_epoch = self._weights_epoch
         return self._trunk
 
     # ---- step-invariant conditioning ------------------------------------------------------------------------
@@ -160,7 +167,7 @@ class B200ControlLDM:
         un, cn = self.model.diffusion_model, self.control_model
         key = (tuple(self._tkey(t) for t in ctx_list), None if cat_list is None else tuple(self._tkey(t) for t in cat_list))
         hit = self._cond_cache.get("k")
-        if hit is not None and hit[0] == key and hit[4] == (un.arena_epoch, cn.arena_epoch):
+        if hit is not None and hit[0] == key and hit[4] == (un.arena_epoch, cn.arena_epoch) + self._weights_epoch:
             if grouped and "kv2" not in hit[1]:
                 self._stack_cond(hit[1])
             return hit[1]
@@ -173,7 +180,9 @@ class B200ControlLDM:
             if grouped:
                 self._stack_cond(prep)
         # keep the source tensors alive so data_ptr-based keys cannot be recycled
-        self._cond_cache["k"] = (key, prep, ctx_list, cat_list, (un.arena_epoch, cn.arena_epoch))
+        # (the weights epoch: K/V projections and hint features are functions of the weights too — a network reloaded through its
+        #  own load_state_dict must not be served the old ones)
+        self._cond_cache["k"] = (key, prep, ctx_list, cat_list, (un.arena_epoch, cn.arena_epoch) + self._weights_epoch)
         return prep
 
     # ---- diffmk/makeup_diffuse.py:152-170 ---------------------------------------------------------------------

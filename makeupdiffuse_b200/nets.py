@@ -198,6 +198,10 @@ class _Net(nn.Module):
                 raise KeyError(f"unexpected keys in state dict: {missing[:5]} ...")
         self._ws = torch.empty(_SPLITK_WS_BYTES // 4, dtype=torch.float32, device=self._device)
         self._loaded = True
+        self._fuse_ok.clear()
+        # every holder of something derived from these tensors — captured graphs (raw pointers), the stacked copies of
+        # B200GroupedTrunk, the timestep-embedding table — compares this counter (B200ControlLDM._weights_epoch)
+        self.load_epoch = getattr(self, "load_epoch", 0) + 1
         return self
 
     def _load_extra(self, g):

@@ -323,11 +323,37 @@ def test_cond_cache_with_inference_tensors_and_silent_refills(faked, pair):
         assert rel(g1, gr) < 5e-5
 
 
-def test_weights_epoch_enters_the_graph_key(pair):
+def test_weights_epoch_enters_the_graph_key(faked, pair):
     o, m = pair
     e0 = m._weights_epoch
-    m.load_state_dict(seeded_state_dict(o, 0))
-    assert m._weights_epoch == e0 + 1  # B200DDIMSampler._eps keys its captured graph on it (stale weight pointers otherwise)
+    sd = seeded_state_dict(o, 0)
+    m.load_state_dict(sd)
+    assert m._weights_epoch != e0  # B200DDIMSampler._eps keys its captured graph on it (stale weight pointers otherwise)
+    # a network reloaded through ITS OWN load_state_dict (INTEGRATION level 1) moves it too, and everything derived from the old
+    # weights — hoisted K/V and hint features, the stacked trunk copies, the timestep-embedding table — is rebuilt
+    cond, x = cond_x(2, 8, seed=23)
+    t = torch.tensor([601, 601])
+    m.grouped = True
+    try:
+        m.precompute_time_embeddings([601])
+        m.set_step(601, 2)
+        base = m.apply_model(x, t, cond).clone()
+        tr = m._grouped_trunk()
+        e1 = m._weights_epoch
+        cn_sd = {k: (v * 1.5 if k.endswith("input_blocks.1.0.in_layers.2.weight") or "attn2.to_k" in k or k.endswith("time_embed.2.weight") else v)
+                 for k, v in sd.items() if k.startswith("control_model.")}
+        m.control_model.load_state_dict(cn_sd, prefix="control_model.", device="cpu")
+        assert m._weights_epoch != e1
+        assert not m.set_step(601, 2)                      # the table was computed from the old time_embed weights
+        changed = m.apply_model(x, t, cond).clone()
+        assert m._grouped_trunk() is not tr and rel(changed, base) > 1e-3
+        m.grouped = False                                   # the two-network form reads the new weights directly: same result
+        m.invalidate_cond_cache()
+        assert rel(m.apply_model(x, t, cond), changed) < 1e-5
+    finally:
+        m.set_step(None)
+        m.grouped = "auto"
+        m.load_state_dict(sd)
 
 
 def test_non_power_of_two_maps_use_the_two_phase_groupnorm(faked, tiny_params):
@@ -404,7 +430,7 @@ def test_grouped_trunk_matches_two_networks(faked, tiny_params, monkeypatch, dty
     # reloading weights rebuilds the stacked copies
     tr = m._grouped_trunk()
     m.load_state_dict(sd)
-    assert m._trunk is None and m._grouped_trunk() is not tr
+    assert m._grouped_trunk() is not tr
 
 
 def test_timestep_embedding_table(faked, pair, monkeypatch):
