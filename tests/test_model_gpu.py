@@ -72,6 +72,33 @@ def test_apply_model_parity(tiny, B, h):
     assert rel(ref, ref0) > 0.1  # the ControlNet really contributes with the seeded non-zero init
 
 
+@pytest.mark.parametrize("B,h,w", [(2, 24, 24), (1, 24, 16)])
+def test_apply_model_parity_non_power_of_two_maps(tiny, B, h, w):
+    """latent maps that are not powers of two (192^2 / 192 x 128 images: 24 -> 12 -> 6 -> 3 pixels per side; rectangular too): the tensor-core 3x3
+    kernels decline them, so the convs run on the generic kernel, GroupNorm as the two-phase kernel (no fused statistics), attention
+    over token counts that are not multiples of the tile (576, 144, 36, 9) — same gates as the power-of-two sizes"""
+    g = torch.Generator(device=DEV).manual_seed(31)
+    cond = {"c_crossattn": [torch.randn(B, 77, 64, device=DEV, generator=g)],
+            "c_concat": [torch.rand(B, 6, 8 * h, 8 * w, device=DEV, generator=g)]}
+    x = torch.randn(B, 4, h, w, device=DEV, generator=g)
+    t = torch.tensor([801, 101][:B], device=DEV)
+    with torch.no_grad():
+        ref = tiny.oracle.apply_model(x, t, cond)
+    e32, e16 = tiny.f32.apply_model(x, t, cond), tiny.bf16.apply_model(x, t, cond)
+    print(f"tiny apply_model B={B} {h}x{w}: rel-L2 fp32-check {rel(e32, ref):.2e}  bf16 {rel(e16, ref):.2e}")
+    assert e32.shape == ref.shape
+    assert rel(e32, ref) < TOL_F32 and rel(e16, ref) < TOL_BF16_TINY
+    for m in (tiny.f32, tiny.bf16):                     # the stacked form through its per-network fallback: same launches, same bits
+        plain = m.apply_model(x, t, cond).clone()
+        try:
+            m.grouped = True
+            m.invalidate_cond_cache()
+            assert torch.equal(m.apply_model(x, t, cond), plain)
+        finally:
+            m.grouped = "auto"
+            m.invalidate_cond_cache()
+
+
 def test_grouped_trunk_forced(tiny):
     """UNet encoder + ControlNet trunk as one stacked network (B200GroupedTrunk).  At these sizes the grouped kernel declines
     every layer (no whole 256-row tile pairs per network), so each layer runs as one launch per network on the row halves —
