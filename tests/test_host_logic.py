@@ -541,3 +541,27 @@ def test_groupnorm_tail_plumbing(faked, tiny_params, monkeypatch):
         m.invalidate_cond_cache()
         m.apply_model(x, t, cond)
         assert calls["tail"] == len(cn._res_layers())
+
+
+def test_sampler_mask_x0_callbacks_and_intermediates(faked, pair):
+    """the inherited branches of upstream ddim_sampling the reference's sampler keeps: mask / x0 blending through q_sample (which
+    draws noise every step: the RNG stream has to stay in step with the oracle's), callback / img_callback arguments, log_every_t"""
+    o, m = pair
+    cond, x = cond_x(2, 8, seed=29)
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(2, 4, 8, 8, generator=g)
+    mask = (torch.rand(2, 1, 8, 8, generator=g) > 0.5).float()
+    seen = {"o": [], "m": []}
+    outs = {}
+    for name, s in (("o", MKDDIMSampler(o)), ("m", B200DDIMSampler(m))):
+        torch.manual_seed(7)
+        outs[name] = s.sample(5, 2, (4, 8, 8), cond, eta=0.3, x_T=x, mask=mask, x0=x0, verbose=False, log_every_t=2,
+                              callback=lambda i, n=name: seen[n].append(("cb", i)),
+                              img_callback=lambda p, i, n=name: seen[n].append(("img", i, tuple(p.shape))))
+    (a, ia), (b, ib) = outs["o"], outs["m"]
+    assert rel(b, a) < 1e-4 and seen["o"] == seen["m"] and len(seen["m"]) == 10
+    assert len(ia["x_inter"]) == len(ib["x_inter"]) and len(ia["pred_x0"]) == len(ib["pred_x0"])
+    for u, v in zip(ia["x_inter"] + ia["pred_x0"], ib["x_inter"] + ib["pred_x0"]):
+        assert rel(v, u) < 1e-4
+    # where the mask is 1 the last blend put q_sample(x0, t_last) there before the final update: both agree on that too
+    assert rel(b * mask, a * mask) < 1e-4
